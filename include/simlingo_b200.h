@@ -1,0 +1,121 @@
+/* simlingo_b200 - C ABI of the B200 (sm_100a) kernels behind the SimLingo / InternVL2-1B hot path.
+ *
+ * The reference has no native layer: every op below replaces a call the reference makes into
+ * PyTorch / transformers / flash-attn from simlingo_training/models (citations are
+ * /root/reference/<file>:<line>; UPSTREAM = HF-Hub InternVL2-1B remote code, look-alike copies
+ * in this image under vllm/model_executor/models/{intern_vit,internvl}.py and
+ * transformers/models/qwen2/modeling_qwen2.py).
+ *
+ * Conventions
+ *  - plain pointers + sizes, no C++/torch types; device pointers unless stated otherwise
+ *  - caller owns every buffer (incl. workspace); the library never allocates on the hot path
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit sync
+ *  - return 0 on success, negative on error; message via slb_last_error()
+ *  - tensors are row-major contiguous bf16 unless a leading dimension is given
+ */
+#ifndef SIMLINGO_B200_H_
+#define SIMLINGO_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int slb_version(void);
+const char* slb_last_error(void);
+int slb_num_sms(void);
+
+/* ---- GEMM: out = epilogue(alpha * A B^T) -------------------------------------------------------
+ * Replaces every nn.Linear / F.linear on the path: ViT qkv/proj/fc1/fc2 (UPSTREAM
+ * intern_vit.py:237-247,279-284), mlp1 (internvl.py:644-655), Qwen2 q/k/v/o/gate/up/down and
+ * lm_head (modeling_qwen2.py:35-48,161-204; llm.py:227), LoRA A/B (llm.py:106-118), patch-embed
+ * Conv2d as implicit GEMM after slb_im2col_patch (intern_vit.py:59-64), and their backward
+ * (dgrad/wgrad via the transposed-operand flags).
+ * epilogue: v = alpha*acc; v += bias[n]; v = act(v); v *= scale_n[n]; v += residual[m,n]
+ * swiglu:   B holds gate/up interleaved in groups of 128 rows; out[m, j] = silu(g_j) * u_j, N/2 cols */
+enum { SLB_ACT_NONE = 0, SLB_ACT_GELU = 1, SLB_ACT_SILU = 2, SLB_ACT_RELU = 3 };
+typedef struct {
+  int32_t M, N, K;
+  const void* A;   int64_t lda;   /* bf16 [M,K] (a_t=0) or [K,M] (a_t=1), row-major, ld in elements */
+  const void* B;   int64_t ldb;   /* bf16 [N,K] (b_t=0) or [K,N] (b_t=1) */
+  void* out;       int64_t ldo;   /* bf16 or fp32 [M, N] ([M, N/2] for swiglu) */
+  const void* bias;               /* bf16 [N] or NULL */
+  const void* scale_n;            /* bf16 [N] or NULL */
+  const void* residual; int64_t ldr; /* same dtype as out, or NULL */
+  float alpha;
+  int32_t act;
+  int32_t swiglu;
+  int32_t out_fp32;
+  int32_t a_t, b_t;
+  int32_t block_n;                /* 0 = auto, else 128 or 256 */
+} slb_gemm_args;
+int slb_gemm_bf16(const slb_gemm_args* args, void* stream);
+
+/* ---- norms ------------------------------------------------------------------------------------
+ * nn.LayerNorm(1024, eps 1e-6) x2 per ViT layer (intern_vit.py:341-350); Qwen2RMSNorm
+ * (modeling_qwen2.py:258-263).  mean/rstd (fp32 [rows]) are optional outputs for backward. */
+int slb_layernorm_fwd(const void* x, const void* w, const void* b, void* y, int rows, int cols, float eps,
+                      float* mean, float* rstd, void* stream);
+int slb_rmsnorm_fwd(const void* x, const void* w, void* y, int rows, int cols, float eps, float* rstd, void* stream);
+/* ---- ViT embeddings (UPSTREAM InternVisionEmbeddings, intern_vit.py:103-115) ---------------------
+ * im2col: pixels [T,3,448,448] -> patches [T*1024, kpad] (k = c*196 + py*14 + px, zero padded);
+ * assemble: x[t,0] = cls + pos[0]; x[t,1+p] = patch_out[t*1024+p] + pos[1+p] */
+int slb_im2col_patch(const void* pixels, void* patches, int tiles, int kpad, void* stream);
+int slb_vit_assemble(const void* patch_out, const void* cls, const void* pos, void* x, int tiles, void* stream);
+/* ---- projector front: drop CLS + pixel_shuffle(0.5, v2) + LayerNorm(4096) fused
+ * (UPSTREAM extract_feature / pixel_shuffle, internvl.py:657-684; closed form SURVEY 8a note 8) */
+int slb_pixel_shuffle_ln(const void* x, const void* w, const void* b, void* y, int tiles, float eps, float* mean,
+                         float* rstd, void* stream);
+/* ---- attention ---------------------------------------------------------------------------------
+ * ViT: bidirectional MHA, 16 heads x 64, packed qkv [T*n, 3*1024] -> out [T*n, 1024]
+ * (intern_vit.py:237-247; replaces flash_attn_varlen_qkvpacked_func).  lse (fp32 [T,16,n]) optional. */
+int slb_attn_vit_fwd(const void* qkv, void* out, float* lse, int tiles, int n_tokens, int heads, void* stream);
+/* LLM: causal GQA (14 q heads / 2 kv heads x 64) over a KV cache (modeling_qwen2.py:161-204,
+ * replaces flash_attention_2).  q [B, Lq, Hq*64] (row stride ldq), cache k/v [B, Hkv, Lmax, 64];
+ * query i of the chunk sits at absolute position past+i and sees keys j <= past+i with
+ * key_valid[b*key_valid_ld + j] != 0 (key_valid may be NULL).  out [B, Lq, Hq*64]. */
+int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
+                     int key_valid_ld, void* out, float* lse, int batch, int lq, int past, int lmax, int hq, int hkv,
+                     void* stream);
+
+/* ---- RoPE + KV-cache write (modeling_qwen2.py:102-146 rotate_half convention, theta 1e6) --------
+ * qkv [B*Lq, (Hq+2Hkv)*64] from the fused QKV GEMM; rotates q in place, writes rotated k and v
+ * into the caches at positions past..past+Lq-1 (positions are arange over the padded sequence). */
+int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, int lmax, int hq, int hkv,
+                      float theta, void* stream);
+/* ---- embeddings / placeholder substitution (adaptors.py:256; internvl2_model.py:54-91,119-131) --
+ * out[b,l] = table[clamp(ids[b,l],0,V-1)]; rows with ids == img_id take vit[b*n_img + rank] where
+ * rank counts <IMG_CONTEXT> ids before l; rows l in [wp_start[b], wp_start[b]+wp_len) take wp[b, l-wp_start[b]]. */
+int slb_embed_assemble(const int64_t* ids, const void* table, const void* vit, const void* wp, const int32_t* wp_start,
+                       int wp_len, void* out, int batch, int len, int hidden, int vocab, int img_id, int n_img,
+                       void* stream);
+int slb_gather_rows(const void* src, const int64_t* idx, void* dst, int n, int cols, int64_t src_rows, void* stream);
+
+/* ---- elementwise helpers ---- */
+int slb_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);
+int slb_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+int slb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+/* ---- LM head tail: argmax over fp32 logits (llm.py:157-158) ---- */
+int slb_argmax_f32(const float* logits, int64_t ld, int rows, int cols, int64_t* out_idx, float* out_margin,
+                   void* stream);
+/* fused softmax cross-entropy over fp32 logits rows: loss[r] = lse - logit[label]; dlogits optional (bf16) */
+/* ---- driving heads (adaptors.py:113-115,130-132,163-180) and wp encoder (adaptors.py:64-93) ----
+ * feats [B,30,896] -> route [B,20,2] (896->512->256->2 SiLU, cumsum), speed [B,10,2] (896->256->2), fp32 out */
+typedef struct {
+  const void *r0w, *r0b, *r2w, *r2b, *r4w; /* route_head.{0,2,4} */
+  const void *s0w, *s0b, *s2w;             /* speed_wps_head.{0,2} */
+} slb_heads_weights;
+int slb_driving_heads(const void* feats, int64_t ld_batch, const slb_heads_weights* w, float* route, float* speed,
+                      float* delta_ws /* fp32 [B,30,2] scratch */, int batch, void* stream);
+typedef struct { const void *w0, *b0, *w2, *b2, *w4, *b4; } slb_wp_weights;
+int slb_wp_encoder(const float* coords, const slb_wp_weights* w, void* out, int n_points, void* stream);
+
+/* ---- fused multi-tensor AdamW with global-norm clip (driving.py:718-724; train.py:206) ----------
+ * flat fp32 master params / moments, bf16 gradient (flat), bf16 model copy written back. */
+/* ---- data-parallel gradient exchange (Lightning DDP / ZeRO-2 in the reference, train.py:160-168) --
+ * NCCL communicator handled as an opaque pointer; unique id is a 128-byte blob exchanged by the host. */
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMLINGO_B200_H_ */

@@ -1,0 +1,381 @@
+// Flash-style attention for sm_100a.
+//   attn_fwd_kernel: one CTA per (128-query block, head, batch).  S = Q K^T and O_j = P V_j run on tcgen05
+//   (accumulators in TMEM), K/V tiles stream through a 2-stage TMA ring, online softmax in registers of four
+//   softmax warps (thread <-> query row <-> TMEM lane).  Two CTAs are co-resident per SM (112 KB smem,
+//   256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+//   Serves both the bidirectional InternViT attention (packed qkv, N=1025, 16 heads) and the causal GQA
+//   Qwen2 prefill (14 q heads / 2 kv heads over the KV cache, key-padding mask).
+//   attn_small_kernel: decode / 30-query append (Lq <= 32): CUDA-core kernel, one block per (b, head, query).
+#include "common.cuh"
+#include "../../include/simlingo_b200.h"
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128, HD = 64;
+constexpr int ATT_THREADS = 192;
+constexpr int kQBytes = BQ * HD * 2;        // 16 KB
+constexpr int kKVBytes = BKV * HD * 2;      // 16 KB
+constexpr int kPBytes = BQ * BKV * 2;       // 32 KB (two K-major halves of 64 columns)
+constexpr int kSmemQ = 0;
+constexpr int kSmemK = kSmemQ + kQBytes;            // 2 stages
+constexpr int kSmemV = kSmemK + 2 * kKVBytes;       // 2 stages
+constexpr int kSmemP = kSmemV + 2 * kKVBytes;
+constexpr int kSmemBar = kSmemP + kPBytes;
+constexpr int kSmemTotal = kSmemBar + 128;
+constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)
+
+struct AttnParams {
+  int lq, lkv;           // valid query rows per batch item, valid keys per batch item
+  int past;              // absolute position of query row 0 (causal offset)
+  int causal;
+  int hq, group;         // q heads, q heads per kv head
+  int q_col0, k_col0, v_col0;
+  int kv_head_col_stride, kv_batch_stride, kv_head_batch_stride;
+  const uint8_t* key_valid;  // [B, key_valid_ld] or null
+  int key_valid_ld;
+  bf16* out; long long ldo;  // out[(b*lq + i) * ldo + h*64 + d]
+  float* lse;                // [B, hq, lq] or null
+  float scale_log2;          // softmax scale * log2(e)
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * BQ;
+  const int hk = h / p.group;
+  // number of kv blocks this q block needs
+  int kv_end = p.lkv;
+  if (p.causal) kv_end = min(kv_end, p.past + q0 + BQ);
+  const int nkv = (kv_end + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023) != 0) __trap();
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kQBytes);
+      tma_load_3d(smem + kSmemQ, &tmap_q, q_full, p.q_col0 + h * HD, q0, b);
+      const int kc = p.k_col0 + hk * p.kv_head_col_stride, vc = p.v_col0 + hk * p.kv_head_col_stride;
+      const int kb = b * p.kv_batch_stride + hk * p.kv_head_batch_stride;
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * kKVBytes);
+        tma_load_3d(smem + kSmemK + s * kKVBytes, &tmap_k, &kv_full[s], kc, j * BKV, kb);
+        tma_load_3d(smem + kSmemV + s * kKVBytes, &tmap_v, &kv_full[s], vc, j * BKV, kb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major (d contiguous)
+      const uint32_t sq = smem_u32(smem + kSmemQ), sp = smem_u32(smem + kSmemP);
+      const uint64_t dq = umma_desc_kmajor_sw128(sq);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(smem + kSmemK + s * kKVBytes));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      if (nkv > 0) issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(smem + kSmemV + s * kKVBytes), kKVBytes);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t dp = umma_desc_kmajor_sw128(sp + (k >> 2) * (BQ * 128)) + 2 * (k & 3);
+          tc_mma_bf16(tmem_o, dp, dv + (uint64_t)k * (16 * 128 >> 4), idesc_o, k != 0);
+        }
+        tc_commit(o_full);
+        tc_commit(&kv_empty[s]);
+        if (j + 1 < nkv) issue_s(j + 1);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread <-> query row ----------------
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;            // row within the q block
+    const int row = q0 + r;                    // query index within the batch item
+    const int qpos = p.past + row;             // absolute position (causal)
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)b * p.key_valid_ld : nullptr;
+    float o_acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = smem + kSmemP + r * 128;
+    const int rsw = r & 7;
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int col_base = j * BKV;
+      const bool need_mask = (col_base + BKV > p.lkv) || (p.causal && col_base + BKV - 1 > p.past + q0) || kvalid;
+      // pass 1: row max
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t sr[32];
+        tmem_ld_32x32(tmem_s + lane_off + c, sr);
+        tmem_ld_wait();
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = col_base + c + i;
+            bool ok = col < p.lkv && (!p.causal || col <= qpos);
+            if (ok && kvalid) ok = kvalid[col] != 0;
+            if (ok) m_blk = fmaxf(m_blk, __uint_as_float(sr[i]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(sr[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, m_blk);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f((m_run - m_use) * p.scale_log2);  // m_run = -inf -> 0
+      const float moff = m_use * p.scale_log2;
+      float l_blk = 0.f;
+      // pass 2: p = exp2(s*scale - m*scale) -> bf16 -> smem (K-major, 128B swizzle)
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t sr[32];
+        tmem_ld_32x32(tmem_s + lane_off + c, sr);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = exp2f(__uint_as_float(sr[i]) * p.scale_log2 - moff);
+          if (need_mask) {
+            const int col = col_base + c + i;
+            bool ok = col < p.lkv && (!p.causal || col <= qpos);
+            if (ok && kvalid) ok = kvalid[col] != 0;
+            e = ok ? e : 0.f;
+          }
+          pv[i] = e;
+        }
+        // round to bf16 first so the row sum matches what the PV MMA sees
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+          float2 back = unpack_bf16(pk[i]);
+          l_blk += back.x + back.y;
+        }
+        uint8_t* half = prow + (c >> 6) * (BQ * 128);
+        const int chunk0 = (c & 63) >> 3;  // 16-byte chunk index of column c within the 64-column half
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 u = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(half + (((chunk0 + q4) ^ rsw) << 4)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      // O_j from TMEM
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t orr[32];
+        tmem_ld_32x32(tmem_o + lane_off + c, orr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c + i] = o_acc[c + i] * alpha + __uint_as_float(orr[i]);
+      }
+      tc_fence_before();
+    }
+    if (row < p.lq) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      bf16* o = p.out + ((size_t)b * p.lq + row) * p.ldo + h * HD;
+#pragma unroll
+      for (int d = 0; d < HD; d += 8) {
+        uint4 u;
+        u.x = pack_bf16(o_acc[d] * inv, o_acc[d + 1] * inv);
+        u.y = pack_bf16(o_acc[d + 2] * inv, o_acc[d + 3] * inv);
+        u.z = pack_bf16(o_acc[d + 4] * inv, o_acc[d + 5] * inv);
+        u.w = pack_bf16(o_acc[d + 6] * inv, o_acc[d + 7] * inv);
+        *reinterpret_cast<uint4*>(o + d) = u;
+      }
+      if (p.lse) {
+        const float mm = (m_run == -INFINITY) ? 0.f : m_run;
+        p.lse[((size_t)b * p.hq + h) * p.lq + row] = (l_run > 0.f) ? (mm * p.scale_log2 + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small-Lq attention (decode / query append): block per (query, head, batch), 128 threads
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+                  const uint8_t* __restrict__ key_valid, int key_valid_ld, bf16* __restrict__ out, long long ldo, int lq, int past,
+                  int lmax, int hq, int hkv, float scale) {
+  extern __shared__ float sm[];
+  float* qs = sm;            // 64
+  float* red = sm + 64;      // 8 + 128
+  float* sc = sm + 64 + 136; // lmax
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (hq / hkv);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nkeys = past + i + 1;
+  const bf16* qr = q + ((size_t)b * lq + i) * ldq + h * 64;
+  if (tid < 64) qs[tid] = __bfloat162float(qr[tid]) * scale;
+  __syncthreads();
+  const bf16* kbase = kc + ((size_t)b * hkv + hk) * lmax * 64;
+  const bf16* vbase = vc + ((size_t)b * hkv + hk) * lmax * 64;
+  const uint8_t* kv_ok = key_valid ? key_valid + (size_t)b * key_valid_ld : nullptr;
+  float mx = -INFINITY;
+  for (int j = tid; j < nkeys; j += 128) {
+    float s = -INFINITY;
+    if (!kv_ok || kv_ok[j]) {
+      s = 0.f;
+      const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)j * 64);
+#pragma unroll
+      for (int v8 = 0; v8 < 8; ++v8) {
+        uint4 u = kr[v8];
+        float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        const float* qq = qs + v8 * 8;
+        s += a.x * qq[0] + a.y * qq[1] + bb.x * qq[2] + bb.y * qq[3] + c.x * qq[4] + c.y * qq[5] + d.x * qq[6] + d.y * qq[7];
+      }
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  if (mx == -INFINITY) mx = 0.f;
+  float sum = 0.f;
+  for (int j = tid; j < nkeys; j += 128) {
+    const float e = __expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[4 + warp] = sum;
+  __syncthreads();
+  sum = red[4] + red[5] + red[6] + red[7];
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  const int d = tid & 63, part = tid >> 6;
+  float acc = 0.f;
+  for (int j = part; j < nkeys; j += 2) acc += sc[j] * __bfloat162float(vbase[(size_t)j * 64 + d]);
+  red[8 + tid] = acc;
+  __syncthreads();
+  if (tid < 64) out[((size_t)b * lq + i) * ldo + h * 64 + tid] = __float2bfloat16((red[8 + tid] + red[8 + 64 + tid]) * inv);
+}
+
+int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int batch,
+                cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.lq, BQ), p.hq, batch);
+  attn_fwd_kernel<<<grid, ATT_THREADS, kSmemTotal, stream>>>(tq, tk, tv, p);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+}  // namespace
+
+extern "C" int slb_attn_vit_fwd(const void* qkv, void* out, float* lse, int tiles, int n_tokens, int heads, void* stream) {
+  SLB_CHECK_ARG(tiles > 0 && n_tokens > 0 && heads > 0, "attn_vit: bad shape");
+  const int C = heads * HD;
+  CUtensorMap tm;
+  int rc = slb_make_tmap_3d(&tm, qkv, (uint64_t)3 * C, (uint64_t)n_tokens, (uint64_t)tiles, (uint64_t)3 * C * 2,
+                            (uint64_t)n_tokens * 3 * C * 2, HD, BQ, 1);
+  if (rc) return rc;
+  AttnParams p{};
+  p.lq = n_tokens; p.lkv = n_tokens; p.past = 0; p.causal = 0;
+  p.hq = heads; p.group = 1;
+  p.q_col0 = 0; p.k_col0 = C; p.v_col0 = 2 * C;
+  p.kv_head_col_stride = HD; p.kv_batch_stride = 1; p.kv_head_batch_stride = 0;
+  p.key_valid = nullptr; p.key_valid_ld = 0;
+  p.out = (bf16*)out; p.ldo = C; p.lse = lse;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  return launch_attn(tm, tm, tm, p, tiles, (cudaStream_t)stream);
+}
+
+extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
+                                int key_valid_ld, void* out, float* lse, int batch, int lq, int past, int lmax, int hq, int hkv,
+                                void* stream) {
+  SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax && hq % hkv == 0, "attn_gqa: bad shape");
+  SLB_CHECK_ARG((ldq % 8) == 0, "attn_gqa: ldq must be a multiple of 8");
+  const float scale = 0.125f;
+  if (lq <= 32 && lse == nullptr) {
+    dim3 grid(lq, hq, batch);
+    const size_t smem = (64 + 136 + (size_t)lmax) * sizeof(float);
+    SLB_CHECK_ARG(smem <= 48 * 1024, "attn_gqa: lmax=%d too long for the small-Lq kernel", lmax);
+    attn_small_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const bf16*)q, ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid,
+                                                               key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq, hkv, scale);
+    SLB_LAUNCH_CHECK();
+    return SLB_OK;
+  }
+  CUtensorMap tq, tk, tv;
+  int rc = slb_make_tmap_3d(&tq, q, (uint64_t)ldq, (uint64_t)lq, (uint64_t)batch, (uint64_t)ldq * 2, (uint64_t)lq * ldq * 2, HD, BQ, 1);
+  if (rc) return rc;
+  rc = slb_make_tmap_3d(&tk, kcache, HD, (uint64_t)lmax, (uint64_t)batch * hkv, HD * 2, (uint64_t)lmax * HD * 2, HD, BKV, 1);
+  if (rc) return rc;
+  rc = slb_make_tmap_3d(&tv, vcache, HD, (uint64_t)lmax, (uint64_t)batch * hkv, HD * 2, (uint64_t)lmax * HD * 2, HD, BKV, 1);
+  if (rc) return rc;
+  AttnParams p{};
+  p.lq = lq; p.lkv = past + lq; p.past = past; p.causal = 1;
+  p.hq = hq; p.group = hq / hkv;
+  p.q_col0 = 0; p.k_col0 = 0; p.v_col0 = 0;
+  p.kv_head_col_stride = 0; p.kv_batch_stride = hkv; p.kv_head_batch_stride = 1;
+  p.key_valid = key_valid; p.key_valid_ld = key_valid_ld;
+  p.out = (bf16*)out; p.ldo = (long long)hq * HD; p.lse = lse;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  return launch_attn(tq, tk, tv, p, batch, (cudaStream_t)stream);
+}

@@ -1,0 +1,555 @@
+// HBM-bound kernels of the path: LayerNorm / RMSNorm, ViT embedding glue, pixel-shuffle+LN, RoPE + KV-cache
+// write, embedding gather / placeholder substitution, argmax, small fused MLP heads.  All are vectorised
+// (128-bit loads/stores), warp-shuffle reduced, one warp per row where a row reduction is needed.
+#include "common.cuh"
+#include "../../include/simlingo_b200.h"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm forward: one warp per row, row kept in registers (MAXV 8-wide vectors per lane)
+// ------------------------------------------------------------------------------------------------
+template <int MAXV, bool RMS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+norm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b, bf16* __restrict__ y,
+                int rows, int cols, float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = cols >> 3;
+  const bf16* xr = x + (size_t)row * cols;
+  float v[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int vi = lane + 32 * j;
+    if (vi < nvec) {
+      load8(xr + vi * 8, v[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += RMS ? v[j][e] * v[j][e] : v[j][e];
+    }
+  }
+  s = warp_sum(s);
+  float mean = 0.f, rstd;
+  if (RMS) {
+    rstd = rsqrtf(s / cols + eps);
+  } else {
+    mean = s / cols;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int vi = lane + 32 * j;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { float d = v[j][e] - mean; q += d * d; }
+      }
+    }
+    q = warp_sum(q);
+    rstd = rsqrtf(q / cols + eps);
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  bf16* yr = y + (size_t)row * cols;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int vi = lane + 32 * j;
+    if (vi < nvec) {
+      float wv[8], o[8];
+      load8(w + vi * 8, wv);
+      if (RMS) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = v[j][e] * rstd * wv[e];
+      } else {
+        float bv[8];
+        load8(b + vi * 8, bv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * wv[e] + bv[e];
+      }
+      store8(yr + vi * 8, o);
+    }
+  }
+}
+
+// drop CLS + pixel_shuffle(0.5,'v2') + LayerNorm(4096): out row (t, i, j) gathers the 2x2 block of
+// patch tokens [(2i,2j),(2i,2j+1),(2i+1,2j),(2i+1,2j+1)] channel-concatenated.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+pixel_shuffle_ln_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                        bf16* __restrict__ y, int tiles, float eps, float* __restrict__ mean_out,
+                        float* __restrict__ rstd_out) {
+  constexpr int C = 1024, G = 32, G2 = 16, NT = 1025, COLS = 4096, MAXV = 16;
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= tiles * G2 * G2) return;
+  const int t = row / (G2 * G2), ij = row % (G2 * G2), i = ij / G2, j = ij % G2;
+  float v[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < MAXV; ++jj) {
+    const int vi = lane + 32 * jj;       // 0..511
+    const int q = vi >> 7, within = vi & 127;
+    const int src_tok = (2 * i + (q >> 1)) * G + (2 * j + (q & 1));
+    load8(x + ((size_t)t * NT + 1 + src_tok) * C + within * 8, v[jj]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[jj][e];
+  }
+  s = warp_sum(s);
+  const float mean = s / COLS;
+  float qv = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < MAXV; ++jj)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { float d = v[jj][e] - mean; qv += d * d; }
+  qv = warp_sum(qv);
+  const float rstd = rsqrtf(qv / COLS + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  bf16* yr = y + (size_t)row * COLS;
+#pragma unroll
+  for (int jj = 0; jj < MAXV; ++jj) {
+    const int vi = lane + 32 * jj;
+    float wv[8], bv[8], o[8];
+    load8(w + vi * 8, wv);
+    load8(b + vi * 8, bv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (v[jj][e] - mean) * rstd * wv[e] + bv[e];
+    store8(yr + vi * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT embedding glue
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_patch_kernel(const bf16* __restrict__ px, bf16* __restrict__ out, int tiles, int kpad) {
+  // one thread per 2 output elements (k even): out[(t*1024 + py*32 + pxx), k], k = c*196 + ky*14 + kx
+  const size_t total = (size_t)tiles * 1024 * (kpad / 2);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % (kpad / 2)) * 2;
+    const size_t rowi = idx / (kpad / 2);
+    const int p = (int)(rowi % 1024), t = (int)(rowi / 1024);
+    const int py = p >> 5, pxx = p & 31;
+    float v0 = 0.f, v1 = 0.f;
+    if (kk < 588) {
+      // kk even and 14 even => kk and kk+1 are in the same kernel row
+      const int c = kk / 196, r = kk % 196, ky = r / 14, kx = r % 14;
+      const bf16* src = px + (((size_t)t * 3 + c) * 448 + (py * 14 + ky)) * 448 + pxx * 14 + kx;
+      bf162 two = *reinterpret_cast<const bf162*>(src);
+      v0 = __bfloat162float(two.x);
+      v1 = __bfloat162float(two.y);
+    }
+    *reinterpret_cast<uint32_t*>(out + rowi * kpad + kk) = pack_bf16(v0, v1);
+  }
+}
+
+__global__ void vit_assemble_kernel(const bf16* __restrict__ patch_out, const bf16* __restrict__ cls,
+                                    const bf16* __restrict__ pos, bf16* __restrict__ x, int tiles) {
+  constexpr int C = 1024, NT = 1025, VPR = C / 8;
+  const size_t total = (size_t)tiles * NT * VPR;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int vi = (int)(idx % VPR);
+    const size_t r = idx / VPR;
+    const int tok = (int)(r % NT), t = (int)(r / NT);
+    float a[8], pz[8], o[8];
+    if (tok == 0) load8(cls + vi * 8, a);
+    else load8(patch_out + ((size_t)t * 1024 + tok - 1) * C + vi * 8, a);
+    load8(pos + (size_t)tok * C + vi * 8, pz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = a[e] + pz[e];
+    store8(x + r * C + vi * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE (rotate_half convention) on q and k + KV-cache write.  One thread per (row, head, d<32).
+// ------------------------------------------------------------------------------------------------
+__global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, int batch, int lq,
+                                     int past, int lmax, int hq, int hkv, float log2_theta) {
+  const int heads = hq + 2 * hkv;
+  const size_t total = (size_t)batch * lq * heads * 32;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(idx & 31);
+    const int h = (int)((idx >> 5) % heads);
+    const size_t row = (idx >> 5) / heads;  // b*lq + i
+    const int i = (int)(row % lq), b = (int)(row / lq);
+    bf16* src = qkv + row * (size_t)(heads * 64) + h * 64;
+    const float x0 = __bfloat162float(src[d]), x1 = __bfloat162float(src[d + 32]);
+    if (h < hq + hkv) {
+      const float inv_freq = exp2f(-(float)(2 * d) / 64.0f * log2_theta);
+      float sn, cs;
+      sincosf((float)(past + i) * inv_freq, &sn, &cs);
+      const float o0 = x0 * cs - x1 * sn, o1 = x1 * cs + x0 * sn;
+      if (h < hq) {
+        src[d] = __float2bfloat16(o0);
+        src[d + 32] = __float2bfloat16(o1);
+      } else {
+        bf16* dst = kc + (((size_t)b * hkv + (h - hq)) * lmax + past + i) * 64;
+        dst[d] = __float2bfloat16(o0);
+        dst[d + 32] = __float2bfloat16(o1);
+      }
+    } else {
+      bf16* dst = vc + (((size_t)b * hkv + (h - hq - hkv)) * lmax + past + i) * 64;
+      dst[d] = src[d];
+      dst[d + 32] = src[d + 32];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Embedding gather + <IMG_CONTEXT> / <TARGET_POINT> substitution.  One block per batch row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+embed_assemble_kernel(const long long* __restrict__ ids, const bf16* __restrict__ table, const bf16* __restrict__ vit,
+                      const bf16* __restrict__ wp, const int* __restrict__ wp_start, int wp_len, bf16* __restrict__ out,
+                      int len, int hidden, int vocab, int img_id, int n_img) {
+  extern __shared__ const bf16* src_ptr[];
+  __shared__ int warp_counts[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int running = 0;
+  for (int base = 0; base < len; base += 1024) {
+    const int l = base + tid;
+    long long id = (l < len) ? ids[(size_t)b * len + l] : -1;
+    const bool is_img = (l < len) && (id == img_id);
+    const unsigned bal = __ballot_sync(0xffffffffu, is_img);
+    if (lane == 0) warp_counts[warp] = __popc(bal);
+    __syncthreads();
+    int prefix = running;
+    for (int wi = 0; wi < warp; ++wi) prefix += warp_counts[wi];
+    const int rank = prefix + __popc(bal & ((1u << lane) - 1));
+    if (l < len) {
+      const bf16* s;
+      const int ws = wp_start ? wp_start[b] : -1;
+      if (wp && ws >= 0 && l >= ws && l < ws + wp_len) s = wp + ((size_t)b * wp_len + (l - ws)) * hidden;
+      else if (is_img && vit && rank < n_img) s = vit + ((size_t)b * n_img + rank) * hidden;
+      else {
+        long long c = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        s = table + (size_t)c * hidden;
+      }
+      src_ptr[l] = s;
+    }
+    int tot = 0;
+    for (int wi = 0; wi < 32; ++wi) tot += warp_counts[wi];
+    running += tot;
+    __syncthreads();
+  }
+  const int vpr = hidden >> 3;
+  for (int idx = tid; idx < len * vpr; idx += blockDim.x) {
+    const int l = idx / vpr, vi = idx % vpr;
+    *reinterpret_cast<uint4*>(out + ((size_t)b * len + l) * hidden + vi * 8) =
+        *reinterpret_cast<const uint4*>(src_ptr[l] + vi * 8);
+  }
+}
+
+__global__ void gather_rows_kernel(const bf16* __restrict__ src, const long long* __restrict__ idx, bf16* __restrict__ dst,
+                                   int n, int cols, long long src_rows) {
+  const int vpr = cols >> 3;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n * vpr; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vpr), vi = (int)(i % vpr);
+    long long s = idx[r];
+    s = s < 0 ? 0 : (s >= src_rows ? src_rows - 1 : s);
+    *reinterpret_cast<uint4*>(dst + (size_t)r * cols + vi * 8) = *reinterpret_cast<const uint4*>(src + (size_t)s * cols + vi * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// simple elementwise
+// ------------------------------------------------------------------------------------------------
+__global__ void silu_mul_kernel(const bf16* __restrict__ g, const bf16* __restrict__ u, bf16* __restrict__ o, size_t nvec) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float a[8], b[8], r[8];
+    load8(g + i * 8, a);
+    load8(u + i * 8, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = silu(a[e]) * b[e];
+    store8(o + i * 8, r);
+  }
+}
+__global__ void add_kernel(const bf16* __restrict__ a_, const bf16* __restrict__ b_, bf16* __restrict__ o, size_t nvec) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float a[8], b[8], r[8];
+    load8(a_ + i * 8, a);
+    load8(b_ + i * 8, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = a[e] + b[e];
+    store8(o + i * 8, r);
+  }
+}
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// argmax over fp32 logits: one block per row; ties -> lowest index; also top1 - top2 margin
+// ------------------------------------------------------------------------------------------------
+struct Top2 { float v1; int i1; float v2; };
+__device__ __forceinline__ void top2_push(Top2& t, float v, int i) {
+  if (v > t.v1 || (v == t.v1 && i < t.i1)) { t.v2 = t.v1; t.v1 = v; t.i1 = i; }
+  else if (v > t.v2) t.v2 = v;
+}
+__device__ __forceinline__ Top2 top2_merge(Top2 a, const Top2& b) {
+  top2_push(a, b.v1, b.i1);
+  if (b.v2 > a.v2) a.v2 = b.v2;
+  return a;
+}
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const float* __restrict__ logits, long long ld, int cols, long long* __restrict__ out_idx, float* __restrict__ margin) {
+  __shared__ Top2 sh[32];
+  const float* r = logits + (size_t)blockIdx.x * ld;
+  Top2 t{-INFINITY, 0x7fffffff, -INFINITY};
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) top2_push(t, r[i], i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Top2 u;
+    u.v1 = __shfl_xor_sync(0xffffffffu, t.v1, o);
+    u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+    u.v2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
+    t = top2_merge(t, u);
+  }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    t = threadIdx.x < nw ? sh[threadIdx.x] : Top2{-INFINITY, 0x7fffffff, -INFINITY};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Top2 u;
+      u.v1 = __shfl_xor_sync(0xffffffffu, t.v1, o);
+      u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+      u.v2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
+      t = top2_merge(t, u);
+    }
+    if (threadIdx.x == 0) {
+      out_idx[blockIdx.x] = t.i1;
+      if (margin) margin[blockIdx.x] = t.v1 - t.v2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiny fused MLPs (latency-bound): warp-per-output dot products over smem-resident activations
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_dot_bf16(const bf16* __restrict__ wrow, const float* __restrict__ x, int n, int lane) {
+  float acc = 0.f;
+  const int nvec = n >> 3;
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float wv[8];
+    load8(wrow + vi * 8, wv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += wv[e] * x[vi * 8 + e];
+  }
+  return warp_sum(acc);
+}
+// y[j] = act(b[j] + W[j,:] . x) for j in [0, nout); all warps of the block cooperate; x, y in smem
+__device__ __forceinline__ void block_linear(const bf16* W, const bf16* bias, const float* x, float* y, int nin, int nout,
+                                             int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < nout; j += nw) {
+    float v = warp_dot_bf16(W + (size_t)j * nin, x, nin, lane);
+    if (lane == 0) {
+      if (bias) v += __bfloat162float(bias[j]);
+      if (act == SLB_ACT_SILU) v = silu(v);
+      else if (act == SLB_ACT_RELU) v = fmaxf(v, 0.f);
+      y[j] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// one block per (batch, query row): rows 0..19 -> route head, 20..29 -> speed head; writes pre-cumsum deltas
+__global__ void __launch_bounds__(256)
+heads_kernel(const bf16* __restrict__ feats, long long ld_batch, slb_heads_weights w, float* __restrict__ delta) {
+  __shared__ float x[896];
+  __shared__ float h1[512];
+  __shared__ float h2[256];
+  const int b = blockIdx.x / 30, r = blockIdx.x % 30;
+  const bf16* f = feats + (size_t)b * ld_batch + (size_t)r * 896;
+  for (int i = threadIdx.x; i < 896; i += blockDim.x) x[i] = __bfloat162float(f[i]);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (r < 20) {
+    block_linear((const bf16*)w.r0w, (const bf16*)w.r0b, x, h1, 896, 512, SLB_ACT_SILU);
+    block_linear((const bf16*)w.r2w, (const bf16*)w.r2b, h1, h2, 512, 256, SLB_ACT_SILU);
+    if (warp < 2) {
+      float v = warp_dot_bf16((const bf16*)w.r4w + warp * 256, h2, 256, lane);
+      if (lane == 0) delta[((size_t)b * 30 + r) * 2 + warp] = v;
+    }
+  } else {
+    block_linear((const bf16*)w.s0w, (const bf16*)w.s0b, x, h2, 896, 256, SLB_ACT_SILU);
+    if (warp < 2) {
+      float v = warp_dot_bf16((const bf16*)w.s2w + warp * 256, h2, 256, lane);
+      if (lane == 0) delta[((size_t)b * 30 + r) * 2 + warp] = v;
+    }
+  }
+}
+__global__ void heads_cumsum_kernel(const float* __restrict__ delta, float* __restrict__ route, float* __restrict__ speed, int batch) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (b, xy)
+  if (idx >= batch * 2) return;
+  const int b = idx >> 1, c = idx & 1;
+  float s = 0.f;
+  for (int r = 0; r < 20; ++r) { s += delta[((size_t)b * 30 + r) * 2 + c]; route[((size_t)b * 20 + r) * 2 + c] = s; }
+  s = 0.f;
+  for (int r = 0; r < 10; ++r) { s += delta[((size_t)b * 30 + 20 + r) * 2 + c]; speed[((size_t)b * 10 + r) * 2 + c] = s; }
+}
+
+// wp encoder: 2 -> 256 -> 512 -> 896 (ReLU); one block per point
+__global__ void __launch_bounds__(256)
+wp_encoder_kernel(const float* __restrict__ coords, slb_wp_weights w, bf16* __restrict__ out) {
+  __shared__ float h1[256];
+  __shared__ float h2[512];
+  __shared__ float h3[896];
+  const int p = blockIdx.x;
+  const float cx = coords[p * 2], cy = coords[p * 2 + 1];
+  for (int j = threadIdx.x; j < 256; j += blockDim.x) {
+    const bf16* wr = (const bf16*)w.w0 + j * 2;
+    float v = __bfloat162float(wr[0]) * cx + __bfloat162float(wr[1]) * cy + __bfloat162float(((const bf16*)w.b0)[j]);
+    h1[j] = fmaxf(v, 0.f);
+  }
+  __syncthreads();
+  block_linear((const bf16*)w.w2, (const bf16*)w.b2, h1, h2, 256, 512, SLB_ACT_RELU);
+  block_linear((const bf16*)w.w4, (const bf16*)w.b4, h2, h3, 512, 896, SLB_ACT_NONE);
+  for (int j = threadIdx.x; j < 896; j += blockDim.x) out[(size_t)p * 896 + j] = __float2bfloat16(h3[j]);
+}
+
+inline int grid_for(size_t work, int block) {
+  size_t g = (work + block - 1) / block;
+  size_t cap = (size_t)slb_num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" int slb_layernorm_fwd(const void* x, const void* w, const void* b, void* y, int rows, int cols, float eps,
+                                 float* mean, float* rstd, void* stream) {
+  SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 4096, "layernorm: bad shape %d x %d", rows, cols);
+  const int grid = ceil_div(rows, kWarpsPerBlock);
+  if (cols <= 1024)
+    norm_fwd_kernel<4, false><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd);
+  else
+    norm_fwd_kernel<16, false><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_rmsnorm_fwd(const void* x, const void* w, void* y, int rows, int cols, float eps, float* rstd, void* stream) {
+  SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm: bad shape %d x %d", rows, cols);
+  const int grid = ceil_div(rows, kWarpsPerBlock);
+  norm_fwd_kernel<4, true><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_pixel_shuffle_ln(const void* x, const void* w, const void* b, void* y, int tiles, float eps, float* mean,
+                                    float* rstd, void* stream) {
+  SLB_CHECK_ARG(tiles > 0, "pixel_shuffle_ln: tiles=%d", tiles);
+  const int rows = tiles * 256;
+  pixel_shuffle_ln_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ST(stream)>>>(
+      (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, tiles, eps, mean, rstd);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_im2col_patch(const void* pixels, void* patches, int tiles, int kpad, void* stream) {
+  SLB_CHECK_ARG(tiles > 0 && kpad >= 588 && (kpad % 8) == 0, "im2col: tiles=%d kpad=%d", tiles, kpad);
+  const size_t total = (size_t)tiles * 1024 * (kpad / 2);
+  im2col_patch_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)pixels, (bf16*)patches, tiles, kpad);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_vit_assemble(const void* patch_out, const void* cls, const void* pos, void* x, int tiles, void* stream) {
+  SLB_CHECK_ARG(tiles > 0, "vit_assemble: tiles=%d", tiles);
+  const size_t total = (size_t)tiles * 1025 * 128;
+  vit_assemble_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)patch_out, (const bf16*)cls, (const bf16*)pos, (bf16*)x, tiles);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, int lmax, int hq, int hkv,
+                                 float theta, void* stream) {
+  SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax, "rope: batch=%d lq=%d past=%d lmax=%d", batch, lq, past, lmax);
+  const size_t total = (size_t)batch * lq * (hq + 2 * hkv) * 32;
+  rope_kv_write_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq, past, lmax, hq, hkv, log2f(theta));
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_embed_assemble(const int64_t* ids, const void* table, const void* vit, const void* wp, const int32_t* wp_start,
+                                  int wp_len, void* out, int batch, int len, int hidden, int vocab, int img_id, int n_img,
+                                  void* stream) {
+  SLB_CHECK_ARG(batch > 0 && len > 0 && (hidden % 8) == 0, "embed_assemble: batch=%d len=%d hidden=%d", batch, len, hidden);
+  SLB_CHECK_ARG((size_t)len * sizeof(void*) <= 200 * 1024, "embed_assemble: len=%d too long", len);
+  const size_t smem = (size_t)len * sizeof(void*);
+  if (smem > 48 * 1024) SLB_CUDA(cudaFuncSetAttribute(embed_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  embed_assemble_kernel<<<batch, 1024, smem, ST(stream)>>>((const long long*)ids, (const bf16*)table, (const bf16*)vit, (const bf16*)wp,
+                                                          wp_start, wp_len, (bf16*)out, len, hidden, vocab, img_id, n_img);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_gather_rows(const void* src, const int64_t* idx, void* dst, int n, int cols, int64_t src_rows, void* stream) {
+  SLB_CHECK_ARG(n > 0 && (cols % 8) == 0, "gather_rows: n=%d cols=%d", n, cols);
+  gather_rows_kernel<<<grid_for((size_t)n * (cols / 8), 128), 128, 0, ST(stream)>>>((const bf16*)src, (const long long*)idx, (bf16*)dst, n, cols, src_rows);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream) {
+  SLB_CHECK_ARG(n > 0 && (n % 8) == 0, "silu_mul: n=%lld", (long long)n);
+  silu_mul_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)gate, (const bf16*)up, (bf16*)out, n / 8);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+extern "C" int slb_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  SLB_CHECK_ARG(n > 0 && (n % 8) == 0, "add: n=%lld", (long long)n);
+  add_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n / 8);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+extern "C" int slb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  SLB_CHECK_ARG(n > 0, "cast: n=%lld", (long long)n);
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, (bf16*)y, n);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_argmax_f32(const float* logits, int64_t ld, int rows, int cols, int64_t* out_idx, float* out_margin, void* stream) {
+  SLB_CHECK_ARG(rows > 0 && cols > 0, "argmax: rows=%d cols=%d", rows, cols);
+  argmax_kernel<<<rows, 1024, 0, ST(stream)>>>(logits, ld, cols, (long long*)out_idx, out_margin);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_driving_heads(const void* feats, int64_t ld_batch, const slb_heads_weights* w, float* route, float* speed,
+                                 float* delta_ws, int batch, void* stream) {
+  SLB_CHECK_ARG(batch > 0 && w && delta_ws, "driving_heads: bad args");
+  heads_kernel<<<batch * 30, 256, 0, ST(stream)>>>((const bf16*)feats, ld_batch, *w, delta_ws);
+  SLB_LAUNCH_CHECK();
+  heads_cumsum_kernel<<<ceil_div(batch * 2, 64), 64, 0, ST(stream)>>>(delta_ws, route, speed, batch);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_wp_encoder(const float* coords, const slb_wp_weights* w, void* out, int n_points, void* stream) {
+  SLB_CHECK_ARG(n_points > 0 && w, "wp_encoder: bad args");
+  wp_encoder_kernel<<<n_points, 256, 0, ST(stream)>>>(coords, *w, (bf16*)out);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}

@@ -1,0 +1,359 @@
+// bf16 GEMM for sm_100a: TMA (128B swizzle) -> smem ring -> tcgen05.mma (cta_group::1, 128 x BN x 16,
+// fp32 accumulators in TMEM, two accumulator stages) -> tcgen05.ld epilogue with fused
+// bias / activation / layer-scale / residual / SwiGLU.  Persistent, warp-specialised:
+//   warp 0     TMA producer (one elected lane)
+//   warp 1     TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-5  epilogue (warp w reads TMEM lanes 32*(w%4) .. +31 = accumulator rows)
+// Covers K1,K3,K5,K7,K10,K13,K14 of SURVEY.md section 2.2 and their dgrad/wgrad (a_t / b_t operands).
+#include "common.cuh"
+#include "../../include/simlingo_b200.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+struct EpiParams {
+  int M, N, K;
+  void* out;
+  long long ldo;
+  const bf16* bias;
+  const bf16* scale_n;
+  const void* res;
+  long long ldr;
+  float alpha;
+  int act;
+  int swiglu;
+  int out_fp32;
+  int num_m, num_n;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == SLB_ACT_GELU) return gelu_erf(v);
+  if (act == SLB_ACT_SILU) return silu(v);
+  if (act == SLB_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+// Stores 32 consecutive output columns of one row.
+__device__ __forceinline__ void store_row32(const EpiParams& p, int row, int col0, const float (&v)[32], int ncols_total) {
+  if (p.out_fp32) {
+    float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+    bool vec = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (col0 + 32 <= ncols_total);
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) o[i] = v[i];
+    }
+  } else {
+    bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col0;
+    bool vec = ((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (col0 + 32 <= ncols_total);
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(o)[i] = u;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) o[i] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void add_residual32(const EpiParams& p, int row, int col0, float (&v)[32], int ncols_total) {
+  if (p.out_fp32) {
+    const float* r = reinterpret_cast<const float*>(p.res) + (long long)row * p.ldr + col0;
+    bool vec = ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) && (col0 + 32 <= ncols_total);
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 t = reinterpret_cast<const float4*>(r)[i];
+        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) v[i] += r[i];
+    }
+  } else {
+    const bf16* r = reinterpret_cast<const bf16*>(p.res) + (long long)row * p.ldr + col0;
+    bool vec = ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) && (col0 + 32 <= ncols_total);
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u = reinterpret_cast<const uint4*>(r)[i];
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        v[8 * i + 0] += a.x; v[8 * i + 1] += a.y; v[8 * i + 2] += b.x; v[8 * i + 3] += b.y;
+        v[8 * i + 4] += c.x; v[8 * i + 5] += c.y; v[8 * i + 6] += d.x; v[8 * i + 7] += d.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) v[i] += __bfloat162float(r[i]);
+    }
+  }
+}
+
+template <int BN, int TA, int TB>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m * p.num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+  constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512: power of two
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n) * BM;
+        const int n0 = (tile % p.num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          const int k0 = kb * BK;
+          if (TA == 0) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * (64 * BK * 2), &tmap_a, &full_bar[stage], m0 + g * 64, k0);
+          }
+          if (TB == 0) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g) tma_load_2d(sb + g * (64 * BK * 2), &tmap_b, &full_bar[stage], n0 + g * 64, k0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, TA, TB);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t da = TA ? umma_desc_mnmajor_sw128(sa, 64 * BK * 2) : umma_desc_kmajor_sw128(sa);
+          const uint64_t db = TB ? umma_desc_mnmajor_sw128(sb, 64 * BK * 2) : umma_desc_kmajor_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: +32 bytes per UMMA_K inside the swizzle row; MN-major: +16 k-rows * 128 B
+            const uint64_t ka = TA ? (uint64_t)(k * (UMMA_K * 128 >> 4)) : (uint64_t)(k * (UMMA_K * 2 >> 4));
+            const uint64_t kbo = TB ? (uint64_t)(k * (UMMA_K * 128 >> 4)) : (uint64_t)(k * (UMMA_K * 2 >> 4));
+            tc_mma_bf16(tmem_d, da + ka, db + kbo, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int n_out_total = p.swiglu ? p.N / 2 : p.N;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n) * BM;
+      const int n0 = (tile % p.num_n) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+      const bool row_ok = row < p.M;
+      if (!p.swiglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+          const int col0 = n0 + c;
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) v[i] += __bfloat162float(__ldg(p.bias + col0 + i));
+          }
+          if (p.act) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+          }
+          if (p.scale_n) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) v[i] *= __bfloat162float(__ldg(p.scale_n + col0 + i));
+          }
+          if (row_ok) {
+            if (p.res) add_residual32(p, row, col0, v, p.N);
+            store_row32(p, row, col0, v, p.N);
+          }
+        }
+      } else {
+        // gate columns [0,BN/2), up columns [BN/2,BN) of this tile; output column base n0/2
+#pragma unroll 1
+        for (int c = 0; c < BN / 2; c += 32) {
+          uint32_t rg[32], ru[32];
+          tmem_ld_32x32(taddr + c, rg);
+          tmem_ld_32x32(taddr + BN / 2 + c, ru);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = silu(__uint_as_float(rg[i]) * p.alpha) * (__uint_as_float(ru[i]) * p.alpha);
+          if (row_ok) store_row32(p, row, n0 / 2 + c, v, n_out_total);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int TA, int TB>
+int launch_gemm(const slb_gemm_args* a, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!TA) rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM);
+  else     rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, BK);
+  if (rc) return rc;
+  if (!TB) rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN);
+  else     rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, BK);
+  if (rc) return rc;
+  EpiParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.out = a->out; p.ldo = a->ldo;
+  p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
+  p.res = a->residual; p.ldr = a->ldr;
+  p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
+  p.num_m = ceil_div(a->M, BM);
+  p.num_n = ceil_div(a->N, BN);
+  auto kern = gemm_bf16_kernel<BN, TA, TB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  int grid = p.num_m * p.num_n;
+  int sms = slb_num_sms();
+  if (grid > sms) grid = sms;
+  kern<<<grid, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, p);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+}  // namespace
+
+extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SLB_CHECK_ARG(a != nullptr, "gemm: null args");
+  SLB_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  SLB_CHECK_ARG(a->A && a->B && a->out, "gemm: null operand");
+  SLB_CHECK_ARG((a->lda % 8) == 0 && (a->ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (16 B TMA stride), got %lld %lld",
+                (long long)a->lda, (long long)a->ldb);
+  SLB_CHECK_ARG(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0, "gemm: A/B must be 16-byte aligned");
+  SLB_CHECK_ARG(!(a->a_t && !a->b_t), "gemm: a_t=1 requires b_t=1 (wgrad form)");
+  if (a->swiglu) {
+    SLB_CHECK_ARG((a->N % 256) == 0, "gemm: swiglu needs N %% 256 == 0 (got %d)", a->N);
+    SLB_CHECK_ARG(!a->bias && !a->scale_n && !a->residual && !a->act, "gemm: swiglu excludes other epilogue terms");
+  }
+  int bn = a->block_n;
+  if (a->swiglu) bn = 256;
+  if (bn == 0) {
+    // pick the tile width with the fewer (weighted) waves; 256-wide tiles halve A re-reads and are ~10 % more
+    // efficient per flop, but quantise worse on small problems
+    const int sms = slb_num_sms();
+    const int mt = ceil_div(a->M, BM);
+    const float c256 = 2.0f * (float)ceil_div(mt * ceil_div(a->N, 256), sms);
+    const float c128 = 1.1f * (float)ceil_div(mt * ceil_div(a->N, 128), sms);
+    bn = (c256 <= c128) ? 256 : 128;
+  }
+  SLB_CHECK_ARG(bn == 128 || bn == 256, "gemm: block_n must be 0, 128 or 256");
+  if (!a->a_t && !a->b_t) return bn == 256 ? launch_gemm<256, 0, 0>(a, stream) : launch_gemm<128, 0, 0>(a, stream);
+  if (!a->a_t && a->b_t) return bn == 256 ? launch_gemm<256, 0, 1>(a, stream) : launch_gemm<128, 0, 1>(a, stream);
+  return bn == 256 ? launch_gemm<256, 1, 1>(a, stream) : launch_gemm<128, 1, 1>(a, stream);
+}

@@ -1,0 +1,245 @@
+"""ctypes binding of ``libsimlingo_b200.so`` (C ABI declared in ``include/simlingo_b200.h``).
+
+This is the only way the Python side reaches the GPU math: tensors are passed as raw device
+pointers + sizes, the launch stream is ``torch.cuda.current_stream()``.  There is no fallback: if
+the shared library is missing or a call returns non-zero a ``RuntimeError`` is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libsimlingo_b200.so"
+_lib: Optional[C.CDLL] = None
+
+ACT_NONE, ACT_GELU, ACT_SILU, ACT_RELU = 0, 1, 2, 3
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("B", C.c_void_p), ("ldb", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("bias", C.c_void_p), ("scale_n", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("alpha", C.c_float), ("act", C.c_int32), ("swiglu", C.c_int32), ("out_fp32", C.c_int32),
+        ("a_t", C.c_int32), ("b_t", C.c_int32), ("block_n", C.c_int32),
+    ]
+
+
+class HeadsWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("r0w", "r0b", "r2w", "r2b", "r4w", "s0w", "s0b", "s2w")]
+
+
+class WpWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w0", "b0", "w2", "b2", "w4", "b4")]
+
+
+def load() -> C.CDLL:
+    """dlopen the library (building is ``python -m simlingo_b200.build`` / ``__graft_entry__.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built (run `python simlingo_b200/build.py`). "
+            "There is no CPU fallback.")
+    # the torch-bundled NCCL / cudart must be resolvable before our library is opened
+    try:
+        import torch  # noqa: F401  (loads libcudart / libnccl into the process)
+        nccl_dir = Path(torch.__file__).resolve().parent.parent / "nvidia" / "nccl" / "lib"
+        so = nccl_dir / "libnccl.so.2"
+        if so.exists():
+            C.CDLL(str(so), mode=C.RTLD_GLOBAL)
+    except OSError:
+        pass
+    _lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    _lib.slb_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().slb_last_error()
+        raise RuntimeError(f"simlingo_b200: {what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _bf16(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.bfloat16, (t.device, t.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, scale_n=None,
+         residual=None, alpha: float = 1.0, act: int = ACT_NONE, swiglu: bool = False, out_fp32: bool = False,
+         a_t: bool = False, b_t: bool = False, block_n: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(alpha * A @ B^T).  A: [M,K] (or [K,M] if a_t), B: [N,K] (or [K,N] if b_t);
+    2-D, unit inner stride, arbitrary (multiple-of-8) row stride."""
+    _bf16(a, b, bias, scale_n)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
+    assert K == Kb, (a.shape, b.shape, a_t, b_t)
+    n_out = N // 2 if swiglu else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    assert out.dim() == 2 and out.stride(1) == 1 and out.shape == (M, n_out)
+    assert out.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
+    if residual is not None:
+        assert residual.dtype == out.dtype and residual.stride(1) == 1 and residual.shape == out.shape
+    g = GemmArgs(M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
+                 None if bias is None else bias.data_ptr(), None if scale_n is None else scale_n.data_ptr(),
+                 None if residual is None else residual.data_ptr(), 0 if residual is None else residual.stride(0),
+                 alpha, act, int(swiglu), int(out_fp32), int(a_t), int(b_t), block_n)
+    _check(load().slb_gemm_bf16(C.byref(g), _stream()), "gemm_bf16")
+    return out
+
+
+def layernorm(x, w, b, eps, out=None, stats=None):
+    _bf16(x, w, b)
+    rows, cols = x.shape[0], x.shape[1]
+    out = torch.empty_like(x) if out is None else out
+    mean, rstd = (stats if stats is not None else (None, None))
+    _check(load().slb_layernorm_fwd(_p(x), _p(w), _p(b), _p(out), rows, cols, C.c_float(eps), _p(mean), _p(rstd), _stream()),
+           "layernorm_fwd")
+    return out
+
+
+def rmsnorm(x, w, eps, out=None, rstd=None):
+    _bf16(x, w)
+    out = torch.empty_like(x) if out is None else out
+    _check(load().slb_rmsnorm_fwd(_p(x), _p(w), _p(out), x.shape[0], x.shape[1], C.c_float(eps), _p(rstd), _stream()),
+           "rmsnorm_fwd")
+    return out
+
+
+def im2col_patch(pixels, kpad=640, out=None):
+    _bf16(pixels)
+    tiles = pixels.shape[0]
+    assert pixels.shape[1:] == (3, 448, 448) and pixels.is_contiguous()
+    out = torch.empty((tiles * 1024, kpad), device=pixels.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().slb_im2col_patch(_p(pixels), _p(out), tiles, kpad, _stream()), "im2col_patch")
+    return out
+
+
+def vit_assemble(patch_out, cls, pos, tiles, out=None):
+    _bf16(patch_out, cls, pos)
+    out = torch.empty((tiles * 1025, 1024), device=patch_out.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().slb_vit_assemble(_p(patch_out), _p(cls), _p(pos), _p(out), tiles, _stream()), "vit_assemble")
+    return out
+
+
+def pixel_shuffle_ln(x, w, b, tiles, eps, out=None, stats=None):
+    _bf16(x, w, b)
+    out = torch.empty((tiles * 256, 4096), device=x.device, dtype=torch.bfloat16) if out is None else out
+    mean, rstd = (stats if stats is not None else (None, None))
+    _check(load().slb_pixel_shuffle_ln(_p(x), _p(w), _p(b), _p(out), tiles, C.c_float(eps), _p(mean), _p(rstd), _stream()),
+           "pixel_shuffle_ln")
+    return out
+
+
+def attn_vit(qkv, tiles, n_tokens, heads=16, out=None, lse=None):
+    _bf16(qkv)
+    assert qkv.is_contiguous() and qkv.shape == (tiles * n_tokens, 3 * heads * 64)
+    out = torch.empty((tiles * n_tokens, heads * 64), device=qkv.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().slb_attn_vit_fwd(_p(qkv), _p(out), _p(lse), tiles, n_tokens, heads, _stream()), "attn_vit_fwd")
+    return out
+
+
+def attn_gqa(q, ldq, kcache, vcache, batch, lq, past, hq=14, hkv=2, key_valid=None, out=None, lse=None):
+    """q: view into the fused qkv buffer ([B*Lq, ldq] rows, first hq*64 columns are q)."""
+    _bf16(q, kcache, vcache)
+    lmax = kcache.shape[2]
+    assert kcache.shape == (batch, hkv, lmax, 64) and kcache.is_contiguous() and vcache.is_contiguous()
+    out = torch.empty((batch * lq, hq * 64), device=q.device, dtype=torch.bfloat16) if out is None else out
+    kv_ld = 0
+    if key_valid is not None:
+        assert key_valid.dtype == torch.uint8 and key_valid.dim() == 2 and key_valid.stride(1) == 1
+        kv_ld = key_valid.stride(0)
+    _check(load().slb_attn_gqa_fwd(_p(q), C.c_int64(ldq), _p(kcache), _p(vcache), _p(key_valid), kv_ld, _p(out), _p(lse),
+                                   batch, lq, past, lmax, hq, hkv, _stream()), "attn_gqa_fwd")
+    return out
+
+
+def rope_kv_write(qkv, kcache, vcache, batch, lq, past, hq=14, hkv=2, theta=1.0e6):
+    _bf16(qkv, kcache, vcache)
+    assert qkv.is_contiguous() and qkv.shape == (batch * lq, (hq + 2 * hkv) * 64)
+    lmax = kcache.shape[2]
+    _check(load().slb_rope_kv_write(_p(qkv), _p(kcache), _p(vcache), batch, lq, past, lmax, hq, hkv, C.c_float(theta), _stream()),
+           "rope_kv_write")
+
+
+def embed_assemble(ids, table, vit, wp, wp_start, wp_len, img_id, n_img, out=None):
+    """ids int64 [B,L]; table bf16 [V,H]; vit bf16 [B*n_img,H] or None; wp bf16 [B,wp_len,H] or None;
+    wp_start int32 [B] (-1 = none)."""
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous()
+    B, L = ids.shape
+    V, H = table.shape
+    out = torch.empty((B, L, H), device=ids.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().slb_embed_assemble(_p(ids), _p(table), _p(vit), _p(wp), _p(wp_start), wp_len, _p(out), B, L, H, V, img_id, n_img,
+                                     _stream()), "embed_assemble")
+    return out
+
+
+def gather_rows(src, idx, out=None):
+    _bf16(src)
+    assert idx.dtype == torch.int64 and idx.is_cuda
+    n = idx.numel()
+    out = torch.empty((n, src.shape[1]), device=src.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().slb_gather_rows(_p(src), _p(idx), _p(out), n, src.shape[1], C.c_int64(src.shape[0]), _stream()), "gather_rows")
+    return out
+
+
+def silu_mul(g, u, out=None):
+    _bf16(g, u)
+    out = torch.empty_like(g) if out is None else out
+    _check(load().slb_silu_mul(_p(g), _p(u), _p(out), C.c_int64(g.numel()), _stream()), "silu_mul")
+    return out
+
+
+def add(a, b, out=None):
+    _bf16(a, b)
+    out = torch.empty_like(a) if out is None else out
+    _check(load().slb_add_bf16(_p(a), _p(b), _p(out), C.c_int64(a.numel()), _stream()), "add_bf16")
+    return out
+
+
+def argmax(logits, out_idx=None, out_margin=None):
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    rows, cols = logits.shape
+    out_idx = torch.empty((rows,), device=logits.device, dtype=torch.int64) if out_idx is None else out_idx
+    _check(load().slb_argmax_f32(_p(logits), C.c_int64(logits.stride(0)), rows, cols, _p(out_idx), _p(out_margin), _stream()),
+           "argmax_f32")
+    return out_idx
+
+
+def driving_heads(feats, ld_batch, hw: HeadsWeights, batch, route=None, speed=None, ws=None):
+    dev = feats.device
+    route = torch.empty((batch, 20, 2), device=dev, dtype=torch.float32) if route is None else route
+    speed = torch.empty((batch, 10, 2), device=dev, dtype=torch.float32) if speed is None else speed
+    ws = torch.empty((batch, 30, 2), device=dev, dtype=torch.float32) if ws is None else ws
+    _check(load().slb_driving_heads(_p(feats), C.c_int64(ld_batch), C.byref(hw), _p(route), _p(speed), _p(ws), batch, _stream()),
+           "driving_heads")
+    return route, speed
+
+
+def wp_encoder(coords, ww: WpWeights, out=None):
+    assert coords.dtype == torch.float32 and coords.is_cuda and coords.is_contiguous()
+    n = coords.shape[0]
+    out = torch.empty((n, 896), device=coords.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().slb_wp_encoder(_p(coords), C.byref(ww), _p(out), n, _stream()), "wp_encoder")
+    return out

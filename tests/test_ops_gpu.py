@@ -1,0 +1,281 @@
+"""Per-kernel numerics on a B200: every C-ABI op against a plain PyTorch fp32 reference of the same op
+(computed on the GPU from the same bf16 inputs).  Tolerances are stated per test; bf16 outputs are
+compared with max-abs error relative to the reference's max magnitude."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from simlingo_b200 import lib as L
+    L.load()
+    return L
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+GEMM_CASES = [
+    # M, N, K, block_n
+    (128, 128, 64, 128), (256, 256, 128, 256), (300, 200, 72, 0), (2050, 3072, 1024, 0), (2050, 1024, 4096, 128),
+    (2050, 1024, 1024, 256), (545, 1152, 896, 0), (545, 896, 4864, 0), (2048, 1024, 640, 0), (545, 32, 896, 128),
+    (545, 896, 32, 0), (7, 896, 896, 0), (1, 1152, 896, 0),
+]
+
+
+@pytest.mark.parametrize("M,N,K,bn", GEMM_CASES)
+def test_gemm_plain(lib, M, N, K, bn):
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2)
+    out = lib.gemm(a, b, block_n=bn)
+    ref = a.float() @ b.float().t()
+    assert relerr(out, ref) < 1e-2  # bf16 output rounding (2^-9) + fp32 accumulation order
+
+
+def test_gemm_epilogues(lib):
+    M, N, K = 2050, 1024, 1024
+    a, b = rnd(M, K, seed=1, scale=0.5), rnd(N, K, seed=2, scale=0.05)
+    bias, ls, res = rnd(N, seed=3), rnd(N, seed=4, scale=0.2), rnd(M, N, seed=5)
+    acc = a.float() @ b.float().t()
+    out = lib.gemm(a, b, bias=bias)
+    assert relerr(out, acc + bias.float()) < 1e-2
+    out = lib.gemm(a, b, bias=bias, act=lib.ACT_GELU)
+    assert relerr(out, F.gelu(acc + bias.float())) < 1e-2
+    out = lib.gemm(a, b, bias=bias, scale_n=ls, residual=res)
+    assert relerr(out, res.float() + ls.float() * (acc + bias.float())) < 1e-2
+    out = lib.gemm(a, b, residual=res, alpha=2.0)
+    assert relerr(out, res.float() + 2.0 * acc) < 1e-2
+    out = lib.gemm(a, b, act=lib.ACT_SILU)
+    assert relerr(out, F.silu(acc)) < 1e-2
+    out = lib.gemm(a, b, out_fp32=True)
+    assert relerr(out, acc) < 1e-5
+    acc32 = torch.randn(M, N, device="cuda")
+    out = lib.gemm(a, b, out=acc32.clone(), residual=acc32, out_fp32=True)
+    assert relerr(out, acc + acc32) < 1e-5
+
+
+def test_gemm_strided_views(lib):
+    """A as a column slice of a wider buffer (q part of the fused qkv), out as a slice."""
+    M, K, N = 545, 896, 896
+    big = rnd(M, 1152, seed=7)
+    a = big[:, :K]
+    b = rnd(N, K, seed=8, scale=0.05)
+    outbig = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
+    lib.gemm(a, b, out=outbig[:, N:])
+    assert relerr(outbig[:, N:], a.float() @ b.float().t()) < 1e-2
+    assert outbig[:, :N].abs().max().item() == 0
+
+
+def test_gemm_swiglu(lib):
+    M, K, I = 545, 896, 4864
+    a = rnd(M, K, seed=1)
+    wg, wu = rnd(I, K, seed=2, scale=0.05), rnd(I, K, seed=3, scale=0.05)
+    # interleave in groups of 128 rows: [g0..127, u0..127, g128..255, ...]
+    w = torch.stack([wg.view(I // 128, 128, K), wu.view(I // 128, 128, K)], dim=1).reshape(2 * I, K).contiguous()
+    out = lib.gemm(a, w, swiglu=True)
+    ref = F.silu(a.float() @ wg.float().t()) * (a.float() @ wu.float().t())
+    assert out.shape == (M, I)
+    assert relerr(out, ref) < 1e-2
+
+
+def test_gemm_lm_head_odd_vocab(lib):
+    """N = 151655 (odd): fp32 logits with an unaligned row stride."""
+    M, K, N = 3, 896, 151655
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
+    out = lib.gemm(a, b, out_fp32=True)
+    ref = a.float() @ b.float().t()
+    assert relerr(out, ref) < 1e-5
+    assert (out.argmax(-1) == ref.argmax(-1)).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (2050, 1024, 4096), (545, 896, 1152), (591, 4864, 896)])
+def test_gemm_dgrad_form(lib, M, N, K):
+    """b_t: B given as [K, N] row-major (dX = dY @ W with W stored [out,in])."""
+    a, bt = rnd(M, K, seed=1), rnd(K, N, seed=2, scale=0.05)
+    out = lib.gemm(a, bt, b_t=True)
+    assert relerr(out, a.float() @ bt.float()) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1024, 4096, 2050), (896, 32, 545), (32, 896, 4728)])
+def test_gemm_wgrad_form(lib, M, N, K):
+    """a_t + b_t: dW[M=out, N=in] = dY^T X with dY stored [K, M], X stored [K, N] (K = tokens)."""
+    at, bt = rnd(K, M, seed=1), rnd(K, N, seed=2)
+    out = lib.gemm(at, bt, a_t=True, b_t=True, out_fp32=True)
+    assert relerr(out, at.float().t() @ bt.float()) < 1e-4
+
+
+def test_layernorm_rmsnorm(lib):
+    for rows, cols in [(2050, 1024), (512, 4096), (37, 1024)]:
+        x, w, b = rnd(rows, cols, seed=1), rnd(cols, seed=2), rnd(cols, seed=3)
+        y = lib.layernorm(x, w, b, 1e-6)
+        ref = F.layer_norm(x.float(), (cols,), w.float(), b.float(), 1e-6)
+        assert relerr(y, ref) < 1e-2
+    x, w = rnd(575, 896, seed=1), rnd(896, seed=2)
+    y = lib.rmsnorm(x, w, 1e-6)
+    ref = x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()
+    assert relerr(y, ref) < 1e-2
+
+
+def test_patch_embed_glue(lib):
+    T = 2
+    px = rnd(T, 3, 448, 448, seed=1)
+    w = rnd(1024, 3, 14, 14, seed=2, scale=0.02)
+    bias, cls, pos = rnd(1024, seed=3, scale=0.02), rnd(1, 1, 1024, seed=4), rnd(1, 1025, 1024, seed=5)
+    cols = lib.im2col_patch(px, 640)
+    ref_cols = F.unfold(px.float(), kernel_size=14, stride=14).transpose(1, 2).reshape(T * 1024, 588)
+    assert torch.equal(cols[:, :588].float(), ref_cols)
+    assert cols[:, 588:].abs().max().item() == 0
+    wpad = torch.zeros(1024, 640, device="cuda", dtype=torch.bfloat16)
+    wpad[:, :588] = w.reshape(1024, 588)
+    po = lib.gemm(cols, wpad, bias=bias)
+    x = lib.vit_assemble(po, cls, pos, T)
+    conv = F.conv2d(px.float(), w.float(), bias.float(), stride=14).flatten(2).transpose(1, 2)
+    ref = torch.cat([cls.float().expand(T, 1, -1), conv], 1) + pos.float()
+    assert relerr(x.view(T, 1025, 1024), ref) < 1e-2
+
+
+def test_pixel_shuffle_ln(lib):
+    from oracle.model import pixel_shuffle_closed_form
+    T = 3
+    x = rnd(T * 1025, 1024, seed=1)
+    w, b = rnd(4096, seed=2), rnd(4096, seed=3)
+    y = lib.pixel_shuffle_ln(x, w, b, T, 1e-5)
+    xs = pixel_shuffle_closed_form(x.float().view(T, 1025, 1024)[:, 1:], 32)
+    ref = F.layer_norm(xs, (4096,), w.float(), b.float(), 1e-5).reshape(T * 256, 4096)
+    assert relerr(y, ref) < 1e-2
+
+
+@pytest.mark.parametrize("tiles,n", [(1, 128), (2, 1025), (3, 300)])
+def test_attn_vit(lib, tiles, n):
+    H = 16
+    qkv = rnd(tiles * n, 3 * H * 64, seed=1)
+    out = lib.attn_vit(qkv, tiles, n, H)
+    q, k, v = qkv.float().view(tiles, n, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(tiles * n, H * 64)
+    assert relerr(out, ref) < 2e-2
+
+
+def _gqa_ref(q, k, v, past, valid):
+    # q [B,Hq,Lq,64], k/v [B,Hkv,Lk,64]
+    B, Hq, Lq, _ = q.shape
+    Lk = k.shape[2]
+    k = k.repeat_interleave(Hq // k.shape[1], 1)
+    v = v.repeat_interleave(Hq // v.shape[1], 1)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    i = torch.arange(Lq, device=q.device)[:, None] + past
+    j = torch.arange(Lk, device=q.device)[None]
+    m = j <= i
+    if valid is not None:
+        m = m[None, None] & valid[:, None, None, :Lk].bool()
+    s = s.masked_fill(~m, float("-inf"))
+    return torch.softmax(s, -1).nan_to_num(0.0) @ v
+
+
+@pytest.mark.parametrize("B,lq,past,use_valid", [(1, 545, 0, False), (2, 200, 0, True), (2, 30, 549, False),
+                                                 (3, 1, 577, True), (1, 130, 64, False)])
+def test_attn_gqa_and_rope(lib, B, lq, past, use_valid):
+    Hq, Hkv, lmax = 14, 2, 704
+    qkv = rnd(B * lq, (Hq + 2 * Hkv) * 64, seed=1)
+    kc = torch.zeros(B, Hkv, lmax, 64, device="cuda", dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    if past > 0:
+        kc[:, :, :past] = rnd(B, Hkv, past, 64, seed=2)
+        vc[:, :, :past] = rnd(B, Hkv, past, 64, seed=3)
+    valid = None
+    if use_valid:
+        valid = torch.ones(B, lmax, device="cuda", dtype=torch.uint8)
+        valid[1, :5] = 0
+    ref_qkv = qkv.float().view(B, lq, Hq + 2 * Hkv, 64)
+    pos = torch.arange(past, past + lq, device="cuda").float()
+    inv = 1.0 / (1.0e6 ** (torch.arange(0, 64, 2, device="cuda").float() / 64))
+    fr = pos[:, None] * inv
+    cos, sin = torch.cat([fr, fr], -1).cos()[None, :, None], torch.cat([fr, fr], -1).sin()[None, :, None]
+
+    def rot(x):
+        return torch.cat([-x[..., 32:], x[..., :32]], -1)
+
+    qr = ref_qkv[:, :, :Hq] * cos + rot(ref_qkv[:, :, :Hq]) * sin
+    kr = ref_qkv[:, :, Hq:Hq + Hkv] * cos + rot(ref_qkv[:, :, Hq:Hq + Hkv]) * sin
+    vr = ref_qkv[:, :, Hq + Hkv:]
+    kfull = kc.float().clone()
+    vfull = vc.float().clone()
+    kfull[:, :, past:past + lq] = kr.transpose(1, 2)
+    vfull[:, :, past:past + lq] = vr.transpose(1, 2)
+
+    lib.rope_kv_write(qkv, kc, vc, B, lq, past)
+    assert relerr(qkv.view(B, lq, Hq + 2 * Hkv, 64)[:, :, :Hq], qr) < 1e-2
+    assert relerr(kc[:, :, :past + lq], kfull[:, :, :past + lq]) < 1e-2
+    assert torch.equal(vc[:, :, past:past + lq].float(), vr.transpose(1, 2))
+
+    out = lib.attn_gqa(qkv, qkv.stride(0), kc, vc, B, lq, past, key_valid=valid)
+    qq = qkv.float().view(B, lq, Hq + 2 * Hkv, 64)[:, :, :Hq].transpose(1, 2)
+    ref = _gqa_ref(qq, kc.float()[:, :, :past + lq], vc.float()[:, :, :past + lq], past, valid)
+    ref = ref.transpose(1, 2).reshape(B * lq, Hq * 64)
+    assert relerr(out, ref) < 2e-2
+
+
+def test_embed_assemble_gather_argmax(lib):
+    B, L, H, V, n_img = 2, 545, 896, 4096, 512
+    img_id = V - 7
+    table = rnd(V, H, seed=1)
+    ids = torch.randint(0, V - 20, (B, L), device="cuda")
+    ids[:, 4:4 + n_img] = img_id
+    ids[:, 540:542] = V + 7  # out-of-table id -> clamp
+    vit = rnd(B * n_img, H, seed=2)
+    wp = rnd(B, 2, H, seed=3)
+    wp_start = torch.tensor([540, -1], device="cuda", dtype=torch.int32)
+    out = lib.embed_assemble(ids, table, vit, wp, wp_start, 2, img_id, n_img)
+    ref = table[ids.clamp(0, V - 1)].clone()
+    ref[:, 4:4 + n_img] = vit.view(B, n_img, H)
+    ref[0, 540:542] = wp[0]
+    assert torch.equal(out, ref)
+    idx = torch.tensor([5, 0, V + 3, 17], device="cuda")
+    assert torch.equal(lib.gather_rows(table, idx), table[idx.clamp(0, V - 1)])
+    lg = torch.randn(5, 151655, device="cuda")
+    marg = torch.empty(5, device="cuda")
+    am = lib.argmax(lg, out_margin=marg)
+    assert torch.equal(am, lg.argmax(-1))
+    t2 = lg.topk(2, -1).values
+    assert torch.allclose(marg, t2[:, 0] - t2[:, 1])
+
+
+def test_heads_and_wp_encoder(lib):
+    B = 3
+    feats = rnd(B, 30, 896, seed=1)
+    W = {k: rnd(*s, seed=i + 10, scale=0.05) for i, (k, s) in enumerate({
+        "r0w": (512, 896), "r0b": (512,), "r2w": (256, 512), "r2b": (256,), "r4w": (2, 256),
+        "s0w": (256, 896), "s0b": (256,), "s2w": (2, 256)}.items())}
+    hw = lib.HeadsWeights(*[W[k].data_ptr() for k in ("r0w", "r0b", "r2w", "r2b", "r4w", "s0w", "s0b", "s2w")])
+    route, speed = lib.driving_heads(feats, 30 * 896, hw, B)
+    f = feats.float()
+    r = F.silu(F.linear(f[:, :20], W["r0w"].float(), W["r0b"].float()))
+    r = F.silu(F.linear(r, W["r2w"].float(), W["r2b"].float()))
+    r = F.linear(r, W["r4w"].float()).cumsum(1)
+    s = F.linear(F.silu(F.linear(f[:, 20:], W["s0w"].float(), W["s0b"].float())), W["s2w"].float()).cumsum(1)
+    assert relerr(route, r) < 1e-4 and relerr(speed, s) < 1e-4
+    P = {k: rnd(*s_, seed=i + 30, scale=0.05) for i, (k, s_) in enumerate({
+        "w0": (256, 2), "b0": (256,), "w2": (512, 256), "b2": (512,), "w4": (896, 512), "b4": (896,)}.items())}
+    ww = lib.WpWeights(*[P[k].data_ptr() for k in ("w0", "b0", "w2", "b2", "w4", "b4")])
+    coords = torch.randn(4, 2, device="cuda") * 10
+    out = lib.wp_encoder(coords, ww)
+    h = F.relu(F.linear(coords, P["w0"].float(), P["b0"].float()))
+    h = F.relu(F.linear(h, P["w2"].float(), P["b2"].float()))
+    ref = F.linear(h, P["w4"].float(), P["b4"].float())
+    assert relerr(out, ref) < 1e-2
+
+
+def test_silu_mul_add(lib):
+    g, u = rnd(545, 4864, seed=1), rnd(545, 4864, seed=2)
+    assert relerr(lib.silu_mul(g, u), F.silu(g.float()) * u.float()) < 1e-2
+    assert relerr(lib.add(g, u), g.float() + u.float()) < 1e-2
