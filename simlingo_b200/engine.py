@@ -1,0 +1,372 @@
+"""Inference runtime of the SimLingo hot path on top of the C-ABI kernels.
+
+Sequences the sm_100a kernels for: InternViT-300M (UPSTREAM ``InternVisionModel``), pixel-shuffle +
+``mlp1`` (``InternVLChatModel.extract_feature``), placeholder substitution
+(reference ``internvl2_model.py:17-144``), Qwen2-0.5B with LoRA folded into scratch weights
+(``llm.py:106-118``; state_dict untouched), KV-cached greedy decoding with the reference's
+``greedy_sample`` semantics (``llm.py:178-250``), the 30-query append pass and the driving heads
+(``driving.py:104-187``, ``adaptors.py:163-180``).
+
+The engine reads weights from a mapping keyed by the reference ``state_dict`` names holding bf16 CUDA
+tensors (normally the live ``nn.Parameter`` storage of ``simlingo_training.models.driving.DrivingModel``).
+All math runs in ``libsimlingo_b200.so``; torch is used for allocation, views and tiny index glue only.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import lib
+from .spec import LLM_PREFIX, MLP1_PREFIX, VIT_PREFIX, ModelSpec
+
+Tensor = torch.Tensor
+PATCH_KPAD = 640  # 588 = 3*14*14 padded to a multiple of 64 (TMA rows must be 16-byte aligned)
+
+
+def _interleave_gate_up(wg: Tensor, wu: Tensor) -> Tensor:
+    """[g0..127, u0..127, g128..255, u128..255, ...] so that one 256-wide GEMM tile holds matching
+    gate / up columns for the fused SwiGLU epilogue."""
+    I, K = wg.shape
+    assert I % 128 == 0
+    return torch.stack([wg.view(I // 128, 128, K), wu.view(I // 128, 128, K)], dim=1).reshape(2 * I, K).contiguous()
+
+
+class Engine:
+    def __init__(self, sd: Dict[str, Tensor], spec: ModelSpec, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("simlingo_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        lib.load()
+        self.spec = spec
+        self.sd = sd
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self._packed_version = None
+        self.launches = 0
+        self.refresh()
+
+    # ------------------------------------------------------------------------------------------
+    # derived (scratch) weights
+    # ------------------------------------------------------------------------------------------
+    def _w(self, name: str) -> Tensor:
+        t = self.sd[name]
+        if t.dtype != torch.bfloat16 or not t.is_cuda:
+            raise RuntimeError(f"engine weight {name} must be a bf16 CUDA tensor, got {t.dtype} on {t.device}")
+        return t.detach()
+
+    def _version(self) -> int:
+        return sum(int(getattr(v, "_version", 0)) for v in self.sd.values())
+
+    def refresh(self, force: bool = True) -> None:
+        """(Re)build the scratch weights derived from the state_dict: zero-padded patch-embed matrix, fused
+        QKV / gate-up matrices and LoRA folded in fp32 (W + (alpha/r) B A) then rounded once to bf16."""
+        ver = self._version()
+        if not force and ver == self._packed_version:
+            return
+        s, w = self.spec, self._w
+        e = VIT_PREFIX + "embeddings."
+        pw = torch.zeros((s.vit_hidden, PATCH_KPAD), device=self.dev, dtype=torch.bfloat16)
+        pw[:, : s.patch_k] = w(e + "patch_embedding.weight").reshape(s.vit_hidden, s.patch_k)
+        self.patch_w = pw
+        sc = s.lora_scale
+
+        def merged(prefix: str) -> Tensor:
+            base = w(prefix + "base_layer.weight").float()
+            a, b = self.sd.get(prefix + "lora_A.default.weight"), self.sd.get(prefix + "lora_B.default.weight")
+            if a is not None:
+                base = base + sc * (b.detach().float() @ a.detach().float())
+            return base
+
+        self.llm_layers = []
+        for i in range(s.llm_layers):
+            p = f"{LLM_PREFIX}model.layers.{i}."
+            qkv = torch.cat([merged(p + f"self_attn.{n}_proj.") for n in "qkv"], 0).to(torch.bfloat16).contiguous()
+            bqkv = torch.cat([w(p + f"self_attn.{n}_proj.base_layer.bias") for n in "qkv"], 0).contiguous()
+            o = merged(p + "self_attn.o_proj.").to(torch.bfloat16).contiguous()
+            gu = _interleave_gate_up(merged(p + "mlp.gate_proj.").to(torch.bfloat16), merged(p + "mlp.up_proj.").to(torch.bfloat16))
+            d = merged(p + "mlp.down_proj.").to(torch.bfloat16).contiguous()
+            self.llm_layers.append(dict(qkv=qkv, bqkv=bqkv, o=o, gu=gu, d=d, ln1=w(p + "input_layernorm.weight"),
+                                        ln2=w(p + "post_attention_layernorm.weight")))
+        a = "adaptors.driving."
+        self.heads_w = lib.HeadsWeights(*[w(a + k).data_ptr() for k in (
+            "route_head.0.weight", "route_head.0.bias", "route_head.2.weight", "route_head.2.bias", "route_head.4.weight",
+            "speed_wps_head.0.weight", "speed_wps_head.0.bias", "speed_wps_head.2.weight")])
+        self.wp_w = lib.WpWeights(*[w("wp_encoder.mlp." + k).data_ptr() for k in (
+            "0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias")])
+        self.queries = torch.cat([w(a + "query_embeds_wps"), w(a + "query_embeds_speed")], 1)[0].contiguous()  # [30, D]
+        self._packed_version = ver
+
+    # ------------------------------------------------------------------------------------------
+    # InternViT + projector
+    # ------------------------------------------------------------------------------------------
+    def vit(self, pixels: Tensor, collect: Optional[list] = None) -> Tensor:
+        """pixels [T,3,448,448] bf16 -> hidden [T*1025, 1024] (after the last encoder layer)."""
+        s, w = self.spec, self._w
+        T = pixels.shape[0]
+        e = VIT_PREFIX + "embeddings."
+        cols = lib.im2col_patch(pixels.contiguous(), PATCH_KPAD)
+        po = lib.gemm(cols, self.patch_w, bias=w(e + "patch_embedding.bias"))
+        x = lib.vit_assemble(po, w(e + "class_embedding"), w(e + "position_embedding"), T)
+        del cols, po
+        N = s.vit_tokens
+        h = torch.empty_like(x)
+        qkv = torch.empty((T * N, 3 * s.vit_hidden), device=self.dev, dtype=torch.bfloat16)
+        att = torch.empty_like(x)
+        f = torch.empty((T * N, s.vit_mlp), device=self.dev, dtype=torch.bfloat16)
+        for i in range(s.vit_layers):
+            p = f"{VIT_PREFIX}encoder.layers.{i}."
+            lib.layernorm(x, w(p + "norm1.weight"), w(p + "norm1.bias"), s.vit_eps, out=h)
+            lib.gemm(h, w(p + "attn.qkv.weight"), out=qkv, bias=w(p + "attn.qkv.bias"))
+            lib.attn_vit(qkv, T, N, s.vit_heads, out=att)
+            lib.gemm(att, w(p + "attn.proj.weight"), out=x, bias=w(p + "attn.proj.bias"), scale_n=w(p + "ls1"), residual=x)
+            lib.layernorm(x, w(p + "norm2.weight"), w(p + "norm2.bias"), s.vit_eps, out=h)
+            lib.gemm(h, w(p + "mlp.fc1.weight"), out=f, bias=w(p + "mlp.fc1.bias"), act=lib.ACT_GELU)
+            lib.gemm(f, w(p + "mlp.fc2.weight"), out=x, bias=w(p + "mlp.fc2.bias"), scale_n=w(p + "ls2"), residual=x)
+            if collect is not None:
+                collect.append(x.clone())
+        self.launches += 3 + 7 * s.vit_layers
+        return x
+
+    def extract_feature(self, pixels: Tensor) -> Tensor:
+        """``InternVLChatModel.extract_feature``: [T,3,448,448] -> [T*256, 896]."""
+        s, w = self.spec, self._w
+        T = pixels.shape[0]
+        x = self.vit(pixels)
+        y = lib.pixel_shuffle_ln(x, w(MLP1_PREFIX + "0.weight"), w(MLP1_PREFIX + "0.bias"), T, s.proj_eps)
+        y = lib.gemm(y, w(MLP1_PREFIX + "1.weight"), bias=w(MLP1_PREFIX + "1.bias"), act=lib.ACT_GELU)
+        self.launches += 3
+        return lib.gemm(y, w(MLP1_PREFIX + "3.weight"), bias=w(MLP1_PREFIX + "3.bias"))
+
+    # ------------------------------------------------------------------------------------------
+    # prompt embeddings with <IMG_CONTEXT> / <TARGET_POINT> substitution
+    # ------------------------------------------------------------------------------------------
+    def wp_rows(self, ids_cpu: Tensor, placeholder_values: Sequence[dict]) -> Tuple[Optional[Tensor], Optional[Tensor], int]:
+        """Host-side bookkeeping of ``replace_placeholder_tokens`` step 2a (internvl2_model.py:54-91): first
+        occurrence of each added special id per row and the coordinates to encode there.  Only
+        ``<TARGET_POINT>`` ever carries values, so one run per row is supported."""
+        s = self.spec
+        B = ids_cpu.shape[0]
+        if placeholder_values is None or len(placeholder_values) == 0:
+            return None, None, 0
+        starts = np.full((B,), -1, dtype=np.int32)
+        coords: List[np.ndarray] = []
+        n_per = 0
+        ids_np = ids_cpu.numpy()
+        for b in range(B):
+            special = sorted(set(ids_np[b][ids_np[b] >= s.first_added_id].tolist()))
+            special = [sid for sid in special if sid in placeholder_values[b]]
+            if not special:
+                continue
+            if len(special) > 1:
+                raise NotImplementedError("more than one placeholder id with values in a prompt")
+            sid = special[0]
+            pos = int(np.nonzero(ids_np[b] == sid)[0][0])
+            if pos == 0:  # reference: first_occurrences.nonzero() drops index 0
+                continue
+            c = np.asarray(placeholder_values[b][sid], dtype=np.float32).reshape(-1, 2)
+            if n_per and c.shape[0] != n_per:
+                raise NotImplementedError("placeholder runs of different length in one batch")
+            n_per = c.shape[0]
+            starts[b] = pos
+            coords.append(c)
+        if not coords:
+            return None, None, 0
+        full = np.zeros((B, n_per, 2), dtype=np.float32)
+        k = 0
+        for b in range(B):
+            if starts[b] >= 0:
+                full[b] = coords[k]
+                k += 1
+        return torch.from_numpy(full), torch.from_numpy(starts), n_per
+
+    def embed_prompt(self, ids: Tensor, pixels: Optional[Tensor], placeholder_values: Optional[Sequence[dict]],
+                     ids_cpu: Optional[Tensor] = None) -> Tensor:
+        """ids [B,L] int64 (cuda), pixels [B,1,NP,3,448,448] bf16 -> language_inputs [B,L,896] with image and
+        waypoint rows substituted (adaptors.py:256 + internvl2_model.py:54-131)."""
+        s = self.spec
+        B, L = ids.shape
+        vit = None
+        n_img = 0
+        if pixels is not None and pixels.numel() > 0 and L != 1:
+            BS, T, NP = pixels.shape[:3]
+            assert T == 1, "Only one frame is supported for now"
+            vit = self.extract_feature(pixels.reshape(BS * NP, *pixels.shape[3:]))
+            n_img = NP * s.tokens_per_tile
+        wp = wp_start = None
+        wp_len = 0
+        if placeholder_values is not None and len(placeholder_values) > 0:
+            if ids_cpu is None:
+                ids_cpu = ids.cpu()
+            coords, starts, wp_len = self.wp_rows(ids_cpu, placeholder_values)
+            if coords is not None:
+                c = coords.to(self.dev, non_blocking=True).to(torch.bfloat16).float()  # wp_encoder dtype is bf16 in the agent
+                wp = lib.wp_encoder(c.reshape(-1, 2).contiguous(), self.wp_w).view(B, wp_len, s.llm_hidden)
+                wp_start = starts.to(self.dev, non_blocking=True)
+                self.launches += 1
+        self.launches += 1
+        return lib.embed_assemble(ids.contiguous(), self._w(LLM_PREFIX + "model.embed_tokens.weight"), vit, wp, wp_start, wp_len,
+                                  s.img_context_id, n_img)
+
+    # ------------------------------------------------------------------------------------------
+    # Qwen2 with KV cache
+    # ------------------------------------------------------------------------------------------
+    def new_cache(self, batch: int, lmax: int) -> Tuple[Tensor, Tensor]:
+        s = self.spec
+        lmax = (lmax + 127) // 128 * 128
+        shape = (s.llm_layers, batch, s.llm_kv_heads, lmax, s.head_dim)
+        return (torch.zeros(shape, device=self.dev, dtype=torch.bfloat16), torch.zeros(shape, device=self.dev, dtype=torch.bfloat16))
+
+    def llm_chunk(self, x: Tensor, batch: int, lq: int, past: int, cache: Tuple[Tensor, Tensor],
+                  key_valid: Optional[Tensor] = None, collect: Optional[list] = None) -> Tensor:
+        """One pass of ``lq`` new positions per sequence through all decoder layers.
+        x [B*lq, 896] (consumed in place) -> residual stream before the final norm."""
+        s = self.spec
+        kc, vc = cache
+        M = batch * lq
+        h = torch.empty_like(x)
+        qkv = torch.empty((M, s.qkv_dim), device=self.dev, dtype=torch.bfloat16)
+        att = torch.empty((M, s.llm_heads * s.head_dim), device=self.dev, dtype=torch.bfloat16)
+        act = torch.empty((M, s.llm_mlp), device=self.dev, dtype=torch.bfloat16)
+        for i, ly in enumerate(self.llm_layers):
+            lib.rmsnorm(x, ly["ln1"], s.rms_eps, out=h)
+            lib.gemm(h, ly["qkv"], out=qkv, bias=ly["bqkv"])
+            lib.rope_kv_write(qkv, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, s.rope_theta)
+            lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, key_valid=key_valid, out=att)
+            lib.gemm(att, ly["o"], out=x, residual=x)
+            lib.rmsnorm(x, ly["ln2"], s.rms_eps, out=h)
+            lib.gemm(h, ly["gu"], out=act, swiglu=True)
+            lib.gemm(act, ly["d"], out=x, residual=x)
+            if collect is not None:
+                collect.append(x.clone())
+        self.launches += 8 * s.llm_layers
+        return x
+
+    def final_norm(self, x: Tensor) -> Tensor:
+        self.launches += 1
+        return lib.rmsnorm(x, self._w(LLM_PREFIX + "model.norm.weight"), self.spec.rms_eps)
+
+    def logits(self, feats: Tensor) -> Tensor:
+        """fp32 logits of the given feature rows (lm_head is not LoRA-wrapped)."""
+        self.launches += 1
+        return lib.gemm(feats, self._w(LLM_PREFIX + "lm_head.weight"), out_fp32=True)
+
+    def heads(self, feats30: Tensor, batch: int, ld_batch: int) -> Tuple[Tensor, Tensor]:
+        self.launches += 2
+        return lib.driving_heads(feats30, ld_batch, self.heads_w, batch)
+
+    # ------------------------------------------------------------------------------------------
+    # DrivingModel.forward (inference): greedy decode + 30-query pass + heads
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, lang_embeds: Tensor, valid: Optional[Tensor], max_new_tokens: int, eos_token_id: Optional[int],
+                 margins: Optional[list] = None):
+        """Batched, KV-cached equivalent of the reference's per-item loop
+        (``driving.py:133-176`` + ``llm.py:178-250``).  lang_embeds [B,L,896]; valid [B,L] bool or None.
+
+        Every sequence is decoded until its own EOS (EOS-prefilled ``sampled_tokens``, the EOS embedding is
+        still appended, ``llm.py:232-248``); then the 30 driving queries are appended after that sequence's
+        last generated token and one more chunk is run *without* key mask (``driving.py:154-156``).
+        Returns (speed_wps [B,10,2] fp32, route [B,20,2] fp32, list of int64 token tensors)."""
+        s = self.spec
+        B, L, D = lang_embeds.shape
+        nq = s.n_queries
+        has_pad = valid is not None and not bool(valid.all())
+        lmax = L + max_new_tokens + nq
+        cache = self.new_cache(B, lmax)
+        kv_valid = None
+        if has_pad:
+            kv_valid = torch.ones((B, cache[0].shape[3]), device=self.dev, dtype=torch.uint8)
+            kv_valid[:, :L] = valid.to(torch.uint8)
+        emb_w = self._w(LLM_PREFIX + "model.embed_tokens.weight")
+        x = self.llm_chunk(lang_embeds.reshape(B * L, D).clone(), B, L, 0, cache, kv_valid)
+        last = self.final_norm(x.view(B, L, D)[:, -1].contiguous())
+        sampled = torch.full((B, max_new_tokens), eos_token_id if eos_token_id is not None else 0, device=self.dev, dtype=torch.int64)
+        done = torch.zeros((B,), device=self.dev, dtype=torch.bool)
+        n_gen = torch.zeros((B,), device=self.dev, dtype=torch.int64)
+        gen_embeds = []
+        steps = 0
+        for i in range(max_new_tokens):
+            lg = self.logits(last)
+            mg = torch.empty((B,), device=self.dev, dtype=torch.float32) if margins is not None else None
+            nxt = lib.argmax(lg, out_margin=mg)
+            self.launches += 1
+            if margins is not None:
+                margins.append(mg)
+            sampled[:, i] = torch.where(done, sampled[:, i], nxt)
+            n_gen += (~done).long()
+            steps = i + 1
+            e = lib.gather_rows(emb_w, nxt)
+            gen_embeds.append(e)
+            if eos_token_id is not None:
+                done = done | (nxt == eos_token_id)
+                if bool(done.all()):  # host sync, as llm.py:245
+                    break
+            if i + 1 < max_new_tokens:
+                x = self.llm_chunk(e.clone(), B, 1, L + i, cache, kv_valid)
+                last = self.final_norm(x)
+        n_gen_cpu = n_gen.tolist()
+        toks = [sampled[b, : max(n_gen_cpu[b], 1)] for b in range(B)]
+        # 30-query append: positions L+G_b .. L+G_b+29, no key mask (driving.py:154-156)
+        route = torch.empty((B, s.n_route, 2), device=self.dev, dtype=torch.float32)
+        speed = torch.empty((B, s.n_speed, 2), device=self.dev, dtype=torch.float32)
+        if has_pad:
+            # the reference re-runs prompt + generated + queries from scratch without a mask, so pads are
+            # attended by every position: recompute exactly that for padded rows
+            for b in range(B):
+                G = n_gen_cpu[b]
+                seq = torch.cat([lang_embeds[b], torch.cat([g[b:b + 1] for g in gen_embeds[:G]], 0), self.queries], 0)
+                c1 = self.new_cache(1, seq.shape[0])
+                xx = self.llm_chunk(seq.clone(), 1, seq.shape[0], 0, c1, None)
+                f = self.final_norm(xx[-nq:].contiguous())
+                r, sp = self.heads(f, 1, nq * D)
+                route[b], speed[b] = r[0], sp[0]
+        elif all(g == steps for g in n_gen_cpu):
+            # every sequence stopped on its last sampled token, whose K/V are not cached yet (decoding stops right
+            # after sampling it): run [last token | 30 queries] as one 31-row chunk at positions L+G-1 .. L+G+29
+            G = steps
+            chunk = torch.cat([gen_embeds[G - 1].view(B, 1, D), self.queries.unsqueeze(0).expand(B, nq, D)], 1)
+            xx = self.llm_chunk(chunk.reshape(B * (nq + 1), D).contiguous(), B, nq + 1, L + G - 1, cache, None)
+            f = self.final_norm(xx.view(B, nq + 1, D)[:, 1:].reshape(B * nq, D).contiguous())
+            route, speed = self.heads(f, B, nq * D)
+        else:
+            # sequences ended at different lengths: cache the final sampled token for everybody, then append the
+            # queries group-wise at each group's own offset (rows beyond a sequence's end are overwritten / never
+            # visible under the causal mask)
+            self.llm_chunk(gen_embeds[steps - 1].clone(), B, 1, L + steps - 1, cache, None)
+            for G in sorted(set(n_gen_cpu)):
+                idx = [b for b in range(B) if n_gen_cpu[b] == G]
+                ii = torch.tensor(idx, device=self.dev)
+                sub = (cache[0][:, ii].contiguous(), cache[1][:, ii].contiguous())
+                q = self.queries.unsqueeze(0).expand(len(idx), nq, D).reshape(len(idx) * nq, D).clone()
+                xx = self.llm_chunk(q, len(idx), nq, L + G, sub, None)
+                r, sp = self.heads(self.final_norm(xx), len(idx), nq * D)
+                route[ii], speed[ii] = r, sp
+        return speed, route, toks
+
+    @torch.no_grad()
+    def driving_forward(self, camera_images: Tensor, phrase_ids: Tensor, phrase_valid: Tensor, placeholder_values,
+                        max_new_tokens: int = 100, eos_token_id: Optional[int] = None, margins: Optional[list] = None,
+                        ids_cpu: Optional[Tensor] = None):
+        emb = self.embed_prompt(phrase_ids, camera_images, placeholder_values, ids_cpu)
+        return self.generate(emb, phrase_valid, max_new_tokens, eos_token_id, margins)
+
+    # ------------------------------------------------------------------------------------------
+    # teacher-forced single pass (DrivingModel.forward_model; BASELINE config 3 "offline batched forward")
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_model(self, inputs: Tensor, inputs_mask: Optional[Tensor], want_logits_rows: Optional[Tensor] = None):
+        """inputs [B, L+30, 896] (already permuted "valid first"), mask [B, L+30] -> (features [B,L+30,896]
+        after the final norm, fp32 logits for the requested flat row indices or None)."""
+        s = self.spec
+        B, Lt, D = inputs.shape
+        cache = self.new_cache(B, Lt)
+        kv_valid = None
+        if inputs_mask is not None and not bool(inputs_mask.all()):
+            kv_valid = torch.zeros((B, cache[0].shape[3]), device=self.dev, dtype=torch.uint8)
+            kv_valid[:, :Lt] = inputs_mask.to(torch.uint8)
+        x = self.llm_chunk(inputs.reshape(B * Lt, D).clone(), B, Lt, 0, cache, kv_valid)
+        feats = self.final_norm(x)
+        lg = None
+        if want_logits_rows is not None:
+            lg = self.logits(feats[want_logits_rows].contiguous())
+        return feats.view(B, Lt, D), lg
