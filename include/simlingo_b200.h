@@ -91,6 +91,8 @@ int slb_embed_assemble(const int64_t* ids, const void* table, const void* vit, c
                        int wp_len, void* out, int batch, int len, int hidden, int vocab, int img_id, int n_img,
                        void* stream);
 int slb_gather_rows(const void* src, const int64_t* idx, void* dst, int n, int cols, int64_t src_rows, void* stream);
+/* dst[idx[i]] = src[i] (the `inputs_embeds[selected] = vit_embeds` scatter of internvl2_model.py:124) */
+int slb_scatter_rows(void* dst, const int64_t* idx, const void* src, int n, int cols, int64_t dst_rows, void* stream);
 
 /* ---- elementwise helpers ---- */
 int slb_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);

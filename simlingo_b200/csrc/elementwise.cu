@@ -266,6 +266,17 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ src, const long long
   }
 }
 
+__global__ void scatter_rows_kernel(bf16* __restrict__ dst, const long long* __restrict__ idx, const bf16* __restrict__ src, int n,
+                                    int cols, long long dst_rows) {
+  const int vpr = cols >> 3;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n * vpr; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vpr), vi = (int)(i % vpr);
+    const long long d = idx[r];
+    if (d < 0 || d >= dst_rows) continue;
+    *reinterpret_cast<uint4*>(dst + (size_t)d * cols + vi * 8) = *reinterpret_cast<const uint4*>(src + (size_t)r * cols + vi * 8);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // simple elementwise
 // ------------------------------------------------------------------------------------------------
@@ -507,6 +518,14 @@ extern "C" int slb_embed_assemble(const int64_t* ids, const void* table, const v
 extern "C" int slb_gather_rows(const void* src, const int64_t* idx, void* dst, int n, int cols, int64_t src_rows, void* stream) {
   SLB_CHECK_ARG(n > 0 && (cols % 8) == 0, "gather_rows: n=%d cols=%d", n, cols);
   gather_rows_kernel<<<grid_for((size_t)n * (cols / 8), 128), 128, 0, ST(stream)>>>((const bf16*)src, (const long long*)idx, (bf16*)dst, n, cols, src_rows);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_scatter_rows(void* dst, const int64_t* idx, const void* src, int n, int cols, int64_t dst_rows, void* stream) {
+  SLB_CHECK_ARG(n >= 0 && (cols % 8) == 0, "scatter_rows: n=%d cols=%d", n, cols);
+  if (n == 0) return SLB_OK;
+  scatter_rows_kernel<<<grid_for((size_t)n * (cols / 8), 128), 128, 0, ST(stream)>>>((bf16*)dst, (const long long*)idx, (const bf16*)src, n, cols, dst_rows);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

@@ -59,15 +59,18 @@ class Engine:
 
     def refresh(self, force: bool = True) -> None:
         """(Re)build the scratch weights derived from the state_dict: zero-padded patch-embed matrix, fused
-        QKV / gate-up matrices and LoRA folded in fp32 (W + (alpha/r) B A) then rounded once to bf16."""
+        QKV / gate-up matrices and LoRA folded in fp32 (W + (alpha/r) B A) then rounded once to bf16.
+        Parts whose keys are absent (an engine owned by a sub-module) are skipped."""
         ver = self._version()
         if not force and ver == self._packed_version:
             return
         s, w = self.spec, self._w
         e = VIT_PREFIX + "embeddings."
-        pw = torch.zeros((s.vit_hidden, PATCH_KPAD), device=self.dev, dtype=torch.bfloat16)
-        pw[:, : s.patch_k] = w(e + "patch_embedding.weight").reshape(s.vit_hidden, s.patch_k)
-        self.patch_w = pw
+        self.has_vit = (e + "patch_embedding.weight") in self.sd
+        if self.has_vit:
+            pw = torch.zeros((s.vit_hidden, PATCH_KPAD), device=self.dev, dtype=torch.bfloat16)
+            pw[:, : s.patch_k] = w(e + "patch_embedding.weight").reshape(s.vit_hidden, s.patch_k)
+            self.patch_w = pw
         sc = s.lora_scale
 
         def merged(prefix: str) -> Tensor:
@@ -78,7 +81,8 @@ class Engine:
             return base
 
         self.llm_layers = []
-        for i in range(s.llm_layers):
+        self.has_llm = (LLM_PREFIX + "model.norm.weight") in self.sd
+        for i in range(s.llm_layers if self.has_llm else 0):
             p = f"{LLM_PREFIX}model.layers.{i}."
             qkv = torch.cat([merged(p + f"self_attn.{n}_proj.") for n in "qkv"], 0).to(torch.bfloat16).contiguous()
             bqkv = torch.cat([w(p + f"self_attn.{n}_proj.base_layer.bias") for n in "qkv"], 0).contiguous()
@@ -88,12 +92,14 @@ class Engine:
             self.llm_layers.append(dict(qkv=qkv, bqkv=bqkv, o=o, gu=gu, d=d, ln1=w(p + "input_layernorm.weight"),
                                         ln2=w(p + "post_attention_layernorm.weight")))
         a = "adaptors.driving."
-        self.heads_w = lib.HeadsWeights(*[w(a + k).data_ptr() for k in (
-            "route_head.0.weight", "route_head.0.bias", "route_head.2.weight", "route_head.2.bias", "route_head.4.weight",
-            "speed_wps_head.0.weight", "speed_wps_head.0.bias", "speed_wps_head.2.weight")])
-        self.wp_w = lib.WpWeights(*[w("wp_encoder.mlp." + k).data_ptr() for k in (
-            "0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias")])
-        self.queries = torch.cat([w(a + "query_embeds_wps"), w(a + "query_embeds_speed")], 1)[0].contiguous()  # [30, D]
+        if (a + "route_head.0.weight") in self.sd:
+            self.heads_w = lib.HeadsWeights(*[w(a + k).data_ptr() for k in (
+                "route_head.0.weight", "route_head.0.bias", "route_head.2.weight", "route_head.2.bias", "route_head.4.weight",
+                "speed_wps_head.0.weight", "speed_wps_head.0.bias", "speed_wps_head.2.weight")])
+            self.queries = torch.cat([w(a + "query_embeds_wps"), w(a + "query_embeds_speed")], 1)[0].contiguous()  # [30, D]
+        if "wp_encoder.mlp.0.weight" in self.sd:
+            self.wp_w = lib.WpWeights(*[w("wp_encoder.mlp." + k).data_ptr() for k in (
+                "0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias")])
         self._packed_version = ver
 
     # ------------------------------------------------------------------------------------------

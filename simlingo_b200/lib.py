@@ -204,6 +204,15 @@ def gather_rows(src, idx, out=None):
     return out
 
 
+def scatter_rows(dst, idx, src):
+    """dst[idx[i]] = src[i] in place; dst must be a contiguous 2-D bf16 view."""
+    _bf16(dst, src)
+    assert dst.is_contiguous() and src.is_contiguous() and idx.dtype == torch.int64 and idx.is_cuda
+    _check(load().slb_scatter_rows(_p(dst), _p(idx.contiguous()), _p(src), idx.numel(), dst.shape[1], C.c_int64(dst.shape[0]), _stream()),
+           "scatter_rows")
+    return dst
+
+
 def silu_mul(g, u, out=None):
     _bf16(g, u)
     out = torch.empty_like(g) if out is None else out
