@@ -418,9 +418,11 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float,
     return p, m, v
 
 
-def one_cycle_lr(step: int, total_steps: int, max_lr: float, pct_start: float = 0.05,
-                 div_factor: float = 25.0, final_div_factor: float = 1e4) -> float:
-    """torch.optim.lr_scheduler.OneCycleLR (cos anneal, two phases) as used at driving.py:729-731."""
+def one_cycle(step: int, total_steps: int, max_lr: float, pct_start: float = 0.05, div_factor: float = 25.0,
+              final_div_factor: float = 1e4, base_momentum: float = 0.85, max_momentum: float = 0.95):
+    """torch.optim.lr_scheduler.OneCycleLR (cos anneal, two phases) as used at driving.py:729-731 -> (lr, beta1).
+    The reference keeps the default ``cycle_momentum=True``: the scheduler overwrites AdamW's beta1 every step,
+    annealing it 0.95 -> 0.85 while the lr warms up and back to 0.95 while it decays."""
     initial = max_lr / div_factor
     min_lr = initial / final_div_factor
     up_end = float(pct_start * total_steps) - 1
@@ -430,5 +432,11 @@ def one_cycle_lr(step: int, total_steps: int, max_lr: float, pct_start: float = 
         return b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1)
 
     if step <= up_end:
-        return cos(initial, max_lr, step / up_end if up_end > 0 else 1.0)
-    return cos(max_lr, min_lr, (step - up_end) / (down_end - up_end))
+        pct = step / up_end if up_end > 0 else 1.0
+        return cos(initial, max_lr, pct), cos(max_momentum, base_momentum, pct)
+    pct = (step - up_end) / (down_end - up_end)
+    return cos(max_lr, min_lr, pct), cos(base_momentum, max_momentum, pct)
+
+
+def one_cycle_lr(step: int, total_steps: int, max_lr: float, pct_start: float = 0.05) -> float:
+    return one_cycle(step, total_steps, max_lr, pct_start)[0]

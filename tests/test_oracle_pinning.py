@@ -114,10 +114,11 @@ def test_adamw_and_onecycle_match_torch():
     q, m, v = p.detach().clone(), torch.zeros(64), torch.zeros(64)
     for step in range(1, 6):
         g = torch.randn(64)
-        lr = O.one_cycle_lr(step - 1, 50, 3e-5, 0.05)
+        lr, beta1 = O.one_cycle(step - 1, 50, 3e-5, 0.05)
         assert abs(lr - opt.param_groups[0]["lr"]) < 1e-12
+        assert abs(beta1 - opt.param_groups[0]["betas"][0]) < 1e-12  # OneCycleLR cycles AdamW's beta1 (cycle_momentum)
         p.grad = g.clone()
         opt.step()
         sched.step()
-        q, m, v = O.adamw_step(q, g, m, v, step, lr)
+        q, m, v = O.adamw_step(q, g, m, v, step, lr, beta1=beta1)
         assert torch.allclose(q, p.detach(), atol=2e-6, rtol=0)
