@@ -329,8 +329,14 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 }  // namespace
 
+int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_tokens, int heads, cudaStream_t stream, int* rc_out);
+
 extern "C" int slb_attn_vit_fwd(const void* qkv, void* out, float* lse, int tiles, int n_tokens, int heads, void* stream) {
   SLB_CHECK_ARG(tiles > 0 && n_tokens > 0 && heads > 0, "attn_vit: bad shape");
+  {
+    int rc2 = SLB_OK;
+    if (slb_attn_vit2_try(qkv, out, lse, tiles, n_tokens, heads, (cudaStream_t)stream, &rc2)) return rc2;
+  }
   const int C = heads * HD;
   CUtensorMap tm;
   int rc = slb_make_tmap_3d(&tm, qkv, (uint64_t)3 * C, (uint64_t)n_tokens, (uint64_t)tiles, (uint64_t)3 * C * 2,

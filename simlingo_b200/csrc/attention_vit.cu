@@ -1,0 +1,344 @@
+// InternViT attention, second generation (bidirectional, head_dim 64, n_tokens = 1 + 256*k, CLS at row 0).
+//
+//   One CTA per (256 patch-token queries, head, tile), one CTA per SM, 12 warps (setmaxnreg re-balanced):
+//     warp 0      TMA producer: Q0,Q1 once, then K_j/V_j (128 keys) through a 3-stage ring
+//     warp 1      MMA issuer:  S_g = Q_g K_j^T (128x128x64) and O_g += P_g V_j (128x64x128) on tcgen05,
+//                 ping-ponging between the two query halves g = 0,1 so that one half's softmax overlaps the other
+//                 half's MMAs.  O_g accumulates in TMEM across all key blocks.
+//     warps 4-7   softmax warpgroup 0 (thread <-> query row <-> TMEM lane), warps 8-11 softmax warpgroup 1:
+//                 single TMEM pass (the 128 scores of the row live in registers), exp2 with a *lazy* running
+//                 maximum (O/l are rescaled only when the maximum grows by more than 2^8, FA4-style), P written
+//                 to shared memory in the K-major 128B-swizzled UMMA layout.
+//   The CLS token is peeled off the tensor-core tiling: as a *key* it is folded in by the softmax threads
+//   (one 64-long dot product per row, added to O in the epilogue); as a *query* it is handled by a tiny
+//   CUDA-core kernel (one block per (tile, head)).  That keeps every MMA tile full: 1025 = 1 + 8*128.
+#include "common.cuh"
+#include "../../include/simlingo_b200.h"
+
+namespace {
+
+constexpr int HD = 64, BQ = 128, BKV = 128, NSTAGE = 3;
+constexpr int V2_THREADS = 384;  // 3 warpgroups: {TMA, MMA, 2 idle}, softmax 0, softmax 1
+constexpr int kTile = BQ * HD * 2;            // 16 KB: one 128 x 64 bf16 operand tile
+constexpr int kSmQ = 0;                       // 2 tiles
+constexpr int kSmK = kSmQ + 2 * kTile;        // NSTAGE tiles
+constexpr int kSmV = kSmK + NSTAGE * kTile;   // NSTAGE tiles
+constexpr int kSmP = kSmV + NSTAGE * kTile;   // 2 x 32 KB
+constexpr int kSmBar = kSmP + 2 * (BQ * BKV * 2);
+constexpr int kSmTotal = kSmBar + 256;
+constexpr float kLazyThreshold = 8.0f;        // log2 units
+
+struct Vit2Params {
+  const bf16* qkv;   // [tiles * n_tokens, 3C]
+  bf16* out;         // [tiles * n_tokens, C]
+  float* lse;        // [tiles, heads, n_tokens] or null
+  int n_tokens, heads, nkv;
+  float scale_log2;
+};
+
+__device__ __forceinline__ float max32(const uint32_t (&s)[32], float m) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(s[i]));
+  return m;
+}
+
+// p = exp2(s * scale - mref) for 32 scores; accumulates the row sum; writes 64 bytes (4 x 16 B chunks) of P.
+__device__ __forceinline__ float exp_store32(const uint32_t (&s)[32], float scale, float mref, uint8_t* half_row, int chunk0, int rsw) {
+  float sum = 0.f;
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float a = ex2_approx(fmaf(__uint_as_float(s[2 * i]), scale, -mref));
+    const float b = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), scale, -mref));
+    sum += a + b;
+    pk[i] = pack_bf16(a, b);
+  }
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4)
+    *reinterpret_cast<uint4*>(half_row + (((chunk0 + q4) ^ rsw) << 4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+  return sum;
+}
+
+__global__ void __launch_bounds__(V2_THREADS, 1)
+attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmBar);
+  uint64_t* q_full = bars;              // 1
+  uint64_t* kv_full = bars + 1;         // NSTAGE
+  uint64_t* kv_empty = bars + 4;        // NSTAGE
+  uint64_t* s_full = bars + 7;          // 2
+  uint64_t* p_full = bars + 9;          // 2
+  uint64_t* o_done = bars + 11;         // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, t = blockIdx.z;
+  const int C = p.heads * HD;
+  const int q0 = 1 + qb * 2 * BQ;  // first patch-token row of this CTA inside the tile (row 0 is CLS)
+  const int nkv = p.nkv;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023) != 0) __trap();
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&o_done[g], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // register re-balancing between warpgroups (the kernel is launched at 168 regs/thread = 65536 / 384)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * kTile);
+      tma_load_3d(smem + kSmQ, &tmap, q_full, h * HD, q0, t);
+      tma_load_3d(smem + kSmQ + kTile, &tmap, q_full, h * HD, q0 + BQ, t);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % NSTAGE, use = j / NSTAGE;
+        mbar_wait(&kv_empty[st], (use & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * kTile);
+        tma_load_3d(smem + kSmK + st * kTile, &tmap, &kv_full[st], C + h * HD, 1 + j * BKV, t);
+        tma_load_3d(smem + kSmV + st * kTile, &tmap, &kv_full[st], 2 * C + h * HD, 1 + j * BKV, t);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);
+      const uint32_t sq = smem_u32(smem + kSmQ), sk = smem_u32(smem + kSmK), sv = smem_u32(smem + kSmV), sp = smem_u32(smem + kSmP);
+      auto issue_s = [&](int g, int j) {
+        const uint64_t dq = umma_desc_kmajor_sw128(sq + g * kTile);
+        const uint64_t dk = umma_desc_kmajor_sw128(sk + (j % NSTAGE) * kTile);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_base + g * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc_commit(&s_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % NSTAGE;
+        const uint64_t dv = umma_desc_mnmajor_sw128(sv + st * kTile, kTile);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_full[g], j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            const uint64_t dp = umma_desc_kmajor_sw128(sp + g * (BQ * BKV * 2) + (k >> 2) * (BQ * 128)) + 2 * (k & 3);
+            tc_mma_bf16(tmem_base + 256 + g * HD, dp, dv + (uint64_t)k * (16 * 128 >> 4), idesc_o, (j | k) != 0);
+          }
+          tc_commit(&o_done[g]);
+          if (j + 1 < nkv) {
+            if (g == 0) {
+              mbar_wait(&kv_full[(j + 1) % NSTAGE], ((j + 1) / NSTAGE) & 1);
+              tc_fence_after();
+            }
+            issue_s(g, j + 1);
+          }
+        }
+        tc_commit(&kv_empty[st]);
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ---------------- softmax warpgroups ----------------
+    const int g = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int row = q0 + g * BQ + r;  // token index inside the tile
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t tmem_s = tmem_base + g * BKV + lane_off;
+    const uint32_t tmem_o = tmem_base + 256 + g * HD + lane_off;
+    uint8_t* prow = smem + kSmP + g * (BQ * BKV * 2) + r * 128;
+    const int rsw = r & 7;
+    const float scale = p.scale_log2;
+    const bf16* kcls = p.qkv + (size_t)t * p.n_tokens * 3 * C + C + h * HD;
+    const bf16* vcls = kcls + C;
+
+    // CLS key: s_cls = q_row . k_cls (log2 domain), folded in as the initial state of the online softmax
+    mbar_wait(q_full, 0);
+    float s_cls = 0.f;
+    {
+      const uint8_t* qrow = smem + kSmQ + g * kTile + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ rsw) << 4));
+        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kcls) + c);
+        const float2 q0f = unpack_bf16(qv.x), q1f = unpack_bf16(qv.y), q2f = unpack_bf16(qv.z), q3f = unpack_bf16(qv.w);
+        const float2 k0f = unpack_bf16(kv.x), k1f = unpack_bf16(kv.y), k2f = unpack_bf16(kv.z), k3f = unpack_bf16(kv.w);
+        s_cls += q0f.x * k0f.x + q0f.y * k0f.y + q1f.x * k1f.x + q1f.y * k1f.y + q2f.x * k2f.x + q2f.y * k2f.y + q3f.x * k3f.x + q3f.y * k3f.y;
+      }
+      s_cls *= scale;
+    }
+    float m_ref = s_cls;  // running (lazy) maximum, log2 domain
+    float l_run = 1.0f;   // exp2(s_cls - m_ref)
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld_32x32(tmem_s + 0, s0);
+      tmem_ld_32x32(tmem_s + 32, s1);
+      tmem_ld_32x32(tmem_s + 64, s2);
+      tmem_ld_32x32(tmem_s + 96, s3);
+      tmem_ld_wait();
+      float m_blk = max32(s0, -INFINITY);
+      m_blk = max32(s1, m_blk);
+      m_blk = max32(s2, m_blk);
+      m_blk = max32(s3, m_blk);
+      const float m_new = fmaxf(m_ref, m_blk * scale);
+      const bool grow = m_new > m_ref + kLazyThreshold;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float f = grow ? ex2_approx(m_ref - m_new) : 1.0f;
+        if (grow) { m_ref = m_new; l_run *= f; }
+        if (j > 0) {
+          mbar_wait(&o_done[g], (j - 1) & 1);  // every PV MMA issued so far has landed in TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < HD; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(tmem_o + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x32(tmem_o + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      float l_blk = exp_store32(s0, scale, m_ref, prow, 0, rsw);
+      l_blk += exp_store32(s1, scale, m_ref, prow, 4, rsw);
+      l_blk += exp_store32(s2, scale, m_ref, prow + BQ * 128, 0, rsw);
+      l_blk += exp_store32(s3, scale, m_ref, prow + BQ * 128, 4, rsw);
+      l_run += l_blk;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+    }
+    // epilogue: O / l (+ the CLS key's contribution)
+    mbar_wait(&o_done[g], (nkv - 1) & 1);
+    tc_fence_after();
+    const float p_cls = ex2_approx(s_cls - m_ref);
+    const float inv = 1.0f / l_run;
+    bf16* orow = p.out + ((size_t)t * p.n_tokens + row) * C + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32(tmem_o + c, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int v8 = 0; v8 < 4; ++v8) {
+        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vcls + c) + v8);
+        const float2 a = unpack_bf16(vv.x), b = unpack_bf16(vv.y), cc = unpack_bf16(vv.z), d = unpack_bf16(vv.w);
+        const float vf[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+        float of[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) of[e] = (__uint_as_float(o[v8 * 8 + e]) + p_cls * vf[e]) * inv;
+        uint4 u;
+        u.x = pack_bf16(of[0], of[1]); u.y = pack_bf16(of[2], of[3]); u.z = pack_bf16(of[4], of[5]); u.w = pack_bf16(of[6], of[7]);
+        *reinterpret_cast<uint4*>(orow + c + v8 * 8) = u;
+      }
+    }
+    if (p.lse) p.lse[((size_t)t * p.heads + h) * p.n_tokens + row] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// CLS query row: one block per (tile, head), 128 threads, all n_tokens keys.
+__global__ void __launch_bounds__(128)
+attn_vit_cls_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int n_tokens, int heads, float scale) {
+  extern __shared__ float sm[];
+  float* qs = sm;             // 64
+  float* red = sm + 64;       // 8 + 128
+  float* sc = sm + 64 + 136;  // n_tokens
+  const int h = blockIdx.x, t = blockIdx.y;
+  const int C = heads * HD, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bf16* base = qkv + (size_t)t * n_tokens * 3 * C;
+  if (tid < 64) qs[tid] = __bfloat162float(base[h * HD + tid]) * scale;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < n_tokens; j += 128) {
+    const uint4* kr = reinterpret_cast<const uint4*>(base + (size_t)j * 3 * C + C + h * HD);
+    float s = 0.f;
+#pragma unroll
+    for (int v8 = 0; v8 < 8; ++v8) {
+      const uint4 u = kr[v8];
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      const float* qq = qs + v8 * 8;
+      s += a.x * qq[0] + a.y * qq[1] + b.x * qq[2] + b.y * qq[3] + c.x * qq[4] + c.y * qq[5] + d.x * qq[6] + d.y * qq[7];
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float sum = 0.f;
+  for (int j = tid; j < n_tokens; j += 128) {
+    const float e = __expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[4 + warp] = sum;
+  __syncthreads();
+  sum = red[4] + red[5] + red[6] + red[7];
+  const int d = tid & 63, part = tid >> 6;
+  float acc = 0.f;
+  for (int j = part; j < n_tokens; j += 2) acc += sc[j] * __bfloat162float(base[(size_t)j * 3 * C + 2 * C + h * HD + d]);
+  red[8 + tid] = acc;
+  __syncthreads();
+  if (tid < 64) out[(size_t)t * n_tokens * C + h * HD + tid] = __float2bfloat16((red[8 + tid] + red[8 + 64 + tid]) / sum);
+  if (tid == 0 && lse) lse[((size_t)t * heads + h) * n_tokens] = mx + logf(sum);
+}
+
+}  // namespace
+
+// returns 1 if the specialised kernel applies (and was launched), 0 if the caller should use the generic kernel
+int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_tokens, int heads, cudaStream_t stream, int* rc_out) {
+  *rc_out = SLB_OK;
+  if (n_tokens < 257 || ((n_tokens - 1) % 256) != 0) return 0;
+  const int C = heads * HD;
+  CUtensorMap tm;
+  int rc = slb_make_tmap_3d(&tm, qkv, (uint64_t)3 * C, (uint64_t)n_tokens, (uint64_t)tiles, (uint64_t)3 * C * 2,
+                            (uint64_t)n_tokens * 3 * C * 2, HD, BQ, 1);
+  if (rc) { *rc_out = rc; return 1; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_vit2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal);
+    if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_vit2 smem attr: %s", cudaGetErrorString(e)); return 1; }
+    attr_set = true;
+  }
+  Vit2Params p;
+  p.qkv = (const bf16*)qkv; p.out = (bf16*)out; p.lse = lse;
+  p.n_tokens = n_tokens; p.heads = heads; p.nkv = (n_tokens - 1) / BKV;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid((n_tokens - 1) / (2 * BQ), heads, tiles);
+  attn_vit2_kernel<<<grid, V2_THREADS, kSmTotal, stream>>>(tm, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_vit2 launch: %s", cudaGetErrorString(e)); return 1; }
+  const size_t smem = (64 + 136 + (size_t)n_tokens) * sizeof(float);
+  attn_vit_cls_kernel<<<dim3(heads, tiles), 128, smem, stream>>>((const bf16*)qkv, (bf16*)out, lse, n_tokens, heads, 0.125f);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) *rc_out = slb_fail(SLB_ECUDA, "attn_vit_cls launch: %s", cudaGetErrorString(e));
+  return 1;
+}
