@@ -250,7 +250,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    model = build_model(spec, device)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # the reference's constructors print banners; stdout carries the JSON line only
+        model = build_model(spec, device)
     eng = model._engine()
     B = args.frames
     hb = host_batch(spec, B, 1234 + rank)

@@ -1,8 +1,9 @@
 // InternViT attention, second generation (bidirectional, head_dim 64, n_tokens = 1 + 256*k, CLS at row 0).
 //
 //   One CTA per (256 patch-token queries, head, tile), one CTA per SM, 12 warps (setmaxnreg re-balanced):
-//     warp 0      TMA producer: Q0,Q1 once, then K_j/V_j (128 keys) through a 3-stage ring
-//     warp 1      MMA issuer:  S_g = Q_g K_j^T (128x128x64) and O_g += P_g V_j (128x64x128) on tcgen05,
+//     warp 0 / 3  TMA producers: Q0,Q1 once + the K_j stream / the V_j stream (128 keys per tile, 2-deep rings;
+//                 a K tile is recycled right after its S MMAs, a V tile after its PV MMAs)
+//     warps 1,2   MMA issuers (one per query half g): S_g = Q_g K_j^T (128x128x64), O_g += P_g V_j (128x64x128),
 //                 ping-ponging between the two query halves g = 0,1 so that one half's softmax overlaps the other
 //                 half's MMAs.  O_g accumulates in TMEM across all key blocks.
 //     warps 4-7   softmax warpgroup 0 (thread <-> query row <-> TMEM lane), warps 8-11 softmax warpgroup 1:
@@ -17,14 +18,15 @@
 
 namespace {
 
-constexpr int HD = 64, BQ = 128, BKV = 128, NSTAGE = 3;
+constexpr int HD = 64, BQ = 128, BKV = 128, NSTAGE = 2;
 constexpr int V2_THREADS = 384;  // 3 warpgroups: {TMA, MMA, 2 idle}, softmax 0, softmax 1
 constexpr int kTile = BQ * HD * 2;            // 16 KB: one 128 x 64 bf16 operand tile
 constexpr int kSmQ = 0;                       // 2 tiles
 constexpr int kSmK = kSmQ + 2 * kTile;        // NSTAGE tiles
 constexpr int kSmV = kSmK + NSTAGE * kTile;   // NSTAGE tiles
-constexpr int kSmP = kSmV + NSTAGE * kTile;   // 2 x 32 KB
-constexpr int kSmBar = kSmP + 2 * (BQ * BKV * 2);
+constexpr int kSmP = kSmV + NSTAGE * kTile;   // [g][buffer] : 4 x 32 KB (P double-buffered per query half)
+constexpr int kPBuf = BQ * BKV * 2;
+constexpr int kSmBar = kSmP + 4 * kPBuf;
 constexpr int kSmTotal = kSmBar + 256;
 constexpr float kLazyThreshold = 8.0f;        // log2 units
 
@@ -36,27 +38,50 @@ struct Vit2Params {
   float scale_log2;
 };
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ float max32(const uint32_t (&s)[32], float m) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(s[i]));
+  for (int i = 0; i < 32; i += 2) m = fmax3(m, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
   return m;
 }
+// (a, b) * (sc, sc) + (-m, -m) on the packed fp32x2 pipe
+__device__ __forceinline__ void ffma2(float& a, float& b, uint64_t sc2, uint64_t nm2) {
+  uint64_t v, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(v), "l"(sc2), "l"(nm2));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d));
+}
+__device__ __forceinline__ uint64_t pack2f(float a, float b) {
+  uint64_t v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  return v;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
-// p = exp2(s * scale - mref) for 32 scores; accumulates the row sum; writes 64 bytes (4 x 16 B chunks) of P.
-__device__ __forceinline__ float exp_store32(const uint32_t (&s)[32], float scale, float mref, uint8_t* half_row, int chunk0, int rsw) {
-  float sum = 0.f;
+// p = exp2(s * scale - mref) for 32 scores; accumulates the (packed) row sum; writes 64 bytes (4 x 16 B chunks) of P.
+__device__ __forceinline__ void exp_store32(const uint32_t (&s)[32], uint64_t sc2, uint64_t nm2, uint64_t& sum2, uint8_t* half_row,
+                                            int chunk0, int rsw) {
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float a = ex2_approx(fmaf(__uint_as_float(s[2 * i]), scale, -mref));
-    const float b = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), scale, -mref));
-    sum += a + b;
+    float a = __uint_as_float(s[2 * i]), b = __uint_as_float(s[2 * i + 1]);
+    ffma2(a, b, sc2, nm2);
+    a = ex2_approx(a);
+    b = ex2_approx(b);
+    sum2 = fadd2(sum2, pack2f(a, b));
     pk[i] = pack_bf16(a, b);
   }
 #pragma unroll
   for (int q4 = 0; q4 < 4; ++q4)
     *reinterpret_cast<uint4*>(half_row + (((chunk0 + q4) ^ rsw) << 4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-  return sum;
 }
 
 __global__ void __launch_bounds__(V2_THREADS, 1)
@@ -64,12 +89,15 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmBar);
   uint64_t* q_full = bars;              // 1
-  uint64_t* kv_full = bars + 1;         // NSTAGE
-  uint64_t* kv_empty = bars + 4;        // NSTAGE
-  uint64_t* s_full = bars + 7;          // 2
-  uint64_t* p_full = bars + 9;          // 2
-  uint64_t* o_done = bars + 11;         // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* k_full = bars + 1;          // NSTAGE
+  uint64_t* k_empty = bars + 3;         // NSTAGE (both MMA warps commit after their S)
+  uint64_t* v_full = bars + 5;          // NSTAGE
+  uint64_t* v_empty = bars + 7;         // NSTAGE (both MMA warps commit after their PV)
+  uint64_t* s_full = bars + 9;          // [g]
+  uint64_t* p_full = bars + 11;         // [g]
+  uint64_t* s_free = bars + 13;         // [g]: softmax g has pulled S_g(j) into registers
+  uint64_t* o_done = bars + 15;         // [g][j & 1]: PV_g(j) (and everything issued before it) has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, t = blockIdx.z;
@@ -81,8 +109,14 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
     if ((smem_u32(smem) & 1023) != 0) __trap();
     tma_prefetch_desc(&tmap);
     mbar_init(q_full, 1);
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&o_done[g], 1); }
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&s_free[g], 4);
+      mbar_init(&o_done[2 * g], 1); mbar_init(&o_done[2 * g + 1], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -98,56 +132,66 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0) {  // Q once, then the K stream (a K tile is free again as soon as both S MMAs that read it retire)
       mbar_expect_tx(q_full, 2 * kTile);
       tma_load_3d(smem + kSmQ, &tmap, q_full, h * HD, q0, t);
       tma_load_3d(smem + kSmQ + kTile, &tmap, q_full, h * HD, q0 + BQ, t);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % NSTAGE, use = j / NSTAGE;
-        mbar_wait(&kv_empty[st], (use & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * kTile);
-        tma_load_3d(smem + kSmK + st * kTile, &tmap, &kv_full[st], C + h * HD, 1 + j * BKV, t);
-        tma_load_3d(smem + kSmV + st * kTile, &tmap, &kv_full[st], 2 * C + h * HD, 1 + j * BKV, t);
+        mbar_wait(&k_empty[st], (use & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], kTile);
+        tma_load_3d(smem + kSmK + st * kTile, &tmap, &k_full[st], C + h * HD, 1 + j * BKV, t);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 3) {
+    if (lane == 0) {  // the V stream (a V tile is held until both PV MMAs retire)
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % NSTAGE, use = j / NSTAGE;
+        mbar_wait(&v_empty[st], (use & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], kTile);
+        tma_load_3d(smem + kSmV + st * kTile, &tmap, &v_full[st], 2 * C + h * HD, 1 + j * BKV, t);
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // one MMA-issuing warp per query half g: S_g(j+1) is issued as soon as softmax g has pulled S_g(j) into registers
+    // (s_free), i.e. long before P_g(j) is ready, so the softmax warps never wait for a score tile
     if (lane == 0) {
+      const int g = warp - 1;
       constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);
-      const uint32_t sq = smem_u32(smem + kSmQ), sk = smem_u32(smem + kSmK), sv = smem_u32(smem + kSmV), sp = smem_u32(smem + kSmP);
-      auto issue_s = [&](int g, int j) {
-        const uint64_t dq = umma_desc_kmajor_sw128(sq + g * kTile);
-        const uint64_t dk = umma_desc_kmajor_sw128(sk + (j % NSTAGE) * kTile);
+      const uint32_t sk = smem_u32(smem + kSmK), sv = smem_u32(smem + kSmV), sp = smem_u32(smem + kSmP) + g * (2 * kPBuf);
+      const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(smem + kSmQ) + g * kTile);
+      const uint32_t tm_s = tmem_base + g * BKV, tm_o = tmem_base + 256 + g * HD;
+      auto issue_s = [&](int j) {
+        const int st = j % NSTAGE;
+        mbar_wait(&k_full[st], (j / NSTAGE) & 1);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_kmajor_sw128(sk + st * kTile);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_base + g * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tm_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
         tc_commit(&s_full[g]);
+        tc_commit(&k_empty[st]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
+      issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % NSTAGE;
-        const uint64_t dv = umma_desc_mnmajor_sw128(sv + st * kTile, kTile);
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_full[g], j & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            const uint64_t dp = umma_desc_kmajor_sw128(sp + g * (BQ * BKV * 2) + (k >> 2) * (BQ * 128)) + 2 * (k & 3);
-            tc_mma_bf16(tmem_base + 256 + g * HD, dp, dv + (uint64_t)k * (16 * 128 >> 4), idesc_o, (j | k) != 0);
-          }
-          tc_commit(&o_done[g]);
-          if (j + 1 < nkv) {
-            if (g == 0) {
-              mbar_wait(&kv_full[(j + 1) % NSTAGE], ((j + 1) / NSTAGE) & 1);
-              tc_fence_after();
-            }
-            issue_s(g, j + 1);
-          }
+        if (j + 1 < nkv) {
+          mbar_wait(&s_free[g], j & 1);
+          issue_s(j + 1);
         }
-        tc_commit(&kv_empty[st]);
+        mbar_wait(&p_full[g], j & 1);
+        mbar_wait(&v_full[st], (j / NSTAGE) & 1);
+        tc_fence_after();
+        const uint64_t dv = umma_desc_mnmajor_sw128(sv + st * kTile, kTile);
+        const uint32_t spj = sp + (j & 1) * kPBuf;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t dp = umma_desc_kmajor_sw128(spj + (k >> 2) * (BQ * 128)) + 2 * (k & 3);
+          tc_mma_bf16(tm_o, dp, dv + (uint64_t)k * (16 * 128 >> 4), idesc_o, (j | k) != 0);
+        }
+        tc_commit(&o_done[2 * g + (j & 1)]);
+        tc_commit(&v_empty[st]);
       }
     }
   }
@@ -161,7 +205,7 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const uint32_t tmem_s = tmem_base + g * BKV + lane_off;
     const uint32_t tmem_o = tmem_base + 256 + g * HD + lane_off;
-    uint8_t* prow = smem + kSmP + g * (BQ * BKV * 2) + r * 128;
+    uint8_t* prow0 = smem + kSmP + g * (2 * kPBuf) + r * 128;
     const int rsw = r & 7;
     const float scale = p.scale_log2;
     const bf16* kcls = p.qkv + (size_t)t * p.n_tokens * 3 * C + C + h * HD;
@@ -194,17 +238,22 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
       tmem_ld_32x32(tmem_s + 64, s2);
       tmem_ld_32x32(tmem_s + 96, s3);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);
       float m_blk = max32(s0, -INFINITY);
       m_blk = max32(s1, m_blk);
       m_blk = max32(s2, m_blk);
       m_blk = max32(s3, m_blk);
       const float m_new = fmaxf(m_ref, m_blk * scale);
       const bool grow = m_new > m_ref + kLazyThreshold;
+      uint8_t* prow = prow0 + (j & 1) * kPBuf;
       if (__any_sync(0xffffffffu, grow)) {
         const float f = grow ? ex2_approx(m_ref - m_new) : 1.0f;
         if (grow) { m_ref = m_new; l_run *= f; }
         if (j > 0) {
-          mbar_wait(&o_done[g], (j - 1) & 1);  // every PV MMA issued so far has landed in TMEM
+          // rare path: every PV issued so far must have landed in TMEM before O is rescaled in place
+          mbar_wait(&o_done[2 * g + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < HD; c += 32) {
@@ -218,18 +267,26 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
           tmem_st_wait();
         }
       }
-      float l_blk = exp_store32(s0, scale, m_ref, prow, 0, rsw);
-      l_blk += exp_store32(s1, scale, m_ref, prow, 4, rsw);
-      l_blk += exp_store32(s2, scale, m_ref, prow + BQ * 128, 0, rsw);
-      l_blk += exp_store32(s3, scale, m_ref, prow + BQ * 128, 4, rsw);
-      l_run += l_blk;
+      // the P buffer being overwritten was last read by PV_g(j-2)
+      if (j >= 2) mbar_wait(&o_done[2 * g + (j & 1)], ((j - 2) >> 1) & 1);
+      const uint64_t sc2 = pack2f(scale, scale), nm2 = pack2f(-m_ref, -m_ref);
+      uint64_t sum2 = pack2f(0.f, 0.f);
+      exp_store32(s0, sc2, nm2, sum2, prow, 0, rsw);
+      exp_store32(s1, sc2, nm2, sum2, prow, 4, rsw);
+      exp_store32(s2, sc2, nm2, sum2, prow + BQ * 128, 0, rsw);
+      exp_store32(s3, sc2, nm2, sum2, prow + BQ * 128, 4, rsw);
+      {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(sum2));
+        l_run += lo + hi;
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
     }
     // epilogue: O / l (+ the CLS key's contribution)
-    mbar_wait(&o_done[g], (nkv - 1) & 1);
+    mbar_wait(&o_done[2 * g + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1);
     tc_fence_after();
     const float p_cls = ex2_approx(s_cls - m_ref);
     const float inv = 1.0f / l_run;

@@ -116,6 +116,57 @@ __device__ __forceinline__ void add_residual32(const EpiParams& p, int row, int 
   }
 }
 
+// Epilogue of one accumulator tile for one thread (= one output row): TMEM -> registers -> fused epilogue -> global.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr, int row, int n0) {
+  const bool row_ok = row < p.M;
+  if (!p.swiglu) {
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + c, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+      const int col0 = n0 + c;
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) v[i] += __bfloat162float(__ldg(p.bias + col0 + i));
+      }
+      if (p.act) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+      }
+      if (p.scale_n) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) v[i] *= __bfloat162float(__ldg(p.scale_n + col0 + i));
+      }
+      if (row_ok) {
+        if (p.res) add_residual32(p, row, col0, v, p.N);
+        store_row32(p, row, col0, v, p.N);
+      }
+    }
+  } else {
+    // gate columns [0,BN/2), up columns [BN/2,BN) of this tile; output column base n0/2
+    const int n_out_total = p.N / 2;
+#pragma unroll 1
+    for (int c = 0; c < BN / 2; c += 32) {
+      uint32_t rg[32], ru[32];
+      tmem_ld_32x32(taddr + c, rg);
+      tmem_ld_32x32(taddr + BN / 2 + c, ru);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = silu(__uint_as_float(rg[i]) * p.alpha) * (__uint_as_float(ru[i]) * p.alpha);
+      if (row_ok) store_row32(p, row, n0 / 2 + c, v, n_out_total);
+    }
+  }
+}
+
 template <int BN, int TA, int TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
@@ -225,7 +276,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int n_out_total = p.swiglu ? p.N / 2 : p.N;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n) * BM;
       const int n0 = (tile % p.num_n) * BN;
@@ -233,51 +283,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      const bool row_ok = row < p.M;
-      if (!p.swiglu) {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          if (n0 + c >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c, r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-          const int col0 = n0 + c;
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) v[i] += __bfloat162float(__ldg(p.bias + col0 + i));
-          }
-          if (p.act) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-          }
-          if (p.scale_n) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) v[i] *= __bfloat162float(__ldg(p.scale_n + col0 + i));
-          }
-          if (row_ok) {
-            if (p.res) add_residual32(p, row, col0, v, p.N);
-            store_row32(p, row, col0, v, p.N);
-          }
-        }
-      } else {
-        // gate columns [0,BN/2), up columns [BN/2,BN) of this tile; output column base n0/2
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
-          uint32_t rg[32], ru[32];
-          tmem_ld_32x32(taddr + c, rg);
-          tmem_ld_32x32(taddr + BN / 2 + c, ru);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = silu(__uint_as_float(rg[i]) * p.alpha) * (__uint_as_float(ru[i]) * p.alpha);
-          if (row_ok) store_row32(p, row, n0 / 2 + c, v, n_out_total);
-        }
-      }
+      epilogue_tile<BN>(p, taddr, row, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -326,6 +332,168 @@ int launch_gemm(const slb_gemm_args* a, cudaStream_t stream) {
   return SLB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  CTA r holds A rows [128r, 128r+128)
+// and B rows (= output columns) [BN/2 * r, BN/2 * (r+1)) of every k-block in its own shared memory (32 KB per stage
+// instead of 48 KB -> 6 stages instead of 4, and each operand byte is fetched from L2 once per 256-row / BN-col
+// tile); the leader CTA issues M=256 MMAs whose accumulator rows 128r.. live in CTA r's TMEM.  Both CTAs run their
+// own epilogue over their 128 rows.  K-major operands only.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct Smem2 {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = (BN / 2) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 6;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+  using L = Smem2<BN>;
+  constexpr int kStages = L::kStages;
+  constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator stage (BN <= 256)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_tiles = p.num_m * p.num_n;  // cluster tiles (256 x BN)
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(&empty_bar[i], 1);  // one multicast commit per use
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);  // leader's: 4 epilogue warps x 2 CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.num_n) * (2 * BM) + rank * BM;
+        const int n0 = (tile % p.num_n) * BN + rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+          tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          const uint64_t db = umma_desc_kmajor_sw128(sa + L::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc_commit_2sm(&empty_bar[stage], 3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tfull_bar[acc], 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / p.num_n) * (2 * BM) + rank * BM;
+      const int n0 = (tile % p.num_n) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      epilogue_tile<BN>(p, taddr, row, n0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+template <int BN>
+int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
+  using L = Smem2<BN>;
+  CUtensorMap ta, tb;
+  int rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM);
+  if (rc) return rc;
+  rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN / 2);
+  if (rc) return rc;
+  EpiParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.out = a->out; p.ldo = a->ldo;
+  p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
+  p.res = a->residual; p.ldr = a->ldr;
+  p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
+  p.num_m = ceil_div(a->M, 2 * BM);
+  p.num_n = ceil_div(a->N, BN);
+  auto kern = gemm2_bf16_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  int clusters = p.num_m * p.num_n;
+  const int max_clusters = slb_num_sms() / 2;
+  if (clusters > max_clusters) clusters = max_clusters;
+  kern<<<clusters * 2, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, p);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
 }  // namespace
 
 extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
@@ -342,17 +510,30 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
     SLB_CHECK_ARG(!a->bias && !a->scale_n && !a->residual && !a->act, "gemm: swiglu excludes other epilogue terms");
   }
   int bn = a->block_n;
-  if (a->swiglu) bn = 256;
+  if (a->swiglu && bn != 2256 && bn != 256) bn = (a->M >= 4096) ? 2256 : 256;
   if (bn == 0) {
-    // pick the tile width with the fewer (weighted) waves; 256-wide tiles halve A re-reads and are ~10 % more
-    // efficient per flop, but quantise worse on small problems
     const int sms = slb_num_sms();
     const int mt = ceil_div(a->M, BM);
-    const float c256 = 2.0f * (float)ceil_div(mt * ceil_div(a->N, 256), sms);
-    const float c128 = 1.1f * (float)ceil_div(mt * ceil_div(a->N, 128), sms);
-    bn = (c256 <= c128) ? 256 : 128;
+    if (!a->a_t && !a->b_t && a->M >= 4096 && (a->swiglu || (a->N % 256) == 0 || a->N >= 2048)) {
+      bn = 2256;  // cluster of two CTAs per 256 x 256 tile: 6-stage pipeline, half the L2->smem operand traffic
+    } else if (!a->a_t && !a->b_t && a->M >= 4096 && (a->N % 224) == 0) {
+      bn = 2224;
+    } else {
+      // 1-CTA kernel: pick the tile width with the fewer (weighted) waves; 256-wide tiles halve A re-reads and are
+      // ~10 % more efficient per flop, but quantise worse on small problems
+      const float c256 = 2.0f * (float)ceil_div(mt * ceil_div(a->N, 256), sms);
+      const float c128 = 1.1f * (float)ceil_div(mt * ceil_div(a->N, 128), sms);
+      bn = (c256 <= c128) ? 256 : 128;
+    }
   }
-  SLB_CHECK_ARG(bn == 128 || bn == 256, "gemm: block_n must be 0, 128 or 256");
+  if (bn == 2256 || bn == 2224 || bn == 2192) {
+    SLB_CHECK_ARG(!a->a_t && !a->b_t, "gemm: the 2-CTA kernel takes K-major operands only");
+    SLB_CHECK_ARG(!a->swiglu || bn == 2256, "gemm: swiglu needs 256-wide tiles");
+    if (bn == 2256) return launch_gemm2<256>(a, stream);
+    if (bn == 2224) return launch_gemm2<224>(a, stream);
+    return launch_gemm2<192>(a, stream);
+  }
+  SLB_CHECK_ARG(bn == 128 || bn == 256, "gemm: block_n must be 0, 128, 256 (1-CTA) or 2256 / 2224 / 2192 (2-CTA)");
   if (!a->a_t && !a->b_t) return bn == 256 ? launch_gemm<256, 0, 0>(a, stream) : launch_gemm<128, 0, 0>(a, stream);
   if (!a->a_t && a->b_t) return bn == 256 ? launch_gemm<256, 0, 1>(a, stream) : launch_gemm<128, 0, 1>(a, stream);
   return bn == 256 ? launch_gemm<256, 1, 1>(a, stream) : launch_gemm<128, 1, 1>(a, stream);

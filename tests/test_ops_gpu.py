@@ -43,6 +43,30 @@ def test_gemm_plain(lib, M, N, K, bn):
     assert relerr(out, ref) < 1e-2  # bf16 output rounding (2^-9) + fp32 accumulation order
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 2256), (512, 512, 256, 2256), (2050, 3072, 1024, 2256), (2050, 1024, 4096, 2256),
+                                      (300, 200, 72, 2256), (4728, 896, 4864, 2224), (4728, 1152, 896, 2192), (131, 896, 896, 2224),
+                                      (16400, 4096, 1024, 2256), (7, 1152, 896, 2192)])
+def test_gemm_two_cta(lib, M, N, K, bn):
+    """cta_group::2 kernel (cluster of two CTAs per 256 x BN tile)."""
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2)
+    bias, res = rnd(N, seed=3), rnd(M, N, seed=5)
+    out = lib.gemm(a, b, block_n=bn)
+    ref = a.float() @ b.float().t()
+    assert relerr(out, ref) < 1e-2
+    out = lib.gemm(a, b, bias=bias, residual=res, block_n=bn)
+    assert relerr(out, ref + bias.float() + res.float()) < 1e-2
+
+
+def test_gemm_two_cta_swiglu(lib):
+    M, K, I = 1200, 896, 4864
+    a = rnd(M, K, seed=1)
+    wg, wu = rnd(I, K, seed=2, scale=0.05), rnd(I, K, seed=3, scale=0.05)
+    w = torch.stack([wg.view(I // 128, 128, K), wu.view(I // 128, 128, K)], dim=1).reshape(2 * I, K).contiguous()
+    out = lib.gemm(a, w, swiglu=True, block_n=2256)
+    ref = F.silu(a.float() @ wg.float().t()) * (a.float() @ wu.float().t())
+    assert relerr(out, ref) < 1e-2
+
+
 def test_gemm_epilogues(lib):
     M, N, K = 2050, 1024, 1024
     a, b = rnd(M, K, seed=1, scale=0.5), rnd(N, K, seed=2, scale=0.05)

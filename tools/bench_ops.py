@@ -46,7 +46,7 @@ shapes = [
 ]
 for name, M, N, K, kw in shapes:
     a, b = bf(M, K), bf(N, K)
-    for bn in ([256] if kw.get("swiglu") else [128, 256]):
+    for bn in ([256, 2256] if kw.get("swiglu") else [128, 256, 2256] + ([2224] if N % 224 == 0 else []) + ([2192] if N % 192 == 0 else [])):
         out = lib.gemm(a, b, block_n=bn, **kw)
         t = timeit(lambda: lib.gemm(a, b, out=out, block_n=bn, **kw))
         rows.append(dict(op="gemm", name=name, M=M, N=N, K=K, bn=bn, us=t * 1e6, tflops=2.0 * M * N * K / t / 1e12))
