@@ -180,7 +180,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m * p.num_n;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -206,11 +206,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -220,8 +220,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           const int k0 = kb * BK;
+          if (elect_one_sync()) {
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           if (TA == 0) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
           } else {
@@ -234,13 +235,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int g = 0; g < BN / 64; ++g) tma_load_2d(sb + g * (64 * BK * 2), &tmap_b, &full_bar[stage], n0 + g * 64, k0);
           }
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, TA, TB);
       int stage = 0;
       uint32_t phase = 0;
@@ -257,17 +260,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t sb = sa + L::kABytes;
           const uint64_t da = TA ? umma_desc_mnmajor_sw128(sa, 64 * BK * 2) : umma_desc_kmajor_sw128(sa);
           const uint64_t db = TB ? umma_desc_mnmajor_sw128(sb, 64 * BK * 2) : umma_desc_kmajor_sw128(sb);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: +32 bytes per UMMA_K inside the swizzle row; MN-major: +16 k-rows * 128 B
-            const uint64_t ka = TA ? (uint64_t)(k * (UMMA_K * 128 >> 4)) : (uint64_t)(k * (UMMA_K * 2 >> 4));
-            const uint64_t kbo = TB ? (uint64_t)(k * (UMMA_K * 128 >> 4)) : (uint64_t)(k * (UMMA_K * 2 >> 4));
-            tc_mma_bf16(tmem_d, da + ka, db + kbo, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // K-major: +32 bytes per UMMA_K inside the swizzle row; MN-major: +16 k-rows * 128 B
+              const uint64_t ka = TA ? (uint64_t)(k * (UMMA_K * 128 >> 4)) : (uint64_t)(k * (UMMA_K * 2 >> 4));
+              const uint64_t kbo = TB ? (uint64_t)(k * (UMMA_K * 128 >> 4)) : (uint64_t)(k * (UMMA_K * 2 >> 4));
+              tc_mma_bf16(tmem_d, da + ka, db + kbo, idesc, (kb | k) != 0);
+            }
+            tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+            if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -363,7 +369,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -391,10 +397,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -404,15 +410,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-          tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (elect_one_sync()) {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -428,12 +437,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sa + L::kABytes);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          tc_commit_2sm(&empty_bar[stage], 3);
+            for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            tc_commit_2sm(&empty_bar[stage], 3);
+            if (kb == num_kb - 1) tc_commit_2sm(&tfull_bar[acc], 3);
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit_2sm(&tfull_bar[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
