@@ -522,6 +522,7 @@ attn_vit_cls_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
 static long long* g_vit2_trace = nullptr;
 // debug hook (not part of the public header): device buffer of 3 * 256 * 2 int64 receiving CTA 0's timeline
 extern "C" int slb_debug_set_trace(void* dev_buf) { g_vit2_trace = (long long*)dev_buf; return 0; }
+long long* slb_debug_trace_ptr() { return g_vit2_trace; }
 
 // returns 1 if the specialised kernel applies (and was launched), 0 if the caller should use the generic kernel
 int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_tokens, int heads, cudaStream_t stream, int* rc_out) {

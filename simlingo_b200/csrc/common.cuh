@@ -260,6 +260,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// 256-bit global store (one full 32-byte sector per thread)
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g,
+                                             uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+               "r"(g), "r"(h) : "memory");
+}
+
 // ---- misc math ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -281,6 +288,25 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf-GELU for GEMM epilogues: Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7 + MUFU rounding, far below the bf16
+// output rounding) - two MUFU ops and ~10 FMA-pipe ops instead of erff's ~25 instructions with branches
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = ex2_approx(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;  // x * (1 + sign(x) erf|z|) / 2
+}
+__device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.0f + ex2_approx(-x * 1.4426950408889634f)); }
 
 // host: build a 2-D (or 3-D) bf16 TMA descriptor with 128B swizzle (inner box = 64 elements = 128 bytes)
 int slb_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,

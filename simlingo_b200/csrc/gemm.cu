@@ -8,14 +8,17 @@
 #include "common.cuh"
 #include "../../include/simlingo_b200.h"
 
+long long* slb_debug_trace_ptr();
+
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 
 struct EpiParams {
+  long long* dbg;  // optional [16] int64: wait-cycle counters of cluster 0 (slb_debug_set_trace), else null
   int M, N, K;
   void* out;
   long long ldo;
@@ -41,8 +44,8 @@ struct SmemLayout {
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == SLB_ACT_GELU) return gelu_erf(v);
-  if (act == SLB_ACT_SILU) return silu(v);
+  if (act == SLB_ACT_GELU) return gelu_erf_fast(v);
+  if (act == SLB_ACT_SILU) return silu_fast(v);
   if (act == SLB_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
@@ -52,7 +55,14 @@ __device__ __forceinline__ void store_row32(const EpiParams& p, int row, int col
   if (p.out_fp32) {
     float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
     bool vec = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (col0 + 32 <= ncols_total);
-    if (vec) {
+    const bool vec32 = ((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) && (col0 + 32 <= ncols_total);
+    if (vec32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_global_v8(o + 8 * i, __float_as_uint(v[8 * i]), __float_as_uint(v[8 * i + 1]), __float_as_uint(v[8 * i + 2]),
+                     __float_as_uint(v[8 * i + 3]), __float_as_uint(v[8 * i + 4]), __float_as_uint(v[8 * i + 5]),
+                     __float_as_uint(v[8 * i + 6]), __float_as_uint(v[8 * i + 7]));
+    } else if (vec) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -64,7 +74,15 @@ __device__ __forceinline__ void store_row32(const EpiParams& p, int row, int col
   } else {
     bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col0;
     bool vec = ((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (col0 + 32 <= ncols_total);
-    if (vec) {
+    const bool vec32 = ((p.ldo & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) && (col0 + 32 <= ncols_total);
+    if (vec32) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        st_global_v8(o + 16 * i, pack_bf16(v[16 * i + 0], v[16 * i + 1]), pack_bf16(v[16 * i + 2], v[16 * i + 3]),
+                     pack_bf16(v[16 * i + 4], v[16 * i + 5]), pack_bf16(v[16 * i + 6], v[16 * i + 7]),
+                     pack_bf16(v[16 * i + 8], v[16 * i + 9]), pack_bf16(v[16 * i + 10], v[16 * i + 11]),
+                     pack_bf16(v[16 * i + 12], v[16 * i + 13]), pack_bf16(v[16 * i + 14], v[16 * i + 15]));
+    } else if (vec) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 u;
@@ -116,13 +134,31 @@ __device__ __forceinline__ void add_residual32(const EpiParams& p, int row, int 
   }
 }
 
-// Epilogue of one accumulator tile for one thread (= one output row): TMEM -> registers -> fused epilogue -> global.
+__device__ __forceinline__ void load32_bf16(const bf16* p, int col0, int n, float (&f)[32]) {
+  if (col0 + 32 <= n && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + col0) + i);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      f[8 * i + 0] = a.x; f[8 * i + 1] = a.y; f[8 * i + 2] = b.x; f[8 * i + 3] = b.y;
+      f[8 * i + 4] = c.x; f[8 * i + 5] = c.y; f[8 * i + 6] = d.x; f[8 * i + 7] = d.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = (col0 + i < n) ? __bfloat162float(__ldg(p + col0 + i)) : 0.f;
+  }
+}
+
+// Epilogue of one accumulator tile for one thread (= one output row), 32-column chunks [c_begin, c_end):
+// TMEM -> registers -> fused epilogue -> global.  Two warps share a TMEM lane quadrant and split the chunks.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr, int row, int n0) {
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr, int row, int n0, int half) {
   const bool row_ok = row < p.M;
   if (!p.swiglu) {
+    constexpr int kChunks = BN / 32, kFirst = (kChunks + 1) / 2;
+    const int c_begin = half ? kFirst * 32 : 0, c_end = half ? BN : kFirst * 32;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       if (n0 + c >= p.N) break;  // warp-uniform
       uint32_t r[32];
       tmem_ld_32x32(taddr + c, r);
@@ -132,18 +168,26 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
       const int col0 = n0 + c;
       if (p.bias) {
+        float b[32];
+        load32_bf16(p.bias, col0, p.N, b);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < p.N) v[i] += __bfloat162float(__ldg(p.bias + col0 + i));
+        for (int i = 0; i < 32; ++i) v[i] += b[i];
       }
-      if (p.act) {
+      if (p.act == SLB_ACT_GELU) {  // activation switch hoisted out of the per-element loop
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+      } else if (p.act == SLB_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+      } else if (p.act == SLB_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       if (p.scale_n) {
+        float sc[32];
+        load32_bf16(p.scale_n, col0, p.N, sc);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < p.N) v[i] *= __bfloat162float(__ldg(p.scale_n + col0 + i));
+        for (int i = 0; i < 32; ++i) v[i] *= sc[i];
       }
       if (row_ok) {
         if (p.res) add_residual32(p, row, col0, v, p.N);
@@ -154,14 +198,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
     // gate columns [0,BN/2), up columns [BN/2,BN) of this tile; output column base n0/2
     const int n_out_total = p.N / 2;
 #pragma unroll 1
-    for (int c = 0; c < BN / 2; c += 32) {
+    for (int c = half * (BN / 4); c < (half + 1) * (BN / 4); c += 32) {
       uint32_t rg[32], ru[32];
       tmem_ld_32x32(taddr + c, rg);
       tmem_ld_32x32(taddr + BN / 2 + c, ru);
       tmem_ld_wait();
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = silu(__uint_as_float(rg[i]) * p.alpha) * (__uint_as_float(ru[i]) * p.alpha);
+      for (int i = 0; i < 32; ++i) v[i] = silu_fast(__uint_as_float(rg[i]) * p.alpha) * (__uint_as_float(ru[i]) * p.alpha);
       if (row_ok) store_row32(p, row, n0 / 2 + c, v, n_out_total);
     }
   }
@@ -195,7 +239,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     mbar_fence_init();
   }
@@ -289,7 +333,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      epilogue_tile<BN>(p, taddr, row, n0);
+      epilogue_tile<BN>(p, taddr, row, n0, (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -317,6 +361,7 @@ int launch_gemm(const slb_gemm_args* a, cudaStream_t stream) {
   else     rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, BK);
   if (rc) return rc;
   EpiParams p;
+  p.dbg = nullptr;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.out = a->out; p.ldo = a->ldo;
   p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
@@ -386,7 +431,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // leader's: 4 epilogue warps x 2 CTAs
+      mbar_init(&tempty_bar[i], 16);  // leader's: 8 epilogue warps x 2 CTAs
     }
     mbar_fence_init();
   }
@@ -403,11 +448,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0, t_begin = clock64();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile / p.num_n) * (2 * BM) + rank * BM;
         const int n0 = (tile % p.num_n) * BN + rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
+          const long long c0 = clock64();
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          w_empty += clock64() - c0;
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           if (elect_one_sync()) {
@@ -419,6 +467,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg && cluster_id == 0 && leader && lane == 0) { p.dbg[5] = clock64() - t_begin; p.dbg[6] = w_empty; }
     }
   } else if (warp == 1) {
     if (leader) {
@@ -427,12 +476,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_full = 0, w_tempty = 0, t_begin = clock64();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        long long c0 = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        w_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
         for (int kb = 0; kb < num_kb; ++kb) {
+          c0 = clock64();
           mbar_wait(&full_bar[stage], phase);
+          w_full += clock64() - c0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint64_t da = umma_desc_kmajor_sw128(sa);
@@ -448,24 +502,31 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (p.dbg && cluster_id == 0 && lane == 0) {
+        p.dbg[0] = clock64() - t_begin; p.dbg[1] = w_full; p.dbg[2] = w_tempty;
+      }
     }
   } else {
     const int quad = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_tfull = 0, t_begin = clock64();
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m0 = (tile / p.num_n) * (2 * BM) + rank * BM;
       const int n0 = (tile % p.num_n) * BN;
+      const long long c0 = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase);
+      w_tfull += clock64() - c0;
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
-      epilogue_tile<BN>(p, taddr, row, n0);
+      epilogue_tile<BN>(p, taddr, row, n0, (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0) { p.dbg[3] = clock64() - t_begin; p.dbg[4] = w_tfull; }
   }
 
   tc_fence_before();
@@ -485,6 +546,7 @@ int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
   rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN / 2);
   if (rc) return rc;
   EpiParams p;
+  p.dbg = slb_debug_trace_ptr();
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.out = a->out; p.ldo = a->ldo;
   p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
