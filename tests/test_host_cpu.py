@@ -1,0 +1,158 @@
+"""CPU-only checks (run with -m "not gpu"): the C-ABI library loads and exports every symbol the header declares,
+state_dict schema / drop-in module tree, host-side glue (adaptors, losses, sharding), world_size-2 gloo path."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from simlingo_b200 import build
+    lib_path = build.build()
+    so = ctypes.CDLL(str(lib_path))
+    header = open(os.path.join(ROOT, "include", "simlingo_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(slb_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(so, n), n
+    so.slb_last_error.restype = ctypes.c_char_p
+    assert so.slb_version() >= 100
+
+
+def test_invalid_arguments_return_error_codes_not_crashes():
+    from simlingo_b200 import lib
+    L = lib.load()
+    L.slb_last_error.restype = ctypes.c_char_p
+    g = lib.GemmArgs(M=0, N=8, K=8)
+    assert L.slb_gemm_bf16(ctypes.byref(g), None) != 0
+    assert b"bad shape" in L.slb_last_error()
+    assert L.slb_layernorm_fwd(None, None, None, None, 4, 7, ctypes.c_float(1e-6), None, None, None) != 0  # cols % 8
+
+
+def test_state_dict_schema_matches_dropin_module_tree():
+    from simlingo_b200.modules import register_variant
+    from simlingo_b200.spec import INTERNVL2_1B, init_state_dict, state_dict_schema, tiny_spec, trainable
+    from simlingo_training.models.driving import DrivingModel
+    from tests.helpers import StubTokenizer
+    full = state_dict_schema(INTERNVL2_1B)
+    assert 980 <= len(full) <= 1000  # "about 990 keys"
+    spec = tiny_spec(2, 2, 4096)
+    register_variant("internvl2-tiny-cpu", spec)
+    cfg = dict(vision_model=dict(_target_="simlingo_training.models.encoder.vlm.VLMEncoderModel", variant="internvl2-tiny-cpu", embed_dim=512, freeze=False),
+               language_model=dict(_target_="simlingo_training.models.language_model.llm.LLM", variant="internvl2-tiny-cpu", lora=True, lora_alpha=64,
+                                   lora_r=32, lora_dropout=0.1),
+               lr=3e-5, weight_decay=0.1, betas=(0.9, 0.999), pct_start=0.05, speed_wps_mode="2d", predict_route_as_wps=True)
+    m = DrivingModel(cfg_data_module={"use_global_img": False}, processor=StubTokenizer(spec), cache_dir=None, **cfg)
+    schema = state_dict_schema(spec)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(schema.keys())
+    for k, (shape, _) in schema.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    m.load_state_dict(init_state_dict(spec, with_aliases=True), strict=True)
+    # aliases share storage (llm.py:91, adaptors.py:227-229)
+    assert m.adaptors.language.lm_head.weight is m.language_model.model.base_model.model.lm_head.weight
+    assert m.adaptors.language.embed_tokens.weight.data_ptr() == sd["language_model.model.base_model.model.embed_tokens.weight"].data_ptr()
+    # trainability: ViT + mlp1 + LoRA + heads + wp_encoder train, Qwen2 base / embeddings / lm_head are frozen
+    for n, p in m.named_parameters():
+        assert p.requires_grad == trainable(n), n
+    # no CPU fallback: using the model without a GPU fails loudly
+    with pytest.raises(RuntimeError):
+        m.adaptors.language.embed_tokens(torch.zeros(1, 2, dtype=torch.long))
+
+
+def test_adaptor_list_matches_oracle_glue():
+    """AdaptorList permutation / split (host index glue) against the oracle's restatement, with stub adaptors."""
+    from oracle import model as O
+    from simlingo_b200.spec import init_state_dict, tiny_spec
+    from simlingo_training.models.adaptors.adaptors import AdaptorList, DrivingAdaptor
+    spec = tiny_spec(1, 1, 512)
+    sd = init_state_dict(spec)
+    B, L = 3, 9
+    ids = torch.randint(0, 500, (B, L))
+    valid = torch.ones(B, L, dtype=torch.bool)
+    valid[1, :3] = False
+    valid[2, :5] = False
+
+    class Lang(torch.nn.Module):
+        def forward(self, example, **kw):
+            return {"inputs": O.language_embed(sd, spec, ids), "inputs_mask": valid, "_ids": ids, "_ids_mask": torch.zeros_like(valid)}
+
+    drv = DrivingAdaptor(spec.llm_hidden, speed_wps_mode="2d", predict_route_as_wps=True)
+    with torch.no_grad():
+        drv.query_embeds_wps.copy_(sd["adaptors.driving.query_embeds_wps"])
+        drv.query_embeds_speed.copy_(sd["adaptors.driving.query_embeds_speed"])
+    al = AdaptorList(language=Lang(), driving=drv)
+
+    class Ex:
+        camera_images = torch.zeros(B, 1)
+    out = al(Ex())
+    ref = O.adaptor_list_forward(sd, spec, ids, valid, torch.zeros_like(valid))
+    assert torch.equal(out["perm"], ref["perm"]) and torch.equal(out["inputs_mask"], ref["inputs_mask"])
+    assert torch.allclose(out["inputs"], ref["inputs"])
+    feats = torch.randn(B, L + 30, 8)
+    a, b = O.split_outputs(ref, feats)
+    sp = al.split_outputs_by_adaptor(out, feats)
+    assert torch.equal(sp["language"], a) and torch.equal(sp["driving"], b)
+
+
+def test_summarise_losses_and_helpers():
+    from simlingo_training.models.adaptors.adaptors import cross_track_error
+    from simlingo_training.models.utils import summarise_losses
+    v1, n1 = torch.tensor([2.0, 4.0]), torch.tensor([1, 3])
+    v2, n2 = torch.tensor([0.0, 0.0]), torch.tensor([0, 0])
+    out = summarise_losses({"a_loss": (v1, n1), "b_loss": (v2, n2)})
+    assert torch.isclose(out.loss, torch.tensor(1.5)) and float(out.loss_averages["b_loss"]) == 0.0
+    path = torch.stack([torch.arange(5.0), torch.zeros(5)], -1)[None]
+    pts = torch.tensor([[[2.0, 1.0], [3.0, -2.0]]])
+    assert torch.allclose(cross_track_error(pts, path), torch.tensor([[1.0, 2.0]]))
+
+
+def test_shard_ranges_cover_everything():
+    from simlingo_b200.dist import shard_range
+    for n, w in [(64, 8), (64, 3), (5, 8), (7, 2)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from simlingo_b200.dist import env_rank_world, gather_predictions, max_over_ranks, shard_range
+rank, world, _ = env_rank_world()
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+lo, hi = shard_range(7, rank, world)
+local = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1).expand(-1, 2, 2).contiguous()
+ms = max_over_ranks(10.0 + rank)
+assert ms == 10.0 + world - 1, ms
+out = gather_predictions(local, [shard_range(7, r, world)[1] - shard_range(7, r, world)[0] for r in range(world)])
+if rank == 0:
+    full = torch.cat(out)
+    assert full[:, 0, 0].tolist() == [float(i) for i in range(7)], full
+# gradient all-reduce semantics of the training path (sum then / world), bf16 buckets
+g = torch.full((16,), float(rank + 1), dtype=torch.bfloat16)
+dist.all_reduce(g)
+g /= world
+assert torch.allclose(g.float(), torch.full((16,), (world + 1) / 2.0))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_world_size_2_gloo():
+    port = 29500 + (os.getpid() % 500)
+    code = _WORKER.format(root=ROOT, port=port)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out
