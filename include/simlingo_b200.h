@@ -117,6 +117,46 @@ int slb_wp_encoder(const float* coords, const slb_wp_weights* w, void* out, int 
  * flat fp32 master params / moments, bf16 gradient (flat), bf16 model copy written back. */
 /* ---- data-parallel gradient exchange (Lightning DDP / ZeRO-2 in the reference, train.py:160-168) --
  * NCCL communicator handled as an opaque pointer; unique id is a 128-byte blob exchanged by the host. */
+/* ================================ training-only entry points ===================================
+ * The reference trains through torch autograd + flash-attn backward + torch.optim.AdamW under Lightning
+ * (driving.py:236-271,718-732; train.py:160-217).  dgrad / wgrad GEMMs use slb_gemm_bf16 with b_t / a_t+b_t. */
+int slb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                      float* dw_accum, float* db_accum, int rows, int cols, void* stream);
+int slb_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw_accum, int rows,
+                    int cols, void* stream);
+int slb_pixel_shuffle_ln_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                             void* dx, float* dw_accum, float* db_accum, int tiles, void* stream);
+int slb_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
+int slb_gelu_bwd(const void* pre, const void* dout, void* dpre, int64_t n, void* stream);
+int slb_silu_mul_bwd(const void* gate, const void* up, const void* dout, void* dgate, void* dup, int64_t n, void* stream);
+/* counter-based dropout (peft lora_dropout=0.1): y = keep(seed, i) ? x / (1-p) : 0; same call on the gradient = backward */
+int slb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream);
+int slb_add_inplace_bf16(void* a, const void* b, int64_t n, void* stream);
+int slb_scale_cols(const void* x, const void* s, void* out, int rows, int cols, void* stream);
+/* acc[c] += alpha * sum_r a[r,c] * (b ? b[r,c] : 1)   (bias / layer-scale / norm-weight gradients) */
+int slb_col_reduce(const void* a, int64_t lda, const void* b, int64_t ldb, float* acc, int rows, int cols, float alpha,
+                   void* stream);
+int slb_vit_assemble_bwd(const void* dx, void* dpatch_out, float* dcls_accum, float* dpos_accum, int tiles, void* stream);
+/* packs attention gradients (dq fp32 [B*L, Hq*64], dk/dv fp32 [B, Hkv, L, 64]) into the fused-QKV gradient
+ * [B*L, (Hq+2Hkv)*64] bf16, rotating dq/dk back (theta <= 1: no rotation, the ViT case) */
+int slb_rope_bwd(const float* dq, const float* dk, const float* dv, void* dqkv, int batch, int lq, int hq, int hkv,
+                 float theta, void* stream);
+int slb_attn_delta(const void* o, const void* dout, float* delta, int batch, int lq, int heads, void* stream);
+int slb_attn_vit_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq, float* dk,
+                     float* dv, int tiles, int n_tokens, int heads, void* stream);
+int slb_attn_gqa_bwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
+                     int key_valid_ld, const void* dout, const float* lse, const float* delta, float* dq, float* dk,
+                     float* dv, int batch, int lq, int lmax, int hq, int hkv, void* stream);
+/* fused softmax cross-entropy over fp32 logits rows (adaptors.py:271-273): loss[r] = lse - logit[label];
+ * dlogits (bf16, row stride ldd >= cols, zero padded) = (softmax - onehot) * grad_scale; label < 0 => ignored */
+int slb_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* labels, float* loss, void* dlogits, int64_t ldd,
+                   float grad_scale, int rows, int cols, void* stream);
+/* fused AdamW + global-norm clip over flat buffers (driving.py:718-724; train.py:206) */
+int slb_grad_sqnorm(const void* grad_bf16, int64_t n, float* out_sq, void* stream);
+int slb_adamw_fused(float* master, float* m, float* v, const void* grad_bf16, void* param_bf16, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float wd, int step, const float* grad_sqnorm, float max_norm,
+                    float grad_prescale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -252,3 +252,159 @@ def wp_encoder(coords, ww: WpWeights, out=None):
     out = torch.empty((n, 896), device=coords.device, dtype=torch.bfloat16) if out is None else out
     _check(load().slb_wp_encoder(_p(coords), C.byref(ww), _p(out), n, _stream()), "wp_encoder")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# training-only ops
+# ------------------------------------------------------------------------------------------------
+def _f32(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), (t.device, t.dtype)
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dw_acc, db_acc, dx=None):
+    _bf16(dy, x, w); _f32(mean, rstd, dw_acc, db_acc)
+    dx = torch.empty_like(x) if dx is None else dx
+    _check(load().slb_layernorm_bwd(_p(dy), _p(x), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw_acc), _p(db_acc), x.shape[0], x.shape[1], _stream()),
+           "layernorm_bwd")
+    return dx
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dx=None):
+    _bf16(dy, x, w); _f32(rstd)
+    dx = torch.empty_like(x) if dx is None else dx
+    _check(load().slb_rmsnorm_bwd(_p(dy), _p(x), _p(w), _p(rstd), _p(dx), None, x.shape[0], x.shape[1], _stream()), "rmsnorm_bwd")
+    return dx
+
+
+def pixel_shuffle_ln_bwd(dy, x, w, mean, rstd, dw_acc, db_acc, tiles, dx=None):
+    _bf16(dy, x, w); _f32(mean, rstd, dw_acc, db_acc)
+    dx = torch.empty_like(x) if dx is None else dx
+    _check(load().slb_pixel_shuffle_ln_bwd(_p(dy), _p(x), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw_acc), _p(db_acc), tiles, _stream()),
+           "pixel_shuffle_ln_bwd")
+    return dx
+
+
+def gelu_fwd(x, out=None):
+    _bf16(x)
+    out = torch.empty_like(x) if out is None else out
+    _check(load().slb_gelu_fwd(_p(x), _p(out), C.c_int64(x.numel()), _stream()), "gelu_fwd")
+    return out
+
+
+def gelu_bwd(pre, dout, out=None):
+    _bf16(pre, dout)
+    out = torch.empty_like(pre) if out is None else out
+    _check(load().slb_gelu_bwd(_p(pre), _p(dout), _p(out), C.c_int64(pre.numel()), _stream()), "gelu_bwd")
+    return out
+
+
+def silu_mul_bwd(g, u, dout, dg=None, du=None):
+    _bf16(g, u, dout)
+    dg = torch.empty_like(g) if dg is None else dg
+    du = torch.empty_like(u) if du is None else du
+    _check(load().slb_silu_mul_bwd(_p(g), _p(u), _p(dout), _p(dg), _p(du), C.c_int64(g.numel()), _stream()), "silu_mul_bwd")
+    return dg, du
+
+
+def dropout(x, p, seed, out=None):
+    _bf16(x)
+    out = torch.empty_like(x) if out is None else out
+    _check(load().slb_dropout(_p(x), _p(out), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed), _stream()), "dropout")
+    return out
+
+
+def add_inplace(a, b):
+    _bf16(a, b)
+    _check(load().slb_add_inplace_bf16(_p(a), _p(b), C.c_int64(a.numel()), _stream()), "add_inplace")
+    return a
+
+
+def scale_cols(x, s, out=None):
+    _bf16(x, s)
+    out = torch.empty_like(x) if out is None else out
+    _check(load().slb_scale_cols(_p(x), _p(s), _p(out), x.shape[0], x.shape[1], _stream()), "scale_cols")
+    return out
+
+
+def col_reduce(a, acc, b=None, alpha=1.0):
+    """acc[c] += alpha * sum_r a[r,c] * (b[r,c] if b is given else 1); acc fp32 [cols]."""
+    _bf16(a, b); _f32(acc)
+    assert a.dim() == 2 and a.stride(1) == 1 and (b is None or (b.stride(1) == 1 and b.shape == a.shape))
+    _check(load().slb_col_reduce(_p(a), C.c_int64(a.stride(0)), _p(b), C.c_int64(0 if b is None else b.stride(0)), _p(acc), a.shape[0], a.shape[1],
+                                 C.c_float(alpha), _stream()), "col_reduce")
+    return acc
+
+
+def vit_assemble_bwd(dx, dcls_acc, dpos_acc, tiles, dpatch=None):
+    _bf16(dx); _f32(dcls_acc, dpos_acc)
+    dpatch = torch.empty((tiles * 1024, 1024), device=dx.device, dtype=torch.bfloat16) if dpatch is None else dpatch
+    _check(load().slb_vit_assemble_bwd(_p(dx), _p(dpatch), _p(dcls_acc), _p(dpos_acc), tiles, _stream()), "vit_assemble_bwd")
+    return dpatch
+
+
+def rope_bwd(dq, dk, dv, batch, lq, hq, hkv, theta, out=None):
+    _f32(dq, dk, dv)
+    out = torch.empty((batch * lq, (hq + 2 * hkv) * 64), device=dq.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().slb_rope_bwd(_p(dq), _p(dk), _p(dv), _p(out), batch, lq, hq, hkv, C.c_float(theta), _stream()), "rope_bwd")
+    return out
+
+
+def attn_delta(o, dout, batch, lq, heads, out=None):
+    _bf16(o, dout)
+    out = torch.empty((batch, heads, lq), device=o.device, dtype=torch.float32) if out is None else out
+    _check(load().slb_attn_delta(_p(o), _p(dout), _p(out), batch, lq, heads, _stream()), "attn_delta")
+    return out
+
+
+def attn_vit_bwd(qkv, dout, lse, delta, tiles, n_tokens, heads=16):
+    """-> (dq fp32 [T*n, H*64], dk fp32 [T,H,n,64], dv fp32 [T,H,n,64])"""
+    _bf16(qkv, dout); _f32(lse, delta)
+    dev = qkv.device
+    dq = torch.zeros((tiles * n_tokens, heads * 64), device=dev, dtype=torch.float32)
+    dk = torch.empty((tiles, heads, n_tokens, 64), device=dev, dtype=torch.float32)
+    dv = torch.empty_like(dk)
+    _check(load().slb_attn_vit_bwd(_p(qkv), _p(dout), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), tiles, n_tokens, heads, _stream()), "attn_vit_bwd")
+    return dq, dk, dv
+
+
+def attn_gqa_bwd(q, ldq, kcache, vcache, dout, lse, delta, batch, lq, hq=14, hkv=2, key_valid=None):
+    """-> (dq fp32 [B*L, Hq*64] (post-RoPE space), dk fp32 [B,Hkv,L,64], dv fp32 [B,Hkv,L,64])"""
+    _bf16(q, kcache, vcache, dout); _f32(lse, delta)
+    dev = q.device
+    lmax = kcache.shape[2]
+    dq = torch.zeros((batch * lq, hq * 64), device=dev, dtype=torch.float32)
+    dk = torch.empty((batch, hkv, lq, 64), device=dev, dtype=torch.float32)
+    dv = torch.empty_like(dk)
+    kv_ld = 0 if key_valid is None else key_valid.stride(0)
+    _check(load().slb_attn_gqa_bwd(_p(q), C.c_int64(ldq), _p(kcache), _p(vcache), _p(key_valid), kv_ld, _p(dout), _p(lse), _p(delta), _p(dq),
+                                   _p(dk), _p(dv), batch, lq, lmax, hq, hkv, _stream()), "attn_gqa_bwd")
+    return dq, dk, dv
+
+
+def ce_fwd_bwd(logits, labels, grad_scale=1.0, want_grad=True):
+    """logits fp32 [R, V]; labels int64 [R] (<0 = ignore) -> (loss fp32 [R], dlogits bf16 [R, Vpad] or None)"""
+    _f32(logits)
+    R, V = logits.shape
+    loss = torch.empty((R,), device=logits.device, dtype=torch.float32)
+    dl, ldd = None, 0
+    if want_grad:
+        ldd = (V + 63) // 64 * 64
+        dl = torch.empty((R, ldd), device=logits.device, dtype=torch.bfloat16)
+    _check(load().slb_ce_fwd_bwd(_p(logits), C.c_int64(logits.stride(0)), _p(labels.contiguous()), _p(loss), _p(dl), C.c_int64(ldd),
+                                 C.c_float(grad_scale), R, V, _stream()), "ce_fwd_bwd")
+    return loss, dl
+
+
+def grad_sqnorm(g, out):
+    _bf16(g); _f32(out)
+    _check(load().slb_grad_sqnorm(_p(g), C.c_int64(g.numel()), _p(out), _stream()), "grad_sqnorm")
+    return out
+
+
+def adamw_fused(master, m, v, grad, param, lr, beta1, beta2, eps, wd, step, sqnorm=None, max_norm=0.0, prescale=1.0):
+    _f32(master, m, v, sqnorm); _bf16(grad, param)
+    _check(load().slb_adamw_fused(_p(master), _p(m), _p(v), _p(grad), _p(param), C.c_int64(master.numel()), C.c_float(lr), C.c_float(beta1),
+                                  C.c_float(beta2), C.c_float(eps), C.c_float(wd), step, _p(sqnorm), C.c_float(max_norm), C.c_float(prescale),
+                                  _stream()), "adamw_fused")
