@@ -131,8 +131,14 @@ int slb_gelu_bwd(const void* pre, const void* dout, void* dpre, int64_t n, void*
 int slb_silu_mul_bwd(const void* gate, const void* up, const void* dout, void* dgate, void* dup, int64_t n, void* stream);
 /* counter-based dropout (peft lora_dropout=0.1): y = keep(seed, i) ? x / (1-p) : 0; same call on the gradient = backward */
 int slb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream);
+/* y += dropout(x) with the same (seed, index) mask as slb_dropout */
+int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream);
+/* y (bf16) = (accumulate ? y : 0) + x (fp32): flush of fp32 small-parameter gradient accumulators */
+int slb_flush_f32_to_bf16(const float* x, void* y, int64_t n, int accumulate, void* stream);
 int slb_add_inplace_bf16(void* a, const void* b, int64_t n, void* stream);
 int slb_scale_cols(const void* x, const void* s, void* out, int rows, int cols, void* stream);
+/* out = res + s[col] * x  (layer-scale residual of InternViT when the branch output must be kept for backward) */
+int slb_scale_cols_add(const void* x, const void* s, const void* res, void* out, int rows, int cols, void* stream);
 /* acc[c] += alpha * sum_r a[r,c] * (b ? b[r,c] : 1)   (bias / layer-scale / norm-weight gradients) */
 int slb_col_reduce(const void* a, int64_t lda, const void* b, int64_t ldb, float* acc, int rows, int cols, float alpha,
                    void* stream);

@@ -202,6 +202,22 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
     store8(y + i * 8, a);
   }
 }
+// y += dropout(x): backward of the LoRA-input dropout, accumulated straight into the gradient of the shared input
+__global__ void dropout_add_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t nvec, uint32_t thresh, float scale, uint64_t seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    load8(x + i * 8, a);
+    load8(y + i * 8, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) b[e] += (mix32(seed * 0x9E3779B97F4A7C15ULL + i * 8 + e) >= thresh) ? a[e] * scale : 0.f;
+    store8(y + i * 8, b);
+  }
+}
+// y (bf16) = [y +] x (fp32): flush of the fp32 small-parameter gradient accumulators into the flat bf16 gradient buffer
+__global__ void flush_f32_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n, int accumulate) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i] + (accumulate ? __bfloat162float(y[i]) : 0.f));
+}
 __global__ void add_inplace_kernel(bf16* __restrict__ a_, const bf16* __restrict__ b_, size_t nvec) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float a[8], b[8];
@@ -222,6 +238,21 @@ __global__ void scale_cols_kernel(const bf16* __restrict__ x, const bf16* __rest
     load8(s + vi * 8, b);
 #pragma unroll
     for (int e = 0; e < 8; ++e) a[e] *= b[e];
+    store8(y + i * 8, a);
+  }
+}
+
+__global__ void scale_cols_add_kernel(const bf16* __restrict__ x, const bf16* __restrict__ s, const bf16* __restrict__ res,
+                                      bf16* __restrict__ y, int rows, int cols) {
+  const int vpr = cols >> 3;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)rows * vpr; i += (size_t)gridDim.x * blockDim.x) {
+    const int vi = (int)(i % vpr);
+    float a[8], b[8], c[8];
+    load8(x + i * 8, a);
+    load8(s + vi * 8, b);
+    load8(res + i * 8, c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = c[e] + a[e] * b[e];
     store8(y + i * 8, a);
   }
 }
@@ -426,6 +457,19 @@ extern "C" int slb_dropout(const void* x, void* y, int64_t n, float p, uint64_t 
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
+extern "C" int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream) {
+  SLB_CHECK_ARG(n > 0 && (n % 8) == 0 && p >= 0.f && p < 1.f, "dropout_add: n=%lld p=%f", (long long)n, p);
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  dropout_add_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)y, n / 8, thresh, 1.0f / (1.0f - p), seed);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+extern "C" int slb_flush_f32_to_bf16(const float* x, void* y, int64_t n, int accumulate, void* stream) {
+  SLB_CHECK_ARG(n > 0, "flush: n=%lld", (long long)n);
+  flush_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, (bf16*)y, n, accumulate);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
 extern "C" int slb_add_inplace_bf16(void* a, const void* b, int64_t n, void* stream) {
   SLB_CHECK_ARG(n > 0 && (n % 8) == 0, "add_inplace: n=%lld", (long long)n);
   add_inplace_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((bf16*)a, (const bf16*)b, n / 8);
@@ -435,6 +479,12 @@ extern "C" int slb_add_inplace_bf16(void* a, const void* b, int64_t n, void* str
 extern "C" int slb_scale_cols(const void* x, const void* s, void* out, int rows, int cols, void* stream) {
   SLB_CHECK_ARG(rows > 0 && (cols % 8) == 0, "scale_cols: %d x %d", rows, cols);
   scale_cols_kernel<<<grid_for((size_t)rows * (cols / 8), 256), 256, 0, ST(stream)>>>((const bf16*)x, (const bf16*)s, (bf16*)out, rows, cols);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+extern "C" int slb_scale_cols_add(const void* x, const void* s, const void* res, void* out, int rows, int cols, void* stream) {
+  SLB_CHECK_ARG(rows > 0 && (cols % 8) == 0, "scale_cols_add: %d x %d", rows, cols);
+  scale_cols_add_kernel<<<grid_for((size_t)rows * (cols / 8), 256), 256, 0, ST(stream)>>>((const bf16*)x, (const bf16*)s, (const bf16*)res, (bf16*)out, rows, cols);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

@@ -43,6 +43,7 @@ class Engine:
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self._packed_version = None
         self.launches = 0
+        self.generation_fn = None  # set by runtime when a training ParamStore updates the weights behind torch's back
         self.refresh()
 
     # ------------------------------------------------------------------------------------------
@@ -55,7 +56,8 @@ class Engine:
         return t.detach()
 
     def _version(self) -> int:
-        return sum(int(getattr(v, "_version", 0)) for v in self.sd.values())
+        gen = self.generation_fn() if self.generation_fn is not None else 0
+        return sum(int(getattr(v, "_version", 0)) for v in self.sd.values()) + (gen << 32)
 
     def refresh(self, force: bool = True) -> None:
         """(Re)build the scratch weights derived from the state_dict: zero-padded patch-embed matrix, fused

@@ -315,6 +315,22 @@ def dropout(x, p, seed, out=None):
     return out
 
 
+def dropout_add(x, y, p, seed):
+    """y += dropout(x) (same mask as ``dropout(.., p, seed)``)."""
+    _bf16(x, y)
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+    _check(load().slb_dropout_add(_p(x), _p(y), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed), _stream()), "dropout_add")
+    return y
+
+
+def flush_f32(x, y, accumulate=False):
+    """y (bf16) = [y +] x (fp32)"""
+    _f32(x); _bf16(y)
+    assert y.is_contiguous() and x.numel() == y.numel()
+    _check(load().slb_flush_f32_to_bf16(_p(x), _p(y), C.c_int64(x.numel()), int(accumulate), _stream()), "flush_f32")
+    return y
+
+
 def add_inplace(a, b):
     _bf16(a, b)
     _check(load().slb_add_inplace_bf16(_p(a), _p(b), C.c_int64(a.numel()), _stream()), "add_inplace")
@@ -325,6 +341,13 @@ def scale_cols(x, s, out=None):
     _bf16(x, s)
     out = torch.empty_like(x) if out is None else out
     _check(load().slb_scale_cols(_p(x), _p(s), _p(out), x.shape[0], x.shape[1], _stream()), "scale_cols")
+    return out
+
+
+def scale_cols_add(x, s, res, out=None):
+    _bf16(x, s, res)
+    out = torch.empty_like(x) if out is None else out
+    _check(load().slb_scale_cols_add(_p(x), _p(s), _p(res), _p(out), x.shape[0], x.shape[1], _stream()), "scale_cols_add")
     return out
 
 

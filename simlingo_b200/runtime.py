@@ -36,7 +36,10 @@ def engine_for(module: nn.Module, prefix: str, spec: ModelSpec) -> Engine:
                 "team_code/agent_simlingo.py:213-222 does.")
         eng = Engine(sd, spec)
         attach_engine(module, eng)
-    else:
+    tr = module.__dict__.get("_slb_train_engine")
+    if tr is not None and eng.generation_fn is None:
+        eng.generation_fn = lambda st=tr.store: st.generation
+    if eng._packed_version is not None:
         eng.refresh(force=False)
     return eng
 
@@ -44,6 +47,7 @@ def engine_for(module: nn.Module, prefix: str, spec: ModelSpec) -> Engine:
 def invalidate(module: nn.Module) -> None:
     for m in module.modules():
         m.__dict__.pop(_KEY, None)
+        m.__dict__.pop("_slb_train_engine", None)
 
 
 def grad_mode(*tensors: Tensor) -> bool:

@@ -1,0 +1,658 @@
+"""Training runtime of the SimLingo hot path: forward with saved activations, hand-written backward, flat
+gradient / parameter buffers and the bucketed data-parallel gradient exchange.
+
+Replaces what the reference gets from torch autograd + flash-attn backward + PEFT + Lightning DDP / ZeRO-2 for
+``DrivingModel.training_step`` (reference ``simlingo_training/models/driving.py:236-271``, ``train.py:160-217``):
+
+* ``ParamStore``  - every trainable tensor (ViT, mlp1, LoRA A/B, heads, queries, wp_encoder; SURVEY 8a note 5) lives in
+  ONE flat bf16 parameter buffer and ONE flat bf16 gradient buffer, laid out in the order the backward pass finishes
+  them (LLM layers 23..0, mlp1, ViT layers 23..0, ViT embeddings, adaptor heads), so that completed ranges can be
+  all-reduced over NCCL/NVLink while the rest of the backward is still running, and the optimizer is one fused
+  kernel over the flat range (``simlingo_b200.optim.FusedAdamW``).
+* ``TrainEngine`` - sequences the sm_100a kernels: tcgen05 GEMMs for fprop / dgrad / wgrad (``slb_gemm_bf16`` with the
+  ``a_t`` / ``b_t`` operand forms), flash attention forward + backward, norm / activation / dropout / RoPE backward.
+  LoRA runs unmerged (``y = W x + b + (alpha/r) B A dropout(x)``, PEFT semantics) because A, B and the dropout mask
+  need gradients; the frozen Qwen2 base weights get no wgrad.
+* three coarse ``torch.autograd.Function`` s (vision tower + projector, decoder stack, LM head + cross-entropy) splice
+  the engine into the autograd graph of the drop-in modules; parameter gradients are written straight into the
+  flat buffer (the Functions return ``None`` for them), only activation gradients travel through autograd.
+
+No fallback: everything here needs the CUDA library and bf16 CUDA parameters."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+from . import lib
+from .engine import PATCH_KPAD
+from .spec import LLM_PREFIX, MLP1_PREFIX, VIT_PREFIX, ModelSpec
+
+_KEY = "_slb_train_engine"
+_ALIGN = 64  # elements; keeps every parameter 128-byte aligned inside the flat buffers (TMA needs 16 B)
+
+
+def _is_big(key: str) -> bool:
+    """Matrices whose gradient is produced by a wgrad GEMM directly in bf16; everything else in an engine-managed
+    group is accumulated in fp32 (column reductions / norm backward) and flushed once per group."""
+    if ".lora_A." in key or ".lora_B." in key:
+        return True
+    if key.startswith(VIT_PREFIX + "encoder.layers."):
+        return key.endswith(("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"))
+    if key.startswith(VIT_PREFIX + "embeddings."):
+        return key.endswith("patch_embedding.weight")
+    if key.startswith(MLP1_PREFIX):
+        return key.endswith(("1.weight", "3.weight"))
+    return False
+
+
+class _Group:
+    __slots__ = ("name", "keys", "small_keys", "start", "end", "small_start", "small_end", "acc_start", "managed")
+
+    def __init__(self, name: str, managed: bool):
+        self.name, self.managed = name, managed
+        self.keys: List[str] = []
+        self.small_keys: List[str] = []
+        self.start = self.end = self.small_start = self.small_end = self.acc_start = 0
+
+
+class ParamStore:
+    """Flat bf16 parameter + gradient buffers over the trainable parameters of ``root``.
+
+    ``prefix`` maps module-relative names to reference ``state_dict`` keys (``prefix + name``).  After construction
+    every trainable ``Parameter.data`` is a view into ``flat_param`` and ``grad_view[key]`` is the matching view into
+    ``flat_grad``."""
+
+    def __init__(self, root: nn.Module, prefix: str, spec: ModelSpec, bucket_bytes: int = 48 << 20):
+        self.spec = spec
+        params: Dict[str, nn.Parameter] = {}
+        for n, p in root.named_parameters():
+            if p.requires_grad:
+                if not (p.is_cuda and p.dtype == torch.bfloat16):
+                    raise RuntimeError(f"simlingo_b200 trains bf16 CUDA parameters only (no fallback): {n} is {p.dtype} on {p.device}")
+                params[prefix + n] = p
+        if not params:
+            raise RuntimeError("no trainable parameters")
+        self.params = params
+        dev = next(iter(params.values())).device
+        groups: List[_Group] = []
+
+        def take(name: str, pred, managed=True):
+            g = _Group(name, managed)
+            ks = [k for k in params if pred(k) and not any(k in gg.keys for gg in groups)]
+            if not ks:
+                return
+            g.keys = [k for k in ks if _is_big(k)] + [k for k in ks if not _is_big(k)] if managed else ks
+            g.small_keys = [k for k in ks if not _is_big(k)] if managed else []
+            groups.append(g)
+
+        for i in reversed(range(spec.llm_layers)):
+            take(f"llm{i}", lambda k, i=i: k.startswith(f"{LLM_PREFIX}model.layers.{i}."))
+        take("mlp1", lambda k: k.startswith(MLP1_PREFIX))
+        for i in reversed(range(spec.vit_layers)):
+            take(f"vit{i}", lambda k, i=i: k.startswith(f"{VIT_PREFIX}encoder.layers.{i}."))
+        take("vit_emb", lambda k: k.startswith(VIT_PREFIX + "embeddings."))
+        take("other", lambda k: True, managed=False)  # heads, queries, wp_encoder: gradients come from torch autograd
+        self.groups = groups
+        self.group_index = {g.name: i for i, g in enumerate(groups)}
+
+        off, acc_off = 0, 0
+        offsets: Dict[str, Tuple[int, int]] = {}
+        up = lambda n, a: (n + a - 1) // a * a
+        for g in groups:
+            g.start = off
+            for k in g.keys:
+                if k in g.small_keys:
+                    continue
+                offsets[k] = (off, params[k].numel())
+                off += up(params[k].numel(), _ALIGN)
+            g.small_start = off
+            for k in g.small_keys:  # packed densely (16-byte granules): one flush kernel covers the whole run
+                offsets[k] = (off, params[k].numel())
+                off += up(params[k].numel(), 8)
+            g.small_end = off
+            off = up(off, _ALIGN)
+            g.end = off
+            g.acc_start = acc_off
+            acc_off += g.small_end - g.small_start
+        self.numel = off
+        self.offsets = offsets
+        self.flat_param = torch.zeros(off, device=dev, dtype=torch.bfloat16)
+        self.flat_grad = torch.zeros(off, device=dev, dtype=torch.bfloat16)
+        self.small_acc = torch.zeros(max(acc_off, 1), device=dev, dtype=torch.float32)
+        self.grad_view: Dict[str, Tensor] = {}
+        self.acc_view: Dict[str, Tensor] = {}
+        with torch.no_grad():
+            for k, p in params.items():
+                o, n = offsets[k]
+                v = self.flat_param[o:o + n].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                self.grad_view[k] = self.flat_grad[o:o + n].view(p.shape)
+        for g in groups:
+            for k in g.small_keys:
+                o, n = offsets[k]
+                a = g.acc_start + (o - g.small_start)
+                self.acc_view[k] = self.small_acc[a:a + n]
+        self.managed_keys = {k for g in groups if g.managed for k in g.keys}
+        self.accumulate = False          # True once a backward has deposited gradients that must be added to
+        self.generation = 0              # bumped by the optimizer: derived inference weights are stale
+        # ---- data-parallel exchange -----------------------------------------------------------------
+        self.pg = None
+        self.world = 1
+        self._buckets: List[Tuple[int, int, int]] = []  # (start, end, index of the last group inside)
+        self._works: list = []
+        self._next_bucket = 0
+        self.bucket_bytes = bucket_bytes
+        self._make_buckets()
+        self.n_allreduce = 0
+
+    # ---- layout helpers -----------------------------------------------------------------------------
+    def _make_buckets(self) -> None:
+        self._buckets = []
+        start, last = 0, -1
+        for gi, g in enumerate(self.groups):
+            last = gi
+            if (g.end - start) * 2 >= self.bucket_bytes or gi == len(self.groups) - 1:
+                self._buckets.append((start, g.end, gi))
+                start = g.end
+
+    def target(self, key: str) -> Tuple[Tensor, bool]:
+        return self.grad_view[key], self.accumulate
+
+    # ---- step protocol ------------------------------------------------------------------------------
+    def begin_backward(self) -> None:
+        self.small_acc.zero_()
+        self._next_bucket = 0
+        self._works = []
+
+    def flush_group(self, name: str) -> None:
+        """fp32 accumulators of the group's small parameters -> flat bf16 gradients; then the group is final."""
+        gi = self.group_index.get(name)
+        if gi is None:
+            return
+        g = self.groups[gi]
+        n = g.small_end - g.small_start
+        if n > 0:
+            lib.flush_f32(self.small_acc[g.acc_start:g.acc_start + n], self.flat_grad[g.small_start:g.small_end], self.accumulate)
+        self.group_ready(gi)
+
+    def enable_data_parallel(self, process_group=None) -> None:
+        """Average gradients over the ranks of ``process_group`` (default: the world group): SUM all-reduce of the flat
+        bf16 gradient range, bucketed and issued as the backward pass completes each bucket; the 1/world factor is
+        folded into the fused optimizer kernel."""
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("torch.distributed is not initialised")
+        self.pg = process_group if process_group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.pg)
+
+    def group_ready(self, gi: int) -> None:
+        if self.pg is None or self.world == 1:
+            return
+        while self._next_bucket < len(self._buckets) and self._buckets[self._next_bucket][2] <= gi:
+            a, b, _ = self._buckets[self._next_bucket]
+            # async_op: NCCL runs on its own stream after an event on the current (compute) stream
+            self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            self.n_allreduce += 1
+            self._next_bucket += 1
+
+    def finish_backward(self) -> None:
+        """End-of-backward hook: adopt gradients autograd produced for the torch-managed parameters, expose
+        ``p.grad`` views, launch the remaining all-reduce buckets."""
+        for k, p in self.params.items():
+            v = self.grad_view[k]
+            if k not in self.managed_keys and p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                if self.accumulate:
+                    v.add_(p.grad)
+                else:
+                    v.copy_(p.grad)
+            p.grad = v
+        self.group_ready(len(self.groups) - 1)
+        self.accumulate = True
+
+    def wait_exchange(self) -> None:
+        for w in self._works:
+            w.wait()
+        self._works = []
+
+    def zero_grad(self) -> None:
+        """Engine-managed gradients are overwritten by the next backward; the torch-managed tail is zeroed so that
+        autograd can accumulate into the views in place."""
+        g = self.groups[-1]
+        if not g.managed:
+            self.flat_grad[g.start:g.end].zero_()
+        for k, p in self.params.items():
+            p.grad = self.grad_view[k] if k not in self.managed_keys else None
+        self.accumulate = False
+
+
+# ====================================================================================================
+class TrainEngine:
+    def __init__(self, root: nn.Module, prefix: str, spec: ModelSpec):
+        if not torch.cuda.is_available():
+            raise RuntimeError("simlingo_b200 training needs a CUDA device (sm_100a); there is no CPU fallback")
+        lib.load()
+        self.spec = spec
+        self.root = root
+        self.store = ParamStore(root, prefix, spec)
+        self.P: Dict[str, Tensor] = {prefix + k: v for k, v in root.state_dict(keep_vars=True).items()}
+        self.dev = self.store.flat_param.device
+        self.launches = 0
+        self.seed_counter = 0
+        self.base_seed = 0x5151
+        self._frozen = None
+
+    # ---- weights ---------------------------------------------------------------------------------------
+    def w(self, key: str) -> Tensor:
+        return self.P[key].detach()
+
+    def frozen(self):
+        """Concatenated q|k|v base weights / biases of the frozen Qwen2 layers (built once)."""
+        if self._frozen is None:
+            out = []
+            for i in range(self.spec.llm_layers):
+                p = f"{LLM_PREFIX}model.layers.{i}.self_attn."
+                out.append((torch.cat([self.w(p + f"{n}_proj.base_layer.weight") for n in "qkv"], 0).contiguous(),
+                            torch.cat([self.w(p + f"{n}_proj.base_layer.bias") for n in "qkv"], 0).contiguous()))
+            self._frozen = out
+        return self._frozen
+
+    def _wgrad(self, dy: Tensor, x: Tensor, key: str, alpha: float = 1.0) -> None:
+        """grad[key] (+)= alpha * dy^T x      dy [M, out], x [M, in] -> [out, in]"""
+        g, acc = self.store.target(key)
+        g2 = g.view(g.shape[0], -1)
+        lib.gemm(dy, x, out=g2, a_t=True, b_t=True, alpha=alpha, residual=g2 if acc else None)
+        self.launches += 1
+
+    def _acc(self, key: str) -> Tensor:
+        return self.store.acc_view[key]
+
+    # ==================================================================================================
+    # vision tower + projector
+    # ==================================================================================================
+    def vision_forward(self, pixels: Tensor):
+        s, w = self.spec, self.w
+        T = pixels.shape[0]
+        N, Dv = s.vit_tokens, s.vit_hidden
+        M = T * N
+        e = VIT_PREFIX + "embeddings."
+        dev, bf = self.dev, torch.bfloat16
+        pw = torch.zeros((Dv, PATCH_KPAD), device=dev, dtype=bf)
+        pw[:, : s.patch_k] = w(e + "patch_embedding.weight").reshape(Dv, s.patch_k)
+        cols = lib.im2col_patch(pixels.contiguous(), PATCH_KPAD)
+        po = lib.gemm(cols, pw, bias=w(e + "patch_embedding.bias"))
+        x = lib.vit_assemble(po, w(e + "class_embedding"), w(e + "position_embedding"), T)
+        del po
+        layers = []
+        f32 = lambda n: torch.empty(n, device=dev, dtype=torch.float32)
+        for i in range(s.vit_layers):
+            p = f"{VIT_PREFIX}encoder.layers.{i}."
+            st1, st2 = (f32(M), f32(M)), (f32(M), f32(M))
+            h1 = lib.layernorm(x, w(p + "norm1.weight"), w(p + "norm1.bias"), s.vit_eps, stats=st1)
+            qkv = lib.gemm(h1, w(p + "attn.qkv.weight"), bias=w(p + "attn.qkv.bias"))
+            lse = torch.empty((T, s.vit_heads, N), device=dev, dtype=torch.float32)
+            att = lib.attn_vit(qkv, T, N, s.vit_heads, lse=lse)
+            p1 = lib.gemm(att, w(p + "attn.proj.weight"), bias=w(p + "attn.proj.bias"))
+            xm = lib.scale_cols_add(p1, w(p + "ls1"), x)
+            h2 = lib.layernorm(xm, w(p + "norm2.weight"), w(p + "norm2.bias"), s.vit_eps, stats=st2)
+            fpre = lib.gemm(h2, w(p + "mlp.fc1.weight"), bias=w(p + "mlp.fc1.bias"))
+            fact = lib.gelu_fwd(fpre)
+            p2 = lib.gemm(fact, w(p + "mlp.fc2.weight"), bias=w(p + "mlp.fc2.bias"))
+            xo = lib.scale_cols_add(p2, w(p + "ls2"), xm)
+            layers.append(dict(x=x, st1=st1, h1=h1, qkv=qkv, lse=lse, att=att, p1=p1, xm=xm, st2=st2, h2=h2, fpre=fpre, fact=fact, p2=p2))
+            x = xo
+        self.launches += 3 + 10 * s.vit_layers
+        # projector: drop CLS + pixel shuffle + LN(4096) -> Linear -> GELU -> Linear
+        stp = (f32(T * s.tokens_per_tile), f32(T * s.tokens_per_tile))
+        y0 = lib.pixel_shuffle_ln(x, w(MLP1_PREFIX + "0.weight"), w(MLP1_PREFIX + "0.bias"), T, s.proj_eps, stats=stp)
+        y1p = lib.gemm(y0, w(MLP1_PREFIX + "1.weight"), bias=w(MLP1_PREFIX + "1.bias"))
+        y1 = lib.gelu_fwd(y1p)
+        y2 = lib.gemm(y1, w(MLP1_PREFIX + "3.weight"), bias=w(MLP1_PREFIX + "3.bias"))
+        self.launches += 4
+        saved = dict(T=T, cols=cols, layers=layers, xv=x, stp=stp, y0=y0, y1p=y1p, y1=y1)
+        return y2, saved
+
+    def vision_backward(self, dy2: Tensor, sv) -> None:
+        s, w, st = self.spec, self.w, self.store
+        T = sv["T"]
+        dy2 = dy2.contiguous()
+        # ---- projector ----
+        lib.col_reduce(dy2, self._acc(MLP1_PREFIX + "3.bias"))
+        self._wgrad(dy2, sv["y1"], MLP1_PREFIX + "3.weight")
+        dy1 = lib.gemm(dy2, w(MLP1_PREFIX + "3.weight"), b_t=True)
+        dy1p = lib.gelu_bwd(sv["y1p"], dy1)
+        lib.col_reduce(dy1p, self._acc(MLP1_PREFIX + "1.bias"))
+        self._wgrad(dy1p, sv["y0"], MLP1_PREFIX + "1.weight")
+        dy0 = lib.gemm(dy1p, w(MLP1_PREFIX + "1.weight"), b_t=True)
+        dx = lib.pixel_shuffle_ln_bwd(dy0, sv["xv"], w(MLP1_PREFIX + "0.weight"), sv["stp"][0], sv["stp"][1],
+                                      self._acc(MLP1_PREFIX + "0.weight"), self._acc(MLP1_PREFIX + "0.bias"), T)
+        del dy0, dy1, dy1p
+        self.launches += 7
+        st.flush_group("mlp1")
+        # ---- encoder layers ----
+        for i in reversed(range(s.vit_layers)):
+            p = f"{VIT_PREFIX}encoder.layers.{i}."
+            a = sv["layers"][i]
+            sv["layers"][i] = None
+            lib.col_reduce(dx, self._acc(p + "ls2"), a["p2"])
+            dp2 = lib.scale_cols(dx, w(p + "ls2"))
+            lib.col_reduce(dp2, self._acc(p + "mlp.fc2.bias"))
+            self._wgrad(dp2, a["fact"], p + "mlp.fc2.weight")
+            dfact = lib.gemm(dp2, w(p + "mlp.fc2.weight"), b_t=True)
+            dfpre = lib.gelu_bwd(a["fpre"], dfact, out=dfact)
+            lib.col_reduce(dfpre, self._acc(p + "mlp.fc1.bias"))
+            self._wgrad(dfpre, a["h2"], p + "mlp.fc1.weight")
+            dh2 = lib.gemm(dfpre, w(p + "mlp.fc1.weight"), b_t=True, out=dp2)
+            dxm = lib.layernorm_bwd(dh2, a["xm"], w(p + "norm2.weight"), a["st2"][0], a["st2"][1],
+                                    self._acc(p + "norm2.weight"), self._acc(p + "norm2.bias"))
+            lib.add_inplace(dxm, dx)
+            lib.col_reduce(dxm, self._acc(p + "ls1"), a["p1"])
+            dp1 = lib.scale_cols(dxm, w(p + "ls1"), out=dx)
+            lib.col_reduce(dp1, self._acc(p + "attn.proj.bias"))
+            self._wgrad(dp1, a["att"], p + "attn.proj.weight")
+            datt = lib.gemm(dp1, w(p + "attn.proj.weight"), b_t=True, out=dh2)
+            delta = lib.attn_delta(a["att"], datt, T, s.vit_tokens, s.vit_heads)
+            dq, dk, dv = lib.attn_vit_bwd(a["qkv"], datt, a["lse"], delta, T, s.vit_tokens, s.vit_heads)
+            dqkv = lib.rope_bwd(dq, dk, dv, T, s.vit_tokens, s.vit_heads, s.vit_heads, 0.0)
+            del dq, dk, dv
+            lib.col_reduce(dqkv, self._acc(p + "attn.qkv.bias"))
+            self._wgrad(dqkv, a["h1"], p + "attn.qkv.weight")
+            dh1 = lib.gemm(dqkv, w(p + "attn.qkv.weight"), b_t=True, out=dp1)
+            dxi = lib.layernorm_bwd(dh1, a["x"], w(p + "norm1.weight"), a["st1"][0], a["st1"][1],
+                                    self._acc(p + "norm1.weight"), self._acc(p + "norm1.bias"), dx=datt)
+            lib.add_inplace(dxi, dxm)
+            dx = dxi
+            self.launches += 24
+            st.flush_group(f"vit{i}")
+        # ---- embeddings ----
+        e = VIT_PREFIX + "embeddings."
+        dpo = lib.vit_assemble_bwd(dx, self._acc(e + "class_embedding"), self._acc(e + "position_embedding"), T)
+        lib.col_reduce(dpo, self._acc(e + "patch_embedding.bias"))
+        gw = lib.gemm(dpo, sv["cols"], a_t=True, b_t=True)  # [1024, 640]
+        g, acc = st.target(e + "patch_embedding.weight")
+        g2 = g.view(s.vit_hidden, s.patch_k)
+        if acc:
+            g2.add_(gw[:, : s.patch_k])
+        else:
+            g2.copy_(gw[:, : s.patch_k])
+        self.launches += 4
+        st.flush_group("vit_emb")
+
+    # ==================================================================================================
+    # Qwen2 decoder stack with un-merged LoRA
+    # ==================================================================================================
+    def _lora_fwd(self, x: Tensor, pre: str, y: Tensor, seed: Optional[int]):
+        """y (holding base(x)) += scale * B(A(dropout(x)))   [PEFT lora.Linear.forward]"""
+        if seed is not None:
+            xd = lib.dropout(x, self.spec.lora_dropout, seed)
+            self.launches += 1
+        else:
+            xd = x
+        t = lib.gemm(xd, self.w(pre + "lora_A.default.weight"))
+        lib.gemm(t, self.w(pre + "lora_B.default.weight"), out=y, residual=y, alpha=self.spec.lora_scale)
+        self.launches += 2
+        return xd, t, seed
+
+    def _lora_bwd(self, dy: Tensor, pre: str, rec, dx: Tensor) -> None:
+        xd, t, seed = rec
+        sc = self.spec.lora_scale
+        self._wgrad(dy, t, pre + "lora_B.default.weight", alpha=sc)
+        dt = lib.gemm(dy, self.w(pre + "lora_B.default.weight"), b_t=True, alpha=sc)
+        self._wgrad(dt, xd, pre + "lora_A.default.weight")
+        if seed is None:
+            lib.gemm(dt, self.w(pre + "lora_A.default.weight"), b_t=True, out=dx, residual=dx)
+        else:
+            dxd = lib.gemm(dt, self.w(pre + "lora_A.default.weight"), b_t=True)
+            lib.dropout_add(dxd, dx, self.spec.lora_dropout, seed)
+            self.launches += 1
+        self.launches += 2
+
+    def llm_forward(self, inputs: Tensor, mask: Optional[Tensor], dropout: bool):
+        """inputs [B, Lt, D] bf16 -> (features after the final norm [B, Lt, D], saved)"""
+        s, w = self.spec, self.w
+        B, Lt, D = inputs.shape
+        M = B * Lt
+        dev, bf = self.dev, torch.bfloat16
+        Hq, Hkv, hd, I = s.llm_heads, s.llm_kv_heads, s.head_dim, s.llm_mlp
+        qd, kd = Hq * hd, Hkv * hd
+        lmax = (Lt + 127) // 128 * 128
+        kc = torch.zeros((s.llm_layers, B, Hkv, lmax, hd), device=dev, dtype=bf)
+        vc = torch.zeros_like(kc)
+        kv_valid = None
+        if mask is not None and not bool(mask.all()):
+            kv_valid = torch.zeros((B, lmax), device=dev, dtype=torch.uint8)
+            kv_valid[:, :Lt] = mask.to(torch.uint8)
+        use_drop = dropout and s.lora_dropout > 0
+        self.seed_counter += 1
+
+        def seed(i, j):
+            return ((self.base_seed + self.seed_counter) << 16) + i * 8 + j if use_drop else None
+
+        x = inputs.reshape(M, D).contiguous()
+        frozen = self.frozen()
+        layers = []
+        for i in range(s.llm_layers):
+            p = f"{LLM_PREFIX}model.layers.{i}."
+            pa, pm = p + "self_attn.", p + "mlp."
+            r1 = torch.empty(M, device=dev, dtype=torch.float32)
+            h1 = lib.rmsnorm(x, w(p + "input_layernorm.weight"), s.rms_eps, rstd=r1)
+            qkv = lib.gemm(h1, frozen[i][0], bias=frozen[i][1])
+            lq = self._lora_fwd(h1, pa + "q_proj.", qkv[:, :qd], seed(i, 0))
+            lk = self._lora_fwd(h1, pa + "k_proj.", qkv[:, qd:qd + kd], seed(i, 1))
+            lv = self._lora_fwd(h1, pa + "v_proj.", qkv[:, qd + kd:], seed(i, 2))
+            lib.rope_kv_write(qkv, kc[i], vc[i], B, Lt, 0, Hq, Hkv, s.rope_theta)
+            lse = torch.empty((B, Hq, Lt), device=dev, dtype=torch.float32)
+            att = lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], B, Lt, 0, Hq, Hkv, key_valid=kv_valid, lse=lse)
+            xm = lib.gemm(att, w(pa + "o_proj.base_layer.weight"), residual=x)
+            lo = self._lora_fwd(att, pa + "o_proj.", xm, seed(i, 3))
+            r2 = torch.empty(M, device=dev, dtype=torch.float32)
+            h2 = lib.rmsnorm(xm, w(p + "post_attention_layernorm.weight"), s.rms_eps, rstd=r2)
+            g = lib.gemm(h2, w(pm + "gate_proj.base_layer.weight"))
+            lg = self._lora_fwd(h2, pm + "gate_proj.", g, seed(i, 4))
+            u = lib.gemm(h2, w(pm + "up_proj.base_layer.weight"))
+            lu = self._lora_fwd(h2, pm + "up_proj.", u, seed(i, 5))
+            act = lib.silu_mul(g, u)
+            xo = lib.gemm(act, w(pm + "down_proj.base_layer.weight"), residual=xm)
+            ld = self._lora_fwd(act, pm + "down_proj.", xo, seed(i, 6))
+            layers.append(dict(x=x, r1=r1, h1=h1, qkv=qkv, lse=lse, att=att, xm=xm, r2=r2, h2=h2, g=g, u=u, act=act,
+                               lora=(lq, lk, lv, lo, lg, lu, ld)))
+            x = xo
+            self.launches += 10
+        rf = torch.empty(M, device=dev, dtype=torch.float32)
+        feats = lib.rmsnorm(x, w(LLM_PREFIX + "model.norm.weight"), s.rms_eps, rstd=rf)
+        self.launches += 1
+        saved = dict(B=B, Lt=Lt, layers=layers, kc=kc, vc=vc, kv_valid=kv_valid, xf=x, rf=rf)
+        return feats.view(B, Lt, D), saved
+
+    def llm_backward(self, dfeats: Tensor, sv) -> Tensor:
+        s, w, st = self.spec, self.w, self.store
+        B, Lt = sv["B"], sv["Lt"]
+        D = s.llm_hidden
+        M = B * Lt
+        Hq, Hkv, hd = s.llm_heads, s.llm_kv_heads, s.head_dim
+        qd, kd = Hq * hd, Hkv * hd
+        kvv = sv["kv_valid"]
+        frozen = self.frozen()
+        dx = lib.rmsnorm_bwd(dfeats.reshape(M, D).contiguous(), sv["xf"], w(LLM_PREFIX + "model.norm.weight"), sv["rf"])
+        self.launches += 1
+        for i in reversed(range(s.llm_layers)):
+            p = f"{LLM_PREFIX}model.layers.{i}."
+            pa, pm = p + "self_attn.", p + "mlp."
+            a = sv["layers"][i]
+            sv["layers"][i] = None
+            lq, lk, lv, lo, lg, lu, ld = a["lora"]
+            # ---- MLP ----
+            dact = lib.gemm(dx, w(pm + "down_proj.base_layer.weight"), b_t=True)
+            self._lora_bwd(dx, pm + "down_proj.", ld, dact)
+            dg, du = lib.silu_mul_bwd(a["g"], a["u"], dact)
+            dh2 = lib.gemm(dg, w(pm + "gate_proj.base_layer.weight"), b_t=True)
+            lib.gemm(du, w(pm + "up_proj.base_layer.weight"), b_t=True, out=dh2, residual=dh2)
+            self._lora_bwd(dg, pm + "gate_proj.", lg, dh2)
+            self._lora_bwd(du, pm + "up_proj.", lu, dh2)
+            dxm = lib.rmsnorm_bwd(dh2, a["xm"], w(p + "post_attention_layernorm.weight"), a["r2"])
+            lib.add_inplace(dxm, dx)
+            # ---- attention ----
+            datt = lib.gemm(dxm, w(pa + "o_proj.base_layer.weight"), b_t=True)
+            self._lora_bwd(dxm, pa + "o_proj.", lo, datt)
+            delta = lib.attn_delta(a["att"], datt, B, Lt, Hq)
+            dq, dk, dv = lib.attn_gqa_bwd(a["qkv"], s.qkv_dim, sv["kc"][i], sv["vc"][i], datt, a["lse"], delta, B, Lt, Hq, Hkv, key_valid=kvv)
+            dqkv = lib.rope_bwd(dq, dk, dv, B, Lt, Hq, Hkv, s.rope_theta)
+            del dq, dk, dv
+            dh1 = lib.gemm(dqkv, frozen[i][0], b_t=True)
+            self._lora_bwd(dqkv[:, :qd], pa + "q_proj.", lq, dh1)
+            self._lora_bwd(dqkv[:, qd:qd + kd], pa + "k_proj.", lk, dh1)
+            self._lora_bwd(dqkv[:, qd + kd:], pa + "v_proj.", lv, dh1)
+            dxi = lib.rmsnorm_bwd(dh1, a["x"], w(p + "input_layernorm.weight"), a["r1"])
+            lib.add_inplace(dxi, dxm)
+            dx = dxi
+            self.launches += 14
+            st.flush_group(f"llm{i}")
+        return dx.view(B, Lt, D)
+
+
+# ====================================================================================================
+# engine lookup and autograd splice
+# ====================================================================================================
+def engine_for(module: nn.Module, prefix: str, spec: ModelSpec) -> TrainEngine:
+    eng: Optional[TrainEngine] = module.__dict__.get(_KEY)
+    if eng is None:
+        eng = TrainEngine(module, prefix, spec)
+        module.__dict__[_KEY] = eng
+    return eng
+
+
+def attach(module: nn.Module, eng: TrainEngine) -> None:
+    module.__dict__[_KEY] = eng
+
+
+def ensure_store(root: nn.Module, spec: ModelSpec) -> ParamStore:
+    """Builds (once) the flat parameter / gradient store over the whole model and shares its engine with the
+    sub-modules that can also be entered on their own (``extract_feature``, ``Qwen2ForCausalLM``)."""
+    eng = engine_for(root, "", spec)
+    for m in root.modules():
+        if hasattr(m, "spec") and m is not root and type(m).__name__ in ("InternVLChatModel", "Qwen2ForCausalLM"):
+            attach(m, eng)
+    return eng.store
+
+
+def _anchor(eng: TrainEngine, prefix: str) -> Tensor:
+    """Any trainable parameter of the sub-network: ties the Function into the autograd graph (its own gradient is
+    written to the flat buffer like all the others)."""
+    for k, p in eng.store.params.items():
+        if k.startswith(prefix):
+            return p
+    raise RuntimeError(f"no trainable parameter under {prefix}")
+
+
+def _queue_finish(store: ParamStore) -> None:
+    if not getattr(store, "_finish_queued", False):
+        store._finish_queued = True
+
+        def cb():
+            store._finish_queued = False
+            store.finish_backward()
+        torch.autograd.Variable._execution_engine.queue_callback(cb)
+        store.begin_backward()
+
+
+class _VisionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pixels: Tensor, anchor: Tensor, eng: TrainEngine):
+        out, saved = eng.vision_forward(pixels)
+        ctx.eng, ctx.saved = eng, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        _queue_finish(ctx.eng.store)
+        ctx.eng.vision_backward(dout, ctx.saved)
+        ctx.saved = None
+        return None, None, None
+
+
+class _LLMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs: Tensor, anchor: Tensor, eng: TrainEngine, mask: Optional[Tensor], dropout: bool):
+        feats, saved = eng.llm_forward(inputs, mask, dropout)
+        ctx.eng, ctx.saved = eng, saved
+        return feats
+
+    @staticmethod
+    def backward(ctx, dfeats: Tensor):
+        _queue_finish(ctx.eng.store)
+        dx = ctx.eng.llm_backward(dfeats.to(torch.bfloat16), ctx.saved)
+        ctx.saved = None
+        return dx, None, None, None, None
+
+
+class _HeadCEFn(torch.autograd.Function):
+    """loss[r] = CE(lm_head(x[r]), label[r]) with the frozen LM head: fp32 logits from the tcgen05 GEMM, fused
+    softmax / loss / dlogits kernel, and d x = dlogits @ W computed right away (the upstream gradient is a per-row
+    scale)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, labels: Tensor):
+        xb = x.to(torch.bfloat16).contiguous()
+        logits = lib.gemm(xb, weight.detach(), out_fp32=True)
+        need = x.requires_grad
+        loss, dl = lib.ce_fwd_bwd(logits, labels, 1.0, want_grad=need)
+        if need:
+            wpad = weight.detach()
+            V = wpad.shape[0]
+            ctx.dx_unit = lib.gemm(dl[:, :V], wpad, b_t=True)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss: Tensor):
+        return (ctx.dx_unit.float() * dloss.float()[:, None]).to(ctx.dx_unit.dtype), None, None
+
+
+# ---- entry points used by simlingo_b200.runtime / the drop-in modules ------------------------------
+def extract_feature(chat_model: nn.Module, pixel_values: Tensor) -> Tensor:
+    spec = chat_model.spec
+    prefix = VIT_PREFIX[: -len("vision_model.")]
+    eng = engine_for(chat_model, prefix, spec)
+    px = pixel_values.to(torch.bfloat16).contiguous()
+    out = _VisionFn.apply(px, _anchor(eng, MLP1_PREFIX), eng)
+    return out.view(px.shape[0], spec.tokens_per_tile, spec.llm_hidden)
+
+
+def llm_forward(causal_lm: nn.Module, inputs_embeds: Tensor, attention_mask: Optional[Tensor], want_logits: bool):
+    spec = causal_lm.spec
+    eng = engine_for(causal_lm, LLM_PREFIX, spec)
+    mask = None if attention_mask is None else attention_mask.to(torch.bool)
+    feats = _LLMFn.apply(inputs_embeds.to(torch.bfloat16), _anchor(eng, LLM_PREFIX), eng, mask, bool(causal_lm.training))
+    logits = None
+    if want_logits:
+        B, L, D = feats.shape
+        logits = linear_frozen(feats.reshape(B * L, D), causal_lm.lm_head.weight).view(B, L, spec.vocab)
+    return feats, logits
+
+
+class _FrozenLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor):
+        ctx.weight, ctx.shape = weight.detach(), x.shape
+        flat = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()
+        return lib.gemm(flat, ctx.weight, out_fp32=True).view(*x.shape[:-1], weight.shape[0]).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        V = ctx.weight.shape[0]
+        vp = (V + 7) // 8 * 8
+        d2 = torch.zeros((dy.numel() // V, vp), device=dy.device, dtype=torch.bfloat16)
+        d2[:, :V] = dy.reshape(-1, V)
+        return lib.gemm(d2[:, :V], ctx.weight, b_t=True).view(ctx.shape), None
+
+
+def linear_frozen(x: Tensor, weight: Tensor) -> Tensor:
+    """x @ weight^T for a frozen weight (LM head) with gradient to x only."""
+    return _FrozenLinearFn.apply(x, weight)
+
+
+def lm_head_ce(features_rows: Tensor, weight: Tensor, labels: Tensor) -> Tensor:
+    """Per-row cross-entropy of ``lm_head(features_rows)`` against ``labels`` (fp32 [R]); ``adaptors.py:268-274``
+    evaluated only where a label exists."""
+    return _HeadCEFn.apply(features_rows, weight, labels.contiguous())

@@ -203,8 +203,13 @@ class LanguageAdaptor(nn.Module):
             rows = labels.ne(-1)
             loss = torch.zeros(labels.shape, device=labels.device, dtype=torch.float32)
             if rows.any():
-                lg = self.lm_head(adaptor_features[:, :-1][rows])
-                loss[rows] = F.cross_entropy(lg.float(), labels[rows], reduction="none")
+                feats = adaptor_features[:, :-1][rows]
+                if feats.is_cuda and self.lm_head.weight.dtype == torch.bfloat16:
+                    from simlingo_b200 import training as _tr
+                    row_loss = _tr.lm_head_ce(feats, self.lm_head.weight, labels[rows])
+                else:
+                    row_loss = F.cross_entropy(self.lm_head(feats).float(), labels[rows], reduction="none")
+                loss = loss.masked_scatter(rows, row_loss)
             return {"language_loss": (loss, rows)}
         lg = adaptor_logits[:, :-1]
         loss = F.cross_entropy(lg.flatten(0, -2), labels.flatten(), ignore_index=-1, reduction="none").view_as(labels)

@@ -154,8 +154,17 @@ class DrivingModel(_Base):
                                         want_logits=want_logits)
         return feats, logits
 
+    def param_store(self):
+        """Flat bf16 parameter / gradient store of the trainable tensors (created on first use): the hand-written
+        backward writes gradients there, ``FusedAdamW`` updates it in one kernel, and
+        ``param_store().enable_data_parallel()`` turns on the bucketed NCCL gradient all-reduce."""
+        from simlingo_b200 import training
+        return training.ensure_store(self, self.spec)
+
     def forward_loss(self, example: DrivingExample, per_sample=False):
         """Forward + next-token CE on the answer tokens + smooth-L1 on route / speed waypoints."""
+        if torch.is_grad_enabled():
+            self.param_store()
         adaptor_dict = self.adaptors(example)
         feats, _ = self.forward_model(example.driving_input, adaptor_dict, driving_labels=example.driving_label, want_logits=False)
         loss_dict = self.adaptors.compute_loss(feats, None, adaptor_dict, example)
@@ -213,12 +222,21 @@ class DrivingModel(_Base):
         for k, v in sorted(losses.items()):
             self.log(f"{mode}_losses/{k}", v, batch_size=counts[k], sync_dist=True, add_dataloader_idx=False)
 
+    def configure_gradient_clipping(self, optimizer, gradient_clip_val=None, gradient_clip_algorithm=None):
+        """Lightning hook (``Trainer(gradient_clip_val=0.3)``, reference train.py:206): the global-norm clip is folded
+        into the fused AdamW kernel instead of a separate pass over the gradients."""
+        opt = getattr(optimizer, "optimizer", optimizer)
+        if gradient_clip_algorithm not in (None, "norm"):
+            raise NotImplementedError("only global-norm clipping is implemented")
+        opt.max_grad_norm = float(gradient_clip_val or 0.0)
+
     def configure_optimizers(self):
         """AdamW(lr, weight_decay, betas) over all parameters + per-step OneCycleLR (reference :718-732), realised
         by the fused multi-tensor AdamW kernel with fp32 master weights."""
         from simlingo_b200.optim import FusedAdamW
-        optimizer = FusedAdamW([p for p in self.parameters() if p.requires_grad], lr=self.lr, weight_decay=self.weight_decay,
-                               betas=tuple(self.betas))
+        optimizer = FusedAdamW([p for p in self.parameters() if p.requires_grad], self.param_store(), lr=self.lr,
+                               weight_decay=self.weight_decay, betas=tuple(self.betas),
+                               max_grad_norm=float(getattr(self, "gradient_clip_val", 0.0) or 0.0))
         trainer = self.trainer
         max_steps = trainer.estimated_stepping_batches if trainer.max_steps == -1 else trainer.max_steps
         scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=self.lr, total_steps=max_steps, pct_start=self.pct_start)

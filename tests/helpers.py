@@ -46,3 +46,30 @@ def to_driving_input(case, device=None, dtype=None):
                           [""] * case["ids"].shape[0], mv(case["loss_masking"]))
     z = mv(torch.zeros(case["ids"].shape[0], 1))
     return DrivingInput(mv(fr), z, z, z, z, z, label, label)
+
+
+def build_drop_in_model(spec, name, seed=0, device="cuda"):
+    """DrivingModel (drop-in mirror) on ``spec`` with the deterministic synthetic weights, bf16 on ``device``."""
+    from simlingo_b200.modules import register_variant
+    from simlingo_b200.spec import init_state_dict
+    from simlingo_training.models.driving import DrivingModel
+    register_variant(name, spec)
+    cfg = dict(vision_model=dict(_target_="simlingo_training.models.encoder.vlm.VLMEncoderModel", variant=name, embed_dim=512, freeze=False),
+               language_model=dict(_target_="simlingo_training.models.language_model.llm.LLM", variant=name, lora=True, lora_alpha=64,
+                                   lora_r=32, lora_dropout=0.1),
+               lr=3e-5, weight_decay=0.1, betas=(0.9, 0.999), pct_start=0.05, speed_wps_mode="2d", predict_route_as_wps=True)
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        m = DrivingModel(cfg_data_module={"use_global_img": False}, processor=StubTokenizer(spec), cache_dir=None, **cfg)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    m.load_state_dict(init_state_dict(spec, seed=seed, with_aliases=True), strict=True)
+    return m.to(device)
+
+
+def to_driving_example(case, device="cuda", dtype=torch.bfloat16):
+    from simlingo_training.utils.custom_types import DrivingExample, DrivingLabel
+    di = to_driving_input(case, device, dtype)
+    wps, path = case["labels"]
+    B = case["ids"].shape[0]
+    return DrivingExample(di, DrivingLabel(wps.to(device), path.to(device), di.prompt, torch.zeros(1)), ["x"] * B)
