@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the SimLingo (InternVL2-1B) VLA hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload offline64|agent] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload offline64|train] [--impl ours|reference]
 
 Default workload (BASELINE.json configs[2], the configuration the frames/s metric is quoted on):
 "offline batched forward": 64 synthetic frames per GPU per step = 128 InternViT tiles -> pixel-shuffle/mlp1 ->
@@ -150,7 +150,7 @@ def offline_step(model, example):
     return pred["route"], pred["speed_wps"]
 
 
-def gemm_roofline(model, example, peaks):
+def gemm_roofline(model, example, peaks, step_fn=None):
     """Times every launch of the tcgen05 GEMM kernel inside one step with CUDA events (on the launch stream)."""
     from simlingo_b200 import lib
     orig = lib.gemm
@@ -168,7 +168,7 @@ def gemm_roofline(model, example, peaks):
 
     lib.gemm = timed
     try:
-        offline_step(model, example)
+        (step_fn or (lambda: offline_step(model, example)))()
         torch.cuda.synchronize()
     finally:
         lib.gemm = orig
@@ -204,19 +204,196 @@ def cpu_oracle_frames_per_s(steps: int, warmup: int, frames: int = 1):
     return frames / t, cores, t
 
 
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: training step (full ViT + LoRA Qwen2, fused AdamW), batch 8 / GPU, DP gradient all-reduce
+# --------------------------------------------------------------------------------------------------
+TRAIN_BATCH = 8
+ANSWER_LEN = 16
+
+
+def host_train_batch(spec, batch, seed):
+    ids = S.synth_prompt_ids(spec, batch, seed, answer_len=ANSWER_LEN)
+    g = torch.Generator().manual_seed(seed + 9)
+    frames = torch.randn((batch, 1, spec.tiles_per_frame, 3, spec.image, spec.image), generator=g).clamp_(-2.2, 2.7).to(torch.bfloat16)
+    valid = torch.ones_like(ids, dtype=torch.bool)
+    lm = torch.zeros_like(valid)
+    lm[:, -ANSWER_LEN:] = True
+    wps, path = S.synth_labels(spec, batch, seed)
+    return dict(ids=ids.pin_memory(), frames=frames.pin_memory(), valid=valid.pin_memory(), loss_masking=lm.pin_memory(),
+                wps=wps.pin_memory(), path=path.pin_memory(), placeholders=S.synth_placeholders(spec, batch, seed))
+
+
+def make_train_example(hb, device):
+    from simlingo_training.utils.custom_types import DrivingExample, DrivingInput, DrivingLabel, LanguageLabel
+    mv = lambda t: t.to(device, non_blocking=True)
+    ids, valid = mv(hb["ids"]), mv(hb["valid"])
+    lab = LanguageLabel(ids, valid, valid, hb["placeholders"], [""] * ids.shape[0], mv(hb["loss_masking"]))
+    z = torch.zeros((ids.shape[0], 1), device=device)
+    di = DrivingInput(mv(hb["frames"]), z, z, z, z, z, lab, lab)
+    return DrivingExample(di, DrivingLabel(mv(hb["wps"]), mv(hb["path"]), lab, z), ["x"] * ids.shape[0])
+
+
+def train_flops(spec, B, L):
+    """Algorithmic FLOPs of one training step per GPU: ViT and projector x3 (fprop + dgrad + wgrad), frozen
+    Qwen2 base x2 (fprop + dgrad), LoRA x3, LM head + CE on the ANSWER_LEN labelled rows per sample x2."""
+    vit = S.flops_vit(spec, 2 * B) + S.flops_proj(spec, 2 * B)
+    base = S.flops_llm(spec, L, B, lora=False)
+    lora = S.flops_llm(spec, L, B, lora=True) - base
+    head = 2.0 * B * ANSWER_LEN * spec.llm_hidden * spec.vocab
+    return 3 * vit + 2 * base + 3 * lora + 2 * head
+
+
+def run_train(args, rank, world, local):
+    import contextlib
+    spec = S.INTERNVL2_1B
+    B = args.batch
+    L = PROMPT_LEN + ANSWER_LEN
+    cfg = {"workload": f"training step: batch {B}/GPU, 2x448^2 tiles/frame, L={L}+30, full ViT + mlp1 + LoRA(r32, dropout 0.1) Qwen2 fwd+bwd, "
+                       "global-norm clip 0.3 + fused AdamW, bf16 gradient all-reduce overlapped with backward (BASELINE configs[3])",
+           "batch_per_gpu": B, "parallelism": f"dp{world} batch-sharded, NCCL all-reduce of the flat bf16 gradient buffer",
+           "l2": "activations + gradients (> 20 GB per step) far exceed the 126 MB L2; no explicit flush needed"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sps, cores, t = cpu_oracle_train_samples_per_s()
+        line = {"impl": "reference", "metric": "vla_train_samples_per_s", "value": round(sps, 5), "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": 1, "warmup": 0, "ms_per_step": round(t * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": round(sps, 5), "unit": "samples/s", "cores": cores, "kind": "port",
+                                 "sample": "1 sample fwd+bwd (fp32 oracle under torch autograd), single run"},
+                "e2e": {"value": round(sps, 5), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with contextlib.redirect_stdout(sys.stderr):
+        model = build_model(spec, device)
+    model.train()  # LoRA dropout active, as the reference trains
+    from simlingo_b200.optim import FusedAdamW
+    store = model.param_store()
+    if world > 1:
+        store.enable_data_parallel()
+        dist.broadcast(store.flat_param, src=0)
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], store, lr=3e-5, weight_decay=0.1, betas=(0.9, 0.999), max_grad_norm=0.3)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=3e-5, total_steps=10000, pct_start=0.05)
+    teng = model.__dict__["_slb_train_engine"]
+    hb = host_train_batch(spec, B, 4321 + rank)
+    example = make_train_example(hb, device)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(ex):
+        opt.zero_grad()
+        out = model.training_step(ex)
+        out["loss"].backward()
+        opt.step()
+        sched.step()
+        return out["loss"]
+
+    def timed_region(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    import warnings
+    warnings.filterwarnings("ignore", message=".*lr_scheduler.step.*")
+    for _ in range(args.warmup):
+        step(example)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = teng.launches + opt.launches
+    ms = timed_region(lambda: step(example), args.steps)
+    launches = teng.launches + opt.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    def e2e_step():
+        ex = make_train_example(hb, device)
+        loss = step(ex)
+        loss_host.copy_(loss.detach().float(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed_region(e2e_step, args.steps)
+    e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(hb[k].numel() * hb[k].element_size() for k in ("frames", "ids", "valid", "loss_masking", "wps", "path"))
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    roof = gemm_roofline(model, example, peaks, step_fn=lambda: step(example))
+    flops_step = train_flops(spec, B, L + 30)
+    line = {"metric": "vla_train_samples_per_s", "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "e2e": {"value": round(e2e_val, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "loss": round(float(loss_host), 4),
+            "allreduce_calls_per_step": store.n_allreduce // max(1, args.steps * 2 + args.warmup + 3) if world > 1 else 0,
+            "model_tflops_per_gpu": round(flops_step * args.steps / (ms * 1e-3) / 1e12, 1),
+            "algorithmic_tflop_per_step_per_gpu": round(flops_step / 1e12, 2)}
+    if not args.no_cpu_baseline and world == 1:
+        sps, cores, t = cpu_oracle_train_samples_per_s()
+        line["cpu_baseline"] = {"value": round(sps, 5), "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": "1 sample fwd+bwd of the same workload (fp32 oracle under torch autograd), single run"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_oracle_train_samples_per_s():
+    from oracle import model as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = S.INTERNVL2_1B
+    sd = {k: v.requires_grad_(S.trainable(k)) for k, v in S.init_state_dict(spec, seed=0).items()}
+    ids = S.synth_prompt_ids(spec, 1, 7, answer_len=ANSWER_LEN)
+    valid = torch.ones_like(ids, dtype=torch.bool)
+    lm = torch.zeros_like(valid)
+    lm[:, -ANSWER_LEN:] = True
+    wps, path = S.synth_labels(spec, 1, 7)
+    t0 = time.perf_counter()
+    loss, _, _ = O.forward_loss(sd, spec, S.synth_frames(spec, 1, 7), ids, valid, lm, S.synth_placeholders(spec, 1, 7), wps, path, training=True)
+    loss.backward()
+    t = time.perf_counter() - t0
+    return 1.0 / t, cores, t
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="offline64", choices=["offline64"])
+    ap.add_argument("--workload", default="offline64", choices=["offline64", "train"])
+    ap.add_argument("--batch", type=int, default=TRAIN_BATCH, help="training samples per GPU per step (--workload train)")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "train":
+        return run_train(args, rank, world, local)
     spec = S.INTERNVL2_1B
     cfg = {"workload": f"offline batched forward: {args.frames} frames/GPU/step (2x448^2 tiles each), prompt L={PROMPT_LEN}+30 queries, "
                        "teacher-forced Qwen2 pass + route/speed heads (BASELINE configs[2])",

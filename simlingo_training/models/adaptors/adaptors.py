@@ -18,6 +18,19 @@ def _needs_grad(*tensors: Tensor) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+def _mlp_fp32(seq: nn.Sequential, x: Tensor) -> Tensor:
+    """The tiny adaptor MLPs under autograd: fp32 arithmetic on the bf16 parameters (the inference kernels
+    ``slb_driving_heads`` / ``slb_wp_encoder`` also accumulate in fp32), so ReLU / SiLU gates do not flip against
+    the fp32 oracle."""
+    x = x.float()
+    for m in seq:
+        if isinstance(m, nn.Linear):
+            x = F.linear(x, m.weight.float(), None if m.bias is None else m.bias.float())
+        else:
+            x = type(m)()(x)  # activation modules are declared inplace=True; apply a fresh out-of-place instance
+    return x
+
+
 def _unwrap_input(example):
     """Both ``DrivingExample`` and a bare ``DrivingInput`` are accepted (reference adaptors.py:144-147)."""
     return getattr(example, "driving_input", example)
@@ -93,6 +106,8 @@ class WaypointInputAdaptor(nn.Module):
             ww = _lib.WpWeights(*[t.data_ptr() for t in (m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias)])
             flat = x.reshape(-1, 2).float().contiguous()
             return _lib.wp_encoder(flat, ww).view(*x.shape[:-1], 896)
+        if x.is_cuda and self.mlp[0].weight.dtype == torch.bfloat16:
+            return _mlp_fp32(self.mlp, x).to(torch.bfloat16)
         return self.mlp(x)
 
 
@@ -143,9 +158,11 @@ class DrivingAdaptor(nn.Module):
             route, speed = _lib.driving_heads(f, 30 * 896, hw, f.shape[0])
             return {"route": route.to(features.dtype), "speed_wps": speed.to(features.dtype)}
         out, at = {}, 0
+        fp32 = features.is_cuda and features.dtype == torch.bfloat16
         for name in self.order:
             n = self.sizes[name]
-            out[name] = self.heads[name](features[:, at: at + n]).cumsum(1)
+            f = features[:, at: at + n]
+            out[name] = _mlp_fp32(self.heads[name], f).cumsum(1) if fp32 else self.heads[name](f).cumsum(1)
             at += n
         return out
 
