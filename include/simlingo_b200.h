@@ -148,11 +148,17 @@ int slb_vit_assemble_bwd(const void* dx, void* dpatch_out, float* dcls_accum, fl
 int slb_rope_bwd(const float* dq, const float* dk, const float* dv, void* dqkv, int batch, int lq, int hq, int hkv,
                  float theta, void* stream);
 int slb_attn_delta(const void* o, const void* dout, float* delta, int batch, int lq, int heads, void* stream);
-int slb_attn_vit_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq, float* dk,
-                     float* dv, int tiles, int n_tokens, int heads, void* stream);
+/* Flash-attention backward.  Every key block writes its partial dQ tile into its own bf16 slab of `workspace`
+ * (slb_attn_bwd_workspace bytes); a reduction kernel sums the slabs in fp32.
+ * ViT: dqkv (bf16 [T*n, 3*H*64], same packing as qkv) receives dQ | dK | dV directly.
+ * GQA: dq fp32 [B*L, Hq*64] (post-RoPE space, overwritten), dk / dv fp32 [B, Hkv, L, 64]; slb_rope_bwd rotates back. */
+size_t slb_attn_bwd_workspace(int batch, int lq, int hq);
+int slb_attn_vit_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, void* workspace,
+                     size_t workspace_bytes, int tiles, int n_tokens, int heads, void* stream);
 int slb_attn_gqa_bwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
                      int key_valid_ld, const void* dout, const float* lse, const float* delta, float* dq, float* dk,
-                     float* dv, int batch, int lq, int lmax, int hq, int hkv, void* stream);
+                     float* dv, void* workspace, size_t workspace_bytes, int batch, int lq, int lmax, int hq, int hkv,
+                     void* stream);
 /* fused softmax cross-entropy over fp32 logits rows (adaptors.py:271-273): loss[r] = lse - logit[label];
  * dlogits (bf16, row stride ldd >= cols, zero padded) = (softmax - onehot) * grad_scale; label < 0 => ignored */
 int slb_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* labels, float* loss, void* dlogits, int64_t ldd,

@@ -75,3 +75,18 @@ int slb_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d
   if (r != CUDA_SUCCESS) return slb_fail(SLB_ECUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
   return SLB_OK;
 }
+
+int slb_make_tmap_3d_f32(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                         uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return slb_fail(SLB_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return slb_fail(SLB_ECUDA, "cuTensorMapEncodeTiled(3d f32) failed: %d", (int)r);
+  return SLB_OK;
+}

@@ -29,9 +29,13 @@ inline int grid_for(size_t work, int block) {
 // flushed with one atomicAdd per column per warp at the end (ACC=true), or per row (ACC=false, wide rows).
 // ------------------------------------------------------------------------------------------------
 template <int MAXV, bool RMS, bool ACC>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, ACC ? 2 : 1)
 norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ mean,
                 const float* __restrict__ rstd, bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int rows, int cols) {
+  // ACC: per-thread fp32 partials of dw / db over the warp's rows, combined per block in shared memory (bank-conflict
+  // free [e][vec] layout) and flushed with one global atomicAdd per column per block.  Pass 2 re-reads dy / x from L1
+  // instead of holding them in registers, which keeps the kernel at two blocks per SM.
+  __shared__ float s_acc[ACC ? 2 * MAXV * 32 * 8 : 1];
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
   const int nvec = cols >> 3;
@@ -41,10 +45,10 @@ norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const b
     for (int j = 0; j < MAXV; ++j)
 #pragma unroll
       for (int e = 0; e < 8; ++e) { aw[j][e] = 0.f; ab[j][e] = 0.f; }
+    for (int i = threadIdx.x; i < 2 * MAXV * 32 * 8; i += blockDim.x) s_acc[i] = 0.f;
   }
   for (int row = gw; row < rows; row += nw) {
     const float mu = RMS ? 0.f : mean[row], rs = rstd[row];
-    float g[MAXV][8], xh[MAXV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
@@ -56,13 +60,12 @@ norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const b
         load8(w + vi * 8, wv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          xh[j][e] = (xv[e] - mu) * rs;
-          g[j][e] = dyv[e] * wv[e];
-          s1 += g[j][e];
-          s2 += g[j][e] * xh[j][e];
+          const float xh = (xv[e] - mu) * rs, g = dyv[e] * wv[e];
+          s1 += g;
+          s2 += g * xh;
           if (dw) {
-            if (ACC) { aw[j][e] += dyv[e] * xh[j][e]; if (!RMS) ab[j][e] += dyv[e]; }
-            else { atomicAdd(dw + vi * 8 + e, dyv[e] * xh[j][e]); if (!RMS && db) atomicAdd(db + vi * 8 + e, dyv[e]); }
+            if (ACC) { aw[j][e] += dyv[e] * xh; if (!RMS) ab[j][e] += dyv[e]; }
+            else { atomicAdd(dw + vi * 8 + e, dyv[e] * xh); if (!RMS && db) atomicAdd(db + vi * 8 + e, dyv[e]); }
           }
         }
       }
@@ -74,24 +77,33 @@ norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const b
     for (int j = 0; j < MAXV; ++j) {
       const int vi = lane + 32 * j;
       if (vi < nvec) {
-        float o[8];
+        float dyv[8], xv[8], wv[8], o[8];
+        load8(dy + (size_t)row * cols + vi * 8, dyv);
+        load8(x + (size_t)row * cols + vi * 8, xv);
+        load8(w + vi * 8, wv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (g[j][e] - m1 - xh[j][e] * m2);
+        for (int e = 0; e < 8; ++e) o[e] = rs * (dyv[e] * wv[e] - m1 - (xv[e] - mu) * rs * m2);
         store8(dx + (size_t)row * cols + vi * 8, o);
       }
     }
   }
   if (ACC && dw) {
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
       const int vi = lane + 32 * j;
       if (vi < nvec) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          atomicAdd(dw + vi * 8 + e, aw[j][e]);
-          if (!RMS && db) atomicAdd(db + vi * 8 + e, ab[j][e]);
+          atomicAdd(&s_acc[e * (MAXV * 32) + vi], aw[j][e]);
+          if (!RMS && db) atomicAdd(&s_acc[(8 + e) * (MAXV * 32) + vi], ab[j][e]);
         }
       }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+      atomicAdd(dw + i, s_acc[(i & 7) * (MAXV * 32) + (i >> 3)]);
+      if (!RMS && db) atomicAdd(db + i, s_acc[(8 + (i & 7)) * (MAXV * 32) + (i >> 3)]);
     }
   }
 }
@@ -405,7 +417,7 @@ ce_kernel(const float* __restrict__ logits, long long ld, const long long* __res
 extern "C" int slb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
                                  float* dw_accum, float* db_accum, int rows, int cols, void* stream) {
   SLB_CHECK_ARG(rows > 0 && (cols % 8) == 0 && cols <= 4096, "layernorm_bwd: bad shape %d x %d", rows, cols);
-  const int grid = min(ceil_div(rows, kWarps), slb_num_sms() * 2);
+  const int grid = min(ceil_div(rows, kWarps), slb_num_sms() * (cols <= 1024 ? 4 : 2));
   if (cols <= 1024)
     norm_bwd_kernel<4, false, true><<<grid, kWarps * 32, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw_accum, db_accum, rows, cols);
   else
@@ -417,7 +429,7 @@ extern "C" int slb_layernorm_bwd(const void* dy, const void* x, const void* w, c
 extern "C" int slb_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw_accum, int rows,
                                int cols, void* stream) {
   SLB_CHECK_ARG(rows > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm_bwd: bad shape %d x %d", rows, cols);
-  const int grid = min(ceil_div(rows, kWarps), slb_num_sms() * 2);
+  const int grid = min(ceil_div(rows, kWarps), slb_num_sms() * 4);
   norm_bwd_kernel<4, true, true><<<grid, kWarps * 32, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, nullptr, rstd, (bf16*)dx, dw_accum, nullptr, rows, cols);
   SLB_LAUNCH_CHECK();
   return SLB_OK;

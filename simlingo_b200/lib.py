@@ -381,28 +381,49 @@ def attn_delta(o, dout, batch, lq, heads, out=None):
     return out
 
 
-def attn_vit_bwd(qkv, dout, lse, delta, tiles, n_tokens, heads=16):
-    """-> (dq fp32 [T*n, H*64], dk fp32 [T,H,n,64], dv fp32 [T,H,n,64])"""
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per device (callers of the C ABI own all memory; kernels on one stream serialise)."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream if torch.cuda.is_current_stream_capturing() else 0)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        _ws_cache[key] = buf
+    return buf
+
+
+def attn_bwd_workspace(batch, lq, hq) -> int:
+    fn = load().slb_attn_bwd_workspace
+    fn.restype = C.c_size_t
+    return int(fn(batch, lq, hq))
+
+
+def attn_vit_bwd(qkv, dout, lse, delta, tiles, n_tokens, heads=16, out=None, workspace=None):
+    """-> dqkv bf16 [T*n, 3*H*64] (dQ | dK | dV packed like qkv)"""
     _bf16(qkv, dout); _f32(lse, delta)
-    dev = qkv.device
-    dq = torch.zeros((tiles * n_tokens, heads * 64), device=dev, dtype=torch.float32)
-    dk = torch.empty((tiles, heads, n_tokens, 64), device=dev, dtype=torch.float32)
-    dv = torch.empty_like(dk)
-    _check(load().slb_attn_vit_bwd(_p(qkv), _p(dout), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), tiles, n_tokens, heads, _stream()), "attn_vit_bwd")
-    return dq, dk, dv
+    out = torch.empty_like(qkv) if out is None else out
+    nb = attn_bwd_workspace(tiles, n_tokens, heads)
+    ws = _workspace(nb, qkv.device) if workspace is None else workspace
+    _check(load().slb_attn_vit_bwd(_p(qkv), _p(dout), _p(lse), _p(delta), _p(out), _p(ws), C.c_size_t(ws.numel() * ws.element_size()), tiles, n_tokens,
+                                   heads, _stream()), "attn_vit_bwd")
+    return out
 
 
-def attn_gqa_bwd(q, ldq, kcache, vcache, dout, lse, delta, batch, lq, hq=14, hkv=2, key_valid=None):
+def attn_gqa_bwd(q, ldq, kcache, vcache, dout, lse, delta, batch, lq, hq=14, hkv=2, key_valid=None, workspace=None):
     """-> (dq fp32 [B*L, Hq*64] (post-RoPE space), dk fp32 [B,Hkv,L,64], dv fp32 [B,Hkv,L,64])"""
     _bf16(q, kcache, vcache, dout); _f32(lse, delta)
     dev = q.device
     lmax = kcache.shape[2]
-    dq = torch.zeros((batch * lq, hq * 64), device=dev, dtype=torch.float32)
+    dq = torch.empty((batch * lq, hq * 64), device=dev, dtype=torch.float32)
     dk = torch.empty((batch, hkv, lq, 64), device=dev, dtype=torch.float32)
     dv = torch.empty_like(dk)
     kv_ld = 0 if key_valid is None else key_valid.stride(0)
+    nb = attn_bwd_workspace(batch, lq, hq)
+    ws = _workspace(nb, dev) if workspace is None else workspace
     _check(load().slb_attn_gqa_bwd(_p(q), C.c_int64(ldq), _p(kcache), _p(vcache), _p(key_valid), kv_ld, _p(dout), _p(lse), _p(delta), _p(dq),
-                                   _p(dk), _p(dv), batch, lq, lmax, hq, hkv, _stream()), "attn_gqa_bwd")
+                                   _p(dk), _p(dv), _p(ws), C.c_size_t(ws.numel() * ws.element_size()), batch, lq, lmax, hq, hkv, _stream()), "attn_gqa_bwd")
     return dq, dk, dv
 
 

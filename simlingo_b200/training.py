@@ -354,9 +354,7 @@ class TrainEngine:
             self._wgrad(dp1, a["att"], p + "attn.proj.weight")
             datt = lib.gemm(dp1, w(p + "attn.proj.weight"), b_t=True, out=dh2)
             delta = lib.attn_delta(a["att"], datt, T, s.vit_tokens, s.vit_heads)
-            dq, dk, dv = lib.attn_vit_bwd(a["qkv"], datt, a["lse"], delta, T, s.vit_tokens, s.vit_heads)
-            dqkv = lib.rope_bwd(dq, dk, dv, T, s.vit_tokens, s.vit_heads, s.vit_heads, 0.0)
-            del dq, dk, dv
+            dqkv = lib.attn_vit_bwd(a["qkv"], datt, a["lse"], delta, T, s.vit_tokens, s.vit_heads)
             lib.col_reduce(dqkv, self._acc(p + "attn.qkv.bias"))
             self._wgrad(dqkv, a["h1"], p + "attn.qkv.weight")
             dh1 = lib.gemm(dqkv, w(p + "attn.qkv.weight"), b_t=True, out=dp1)

@@ -114,8 +114,7 @@ def test_attn_vit_bwd(lib, tiles, n):
     lse = torch.empty(tiles, H, n, device="cuda")
     out = lib.attn_vit(qkv, tiles, n, H, lse=lse)
     delta = lib.attn_delta(out, dout, tiles, n, H)
-    dq, dk, dv = lib.attn_vit_bwd(qkv, dout, lse, delta, tiles, n, H)
-    dqkv = lib.rope_bwd(dq, dk, dv, tiles, n, H, H, 0.0)
+    dqkv = lib.attn_vit_bwd(qkv, dout, lse, delta, tiles, n, H)
     ref_in = qkv.float().requires_grad_()
     q, k, v = ref_in.view(tiles, n, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(tiles * n, H * 64)
