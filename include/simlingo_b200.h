@@ -129,10 +129,12 @@ int slb_pixel_shuffle_ln_bwd(const void* dy, const void* x, const void* w, const
 int slb_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
 int slb_gelu_bwd(const void* pre, const void* dout, void* dpre, int64_t n, void* stream);
 int slb_silu_mul_bwd(const void* gate, const void* up, const void* dout, void* dgate, void* dup, int64_t n, void* stream);
-/* counter-based dropout (peft lora_dropout=0.1): y = keep(seed, i) ? x / (1-p) : 0; same call on the gradient = backward */
-int slb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream);
+/* counter-based dropout (peft lora_dropout=0.1): y = keep(seed', i) ? x / (1-p) : 0; same call on the gradient = backward.
+ * seed' = seed + (*seed_dev << 16) when seed_dev (device pointer) is given: a step counter living in device memory, so that
+ * a CUDA graph replays with a fresh mask every step */
+int slb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* y += dropout(x) with the same (seed, index) mask as slb_dropout */
-int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream);
+int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* y (bf16) = (accumulate ? y : 0) + x (fp32): flush of fp32 small-parameter gradient accumulators */
 int slb_flush_f32_to_bf16(const float* x, void* y, int64_t n, int accumulate, void* stream);
 int slb_add_inplace_bf16(void* a, const void* b, int64_t n, void* stream);

@@ -13,6 +13,7 @@ namespace {
 
 constexpr int BQ = 128, BKV = 128, HD = 64;
 constexpr int ATT_THREADS = 192;
+constexpr int kMaxKvBlocks = 64;            // key-validity bitmasks in static smem: sequences up to 8192 keys
 constexpr int kQBytes = BQ * HD * 2;        // 16 KB
 constexpr int kKVBytes = BKV * HD * 2;      // 16 KB
 constexpr int kPBytes = BQ * BKV * 2;       // 32 KB (two K-major halves of 64 columns)
@@ -136,6 +137,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int qpos = p.past + row;             // absolute position (causal)
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)b * p.key_valid_ld : nullptr;
+    // per key block, a 128-bit validity mask (inside the sequence and not padding), built once per CTA: the softmax
+    // loops then test a register bit instead of loading key_valid per element, and unmasked blocks take the fast path
+    __shared__ uint32_t kmask[kMaxKvBlocks * 4];
+    for (int j = 0; j < nkv; ++j) {
+      const int col = j * BKV + r;
+      const bool ok = col < p.lkv && (!kvalid || kvalid[col] != 0);
+      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) kmask[j * 4 + quad] = bal;
+    }
+    named_bar_sync(2, 128);
     float o_acc[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
@@ -147,7 +158,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int col_base = j * BKV;
-      const bool need_mask = (col_base + BKV > p.lkv) || (p.causal && col_base + BKV - 1 > p.past + q0) || kvalid;
+      const uint32_t km0 = kmask[j * 4], km1 = kmask[j * 4 + 1], km2 = kmask[j * 4 + 2], km3 = kmask[j * 4 + 3];
+      const bool need_mask = ((km0 & km1 & km2 & km3) != 0xffffffffu) || (p.causal && col_base + BKV - 1 > p.past + q0);
       // pass 1: row max
       float m_blk = -INFINITY;
 #pragma unroll 1
@@ -156,12 +168,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_ld_32x32(tmem_s + lane_off + c, sr);
         tmem_ld_wait();
         if (need_mask) {
+          const uint32_t km = c == 0 ? km0 : (c == 32 ? km1 : (c == 64 ? km2 : km3));
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int col = col_base + c + i;
-            bool ok = col < p.lkv && (!p.causal || col <= qpos);
-            if (ok && kvalid) ok = kvalid[col] != 0;
-            if (ok) m_blk = fmaxf(m_blk, __uint_as_float(sr[i]));
+            const bool ok = ((km >> i) & 1u) && (!p.causal || col_base + c + i <= qpos);
+            m_blk = fmaxf(m_blk, ok ? __uint_as_float(sr[i]) : -INFINITY);
           }
         } else {
 #pragma unroll
@@ -180,15 +191,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_ld_32x32(tmem_s + lane_off + c, sr);
         tmem_ld_wait();
         float pv[32];
+        const uint32_t km = c == 0 ? km0 : (c == 32 ? km1 : (c == 64 ? km2 : km3));
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float e = exp2f(__uint_as_float(sr[i]) * p.scale_log2 - moff);
-          if (need_mask) {
-            const int col = col_base + c + i;
-            bool ok = col < p.lkv && (!p.causal || col <= qpos);
-            if (ok && kvalid) ok = kvalid[col] != 0;
-            e = ok ? e : 0.f;
-          }
+          float e = ex2_approx(fmaf(__uint_as_float(sr[i]), p.scale_log2, -moff));
+          if (need_mask) e = (((km >> i) & 1u) && (!p.causal || col_base + c + i <= qpos)) ? e : 0.f;
           pv[i] = e;
         }
         // round to bf16 first so the row sum matches what the PV MMA sees
@@ -358,6 +365,7 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
                                 void* stream) {
   SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax && hq % hkv == 0, "attn_gqa: bad shape");
   SLB_CHECK_ARG((ldq % 8) == 0, "attn_gqa: ldq must be a multiple of 8");
+  SLB_CHECK_ARG(past + lq <= kMaxKvBlocks * BKV, "attn_gqa: at most %d keys", kMaxKvBlocks * BKV);
   const float scale = 0.125f;
   if (lq <= 32 && lse == nullptr) {
     dim3 grid(lq, hq, batch);

@@ -205,7 +205,9 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
   z ^= z >> 33; z *= 0xff51afd7ed558ccdULL; z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33;
   return (uint32_t)z;
 }
-__global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t nvec, uint32_t thresh, float scale, uint64_t seed) {
+__global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t nvec, uint32_t thresh, float scale, uint64_t seed,
+                               const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev << 16;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float a[8];
     load8(x + i * 8, a);
@@ -215,7 +217,9 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
   }
 }
 // y += dropout(x): backward of the LoRA-input dropout, accumulated straight into the gradient of the shared input
-__global__ void dropout_add_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t nvec, uint32_t thresh, float scale, uint64_t seed) {
+__global__ void dropout_add_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t nvec, uint32_t thresh, float scale, uint64_t seed,
+                                   const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev << 16;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float a[8], b[8];
     load8(x + i * 8, a);
@@ -462,17 +466,17 @@ extern "C" int slb_silu_mul_bwd(const void* gate, const void* up, const void* do
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
-extern "C" int slb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream) {
+extern "C" int slb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
   SLB_CHECK_ARG(n > 0 && (n % 8) == 0 && p >= 0.f && p < 1.f, "dropout: n=%lld p=%f", (long long)n, p);
   const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
-  dropout_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)y, n / 8, thresh, 1.0f / (1.0f - p), seed);
+  dropout_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)y, n / 8, thresh, 1.0f / (1.0f - p), seed, seed_dev);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
-extern "C" int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream) {
+extern "C" int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
   SLB_CHECK_ARG(n > 0 && (n % 8) == 0 && p >= 0.f && p < 1.f, "dropout_add: n=%lld p=%f", (long long)n, p);
   const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
-  dropout_add_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)y, n / 8, thresh, 1.0f / (1.0f - p), seed);
+  dropout_add_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)y, n / 8, thresh, 1.0f / (1.0f - p), seed, seed_dev);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

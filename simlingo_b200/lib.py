@@ -63,7 +63,12 @@ def load() -> C.CDLL:
     return _lib
 
 
-def _check(rc: int, what: str) -> None:
+LAUNCHES = 0  # kernels launched through this binding (one per call unless stated; read as deltas by the engines)
+
+
+def _check(rc: int, what: str, n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
     if rc != 0:
         msg = load().slb_last_error()
         raise RuntimeError(f"simlingo_b200: {what} failed ({rc}): {msg.decode() if msg else ''}")
@@ -308,18 +313,19 @@ def silu_mul_bwd(g, u, dout, dg=None, du=None):
     return dg, du
 
 
-def dropout(x, p, seed, out=None):
+def dropout(x, p, seed, out=None, seed_dev=None):
+    """seed_dev: optional int64 CUDA tensor [1] (step counter read on the device, see slb_dropout)."""
     _bf16(x)
     out = torch.empty_like(x) if out is None else out
-    _check(load().slb_dropout(_p(x), _p(out), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed), _stream()), "dropout")
+    _check(load().slb_dropout(_p(x), _p(out), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed), _p(seed_dev), _stream()), "dropout")
     return out
 
 
-def dropout_add(x, y, p, seed):
-    """y += dropout(x) (same mask as ``dropout(.., p, seed)``)."""
+def dropout_add(x, y, p, seed, seed_dev=None):
+    """y += dropout(x) (same mask as ``dropout(.., p, seed, seed_dev)``)."""
     _bf16(x, y)
     assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
-    _check(load().slb_dropout_add(_p(x), _p(y), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed), _stream()), "dropout_add")
+    _check(load().slb_dropout_add(_p(x), _p(y), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed), _p(seed_dev), _stream()), "dropout_add")
     return y
 
 
@@ -407,7 +413,7 @@ def attn_vit_bwd(qkv, dout, lse, delta, tiles, n_tokens, heads=16, out=None, wor
     nb = attn_bwd_workspace(tiles, n_tokens, heads)
     ws = _workspace(nb, qkv.device) if workspace is None else workspace
     _check(load().slb_attn_vit_bwd(_p(qkv), _p(dout), _p(lse), _p(delta), _p(out), _p(ws), C.c_size_t(ws.numel() * ws.element_size()), tiles, n_tokens,
-                                   heads, _stream()), "attn_vit_bwd")
+                                   heads, _stream()), "attn_vit_bwd", 2)
     return out
 
 
@@ -423,7 +429,7 @@ def attn_gqa_bwd(q, ldq, kcache, vcache, dout, lse, delta, batch, lq, hq=14, hkv
     nb = attn_bwd_workspace(batch, lq, hq)
     ws = _workspace(nb, dev) if workspace is None else workspace
     _check(load().slb_attn_gqa_bwd(_p(q), C.c_int64(ldq), _p(kcache), _p(vcache), _p(key_valid), kv_ld, _p(dout), _p(lse), _p(delta), _p(dq),
-                                   _p(dk), _p(dv), _p(ws), C.c_size_t(ws.numel() * ws.element_size()), batch, lq, lmax, hq, hkv, _stream()), "attn_gqa_bwd")
+                                   _p(dk), _p(dv), _p(ws), C.c_size_t(ws.numel() * ws.element_size()), batch, lq, lmax, hq, hkv, _stream()), "attn_gqa_bwd", 2)
     return dq, dk, dv
 
 

@@ -148,6 +148,8 @@ class ParamStore:
         self.bucket_bytes = bucket_bytes
         self._make_buckets()
         self.n_allreduce = 0
+        self.capture = None            # set while a backward is being captured into CUDA graphs (see TrainEngine)
+        self.layout_version = 0        # bumped when captured graphs must be thrown away (e.g. DP switched on)
 
     # ---- layout helpers -----------------------------------------------------------------------------
     def _make_buckets(self) -> None:
@@ -168,6 +170,11 @@ class ParamStore:
         self._next_bucket = 0
         self._works = []
 
+    def skip_to_bucket_after(self, gi: int) -> None:
+        """After replaying captured segments that already issued every bucket ending at or before group ``gi``."""
+        while self._next_bucket < len(self._buckets) and self._buckets[self._next_bucket][2] <= gi:
+            self._next_bucket += 1
+
     def flush_group(self, name: str) -> None:
         """fp32 accumulators of the group's small parameters -> flat bf16 gradients; then the group is final."""
         gi = self.group_index.get(name)
@@ -187,16 +194,24 @@ class ParamStore:
             raise RuntimeError("torch.distributed is not initialised")
         self.pg = process_group if process_group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.pg)
+        self.layout_version += 1
+
+    def launch_bucket(self, k: int) -> None:
+        a, b, _ = self._buckets[k]
+        # async_op: NCCL runs on its own stream after an event on the current (compute) stream
+        self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        self.n_allreduce += 1
 
     def group_ready(self, gi: int) -> None:
         if self.pg is None or self.world == 1:
             return
         while self._next_bucket < len(self._buckets) and self._buckets[self._next_bucket][2] <= gi:
-            a, b, _ = self._buckets[self._next_bucket]
-            # async_op: NCCL runs on its own stream after an event on the current (compute) stream
-            self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-            self.n_allreduce += 1
+            k = self._next_bucket
             self._next_bucket += 1
+            if self.capture is not None:
+                self.capture.split(k)   # close the graph segment here; the all-reduce is issued between two replays
+            else:
+                self.launch_bucket(k)
 
     def finish_backward(self) -> None:
         """End-of-backward hook: adopt gradients autograd produced for the torch-managed parameters, expose
@@ -240,9 +255,19 @@ class TrainEngine:
         self.P: Dict[str, Tensor] = {prefix + k: v for k, v in root.state_dict(keep_vars=True).items()}
         self.dev = self.store.flat_param.device
         self.launches = 0
-        self.seed_counter = 0
         self.base_seed = 0x5151
+        self.seed_dev = torch.zeros(1, device=self.dev, dtype=torch.int64)  # step counter read by the dropout kernels
         self._frozen = None
+        self._side = None
+        # CUDA graphs: the ~2800 launches of a step are recorded once per input shape and replayed; the first call
+        # with a new shape runs eagerly (it also warms up lazily initialised state), the second one captures.
+        import os
+        self.graphs_enabled = os.environ.get("SLB_TRAIN_GRAPHS", "1") != "0"
+        self._pool = None
+        self._cap_stream = None
+        self._recs: Dict[tuple, dict] = {}
+        self._seen: Dict[tuple, int] = {}
+        self.graph_replays = 0
 
     # ---- weights ---------------------------------------------------------------------------------------
     def w(self, key: str) -> Tensor:
@@ -264,10 +289,190 @@ class TrainEngine:
         g, acc = self.store.target(key)
         g2 = g.view(g.shape[0], -1)
         lib.gemm(dy, x, out=g2, a_t=True, b_t=True, alpha=alpha, residual=g2 if acc else None)
-        self.launches += 1
 
     def _acc(self, key: str) -> Tensor:
         return self.store.acc_view[key]
+
+    def _par(self, *fns):
+        """Runs ``fns[0]`` on the current stream and the others on side streams, concurrently, and joins.  Used for
+        the LoRA chains: each of their GEMMs covers a quarter of the SMs at most, so independent chains overlap
+        (under graph capture the fork / join events become graph edges).  Every tensor a lane touches is created
+        before the fork or inside the lane and stays referenced until after the join."""
+        if len(fns) == 1:
+            return [fns[0]()]
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        outs, joins = [None] * len(fns), []
+        for k, fn in enumerate(fns[1:]):
+            side = self._side[k]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                outs[k + 1] = fn()
+                ev = torch.cuda.Event()
+                ev.record(side)
+            joins.append(ev)
+        outs[0] = fns[0]()
+        for ev in joins:
+            main.wait_event(ev)
+        return outs
+
+
+    # ==================================================================================================
+    # CUDA-graph capture / replay
+    # ==================================================================================================
+    class _Capture:
+        """Records kernels launched by ``fn`` on a side stream into one or more CUDA graphs (shared memory pool).
+        ``split(k)`` closes the current segment: on replay, gradient bucket ``k`` is all-reduced after it."""
+
+        def __init__(self, eng: "TrainEngine"):
+            self.eng = eng
+            self.segments: List[Tuple[torch.cuda.CUDAGraph, Optional[int]]] = []
+            self.g: Optional[torch.cuda.CUDAGraph] = None
+
+        def _begin(self):
+            self.g = torch.cuda.CUDAGraph()
+            self.g.capture_begin(pool=self.eng._pool, capture_error_mode="thread_local")
+
+        def split(self, k: Optional[int]):
+            self.g.capture_end()
+            self.segments.append((self.g, k))
+            self._begin()
+
+        def run(self, fn):
+            eng = self.eng
+            if eng._pool is None:
+                eng._pool = torch.cuda.graph_pool_handle()
+                eng._cap_stream = torch.cuda.Stream(device=eng.dev)
+            torch.cuda.synchronize(eng.dev)
+            cs = eng._cap_stream
+            cs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cs):
+                self._begin()
+                try:
+                    out = fn()
+                finally:
+                    self.g.capture_end()
+                self.segments.append((self.g, None))
+            torch.cuda.current_stream().wait_stream(cs)
+            self.keep = list(lib._ws_cache.values())  # scratch buffers baked into the graphs stay alive with them
+            return out
+
+    def _counted(self, fn, *args):
+        l0 = lib.LAUNCHES
+        out = fn(*args)
+        self.launches += lib.LAUNCHES - l0
+        return out
+
+    def _replay(self, segments) -> None:
+        st = self.store
+        for g, k in segments:
+            g.replay()
+            if k is not None:
+                st.launch_bucket(k)
+        self.graph_replays += len(segments)
+
+    def _graph_ok(self, key: tuple) -> bool:
+        """eager on the first sighting of a shape, captured from the second on"""
+        if not self.graphs_enabled:
+            return False
+        rec = self._recs.get(key)
+        if rec is not None and rec["version"] != self.store.layout_version:
+            del self._recs[key]
+            rec = None
+        if rec is not None:
+            return True
+        n = self._seen.get(key, 0)
+        self._seen[key] = n + 1
+        return n >= 1
+
+    def vision_forward_auto(self, pixels: Tensor):
+        key = ("vis", int(pixels.shape[0]))
+        if not self._graph_ok(key):
+            return self._counted(self.vision_forward, pixels)
+        rec = self._recs.get(key)
+        if rec is None:
+            rec = dict(version=self.store.layout_version, px=torch.empty_like(pixels), bwd=None)
+            cap = TrainEngine._Capture(self)
+            l0 = lib.LAUNCHES
+            rec["out"], rec["saved"] = cap.run(lambda: self.vision_forward(rec["px"]))
+            rec["fwd"], rec["fwd_launches"], rec["keep"] = cap.segments, lib.LAUNCHES - l0, [cap]
+            rec["saved"]["graph"] = rec
+            self._recs[key] = rec
+        self.launches += rec["fwd_launches"]
+        rec["px"].copy_(pixels)
+        self._replay(rec["fwd"])
+        return rec["out"].detach(), rec["saved"]  # fresh alias of the static output buffer for autograd
+
+    def vision_backward_auto(self, dout: Tensor, sv) -> None:
+        rec = sv.get("graph")
+        st = self.store
+        if rec is None or st.accumulate or rec["version"] != st.layout_version:
+            return self._counted(self.vision_backward, dout, sv)
+        if rec["bwd"] is None:
+            rec["dout"] = torch.empty_like(rec["out"])
+            cap = TrainEngine._Capture(self)
+            st.capture = cap
+            nb, l0 = st._next_bucket, lib.LAUNCHES
+            try:
+                cap.run(lambda: self.vision_backward(rec["dout"], sv))
+            finally:
+                st.capture = None
+            rec["bwd"], rec["bwd_launches"] = cap.segments, lib.LAUNCHES - l0
+            rec["keep"].append(cap)
+            st._next_bucket = nb
+        self.launches += rec["bwd_launches"]
+        rec["dout"].copy_(dout)
+        self._replay(rec["bwd"])
+        st.skip_to_bucket_after(st.group_index["vit_emb"])
+
+    def llm_forward_auto(self, inputs: Tensor, mask: Optional[Tensor], dropout: bool):
+        B, Lt, _ = inputs.shape
+        key = ("llm", B, Lt, mask is not None, bool(dropout))
+        if not self._graph_ok(key):
+            return self._counted(self.llm_forward, inputs, mask, dropout)
+        rec = self._recs.get(key)
+        if rec is None:
+            rec = dict(version=self.store.layout_version, x=torch.empty_like(inputs), bwd=None,
+                       mask=None if mask is None else torch.empty_like(mask, dtype=torch.bool))
+            self.frozen()
+            cap = TrainEngine._Capture(self)
+            l0 = lib.LAUNCHES
+            rec["out"], rec["saved"] = cap.run(lambda: self.llm_forward(rec["x"], rec["mask"], dropout, static=True))
+            rec["fwd"], rec["fwd_launches"], rec["keep"] = cap.segments, lib.LAUNCHES - l0, [cap]
+            rec["saved"]["graph"] = rec
+            self._recs[key] = rec
+        self.launches += rec["fwd_launches"]
+        rec["x"].copy_(inputs)
+        if mask is not None:
+            rec["mask"].copy_(mask)
+        self._replay(rec["fwd"])
+        return rec["out"].detach(), rec["saved"]
+
+    def llm_backward_auto(self, dfeats: Tensor, sv) -> Tensor:
+        rec = sv.get("graph")
+        st = self.store
+        if rec is None or st.accumulate or rec["version"] != st.layout_version:
+            return self._counted(self.llm_backward, dfeats, sv)
+        if rec["bwd"] is None:
+            rec["dfeats"] = torch.empty_like(rec["out"])
+            cap = TrainEngine._Capture(self)
+            st.capture = cap
+            nb, l0 = st._next_bucket, lib.LAUNCHES
+            try:
+                rec["dx"] = cap.run(lambda: self.llm_backward(rec["dfeats"], sv))
+            finally:
+                st.capture = None
+            rec["bwd"], rec["bwd_launches"] = cap.segments, lib.LAUNCHES - l0
+            rec["keep"].append(cap)
+            st._next_bucket = nb
+        self.launches += rec["bwd_launches"]
+        rec["dfeats"].copy_(dfeats)
+        self._replay(rec["bwd"])
+        st.skip_to_bucket_after(st.group_index["llm0"])
+        return rec["dx"].detach()
 
     # ==================================================================================================
     # vision tower + projector
@@ -303,14 +508,12 @@ class TrainEngine:
             xo = lib.scale_cols_add(p2, w(p + "ls2"), xm)
             layers.append(dict(x=x, st1=st1, h1=h1, qkv=qkv, lse=lse, att=att, p1=p1, xm=xm, st2=st2, h2=h2, fpre=fpre, fact=fact, p2=p2))
             x = xo
-        self.launches += 3 + 10 * s.vit_layers
         # projector: drop CLS + pixel shuffle + LN(4096) -> Linear -> GELU -> Linear
         stp = (f32(T * s.tokens_per_tile), f32(T * s.tokens_per_tile))
         y0 = lib.pixel_shuffle_ln(x, w(MLP1_PREFIX + "0.weight"), w(MLP1_PREFIX + "0.bias"), T, s.proj_eps, stats=stp)
         y1p = lib.gemm(y0, w(MLP1_PREFIX + "1.weight"), bias=w(MLP1_PREFIX + "1.bias"))
         y1 = lib.gelu_fwd(y1p)
         y2 = lib.gemm(y1, w(MLP1_PREFIX + "3.weight"), bias=w(MLP1_PREFIX + "3.bias"))
-        self.launches += 4
         saved = dict(T=T, cols=cols, layers=layers, xv=x, stp=stp, y0=y0, y1p=y1p, y1=y1)
         return y2, saved
 
@@ -329,13 +532,13 @@ class TrainEngine:
         dx = lib.pixel_shuffle_ln_bwd(dy0, sv["xv"], w(MLP1_PREFIX + "0.weight"), sv["stp"][0], sv["stp"][1],
                                       self._acc(MLP1_PREFIX + "0.weight"), self._acc(MLP1_PREFIX + "0.bias"), T)
         del dy0, dy1, dy1p
-        self.launches += 7
         st.flush_group("mlp1")
         # ---- encoder layers ----
         for i in reversed(range(s.vit_layers)):
             p = f"{VIT_PREFIX}encoder.layers.{i}."
             a = sv["layers"][i]
-            sv["layers"][i] = None
+            if "graph" not in sv:
+                sv["layers"][i] = None  # eager: release the layer's activations as soon as they are consumed
             lib.col_reduce(dx, self._acc(p + "ls2"), a["p2"])
             dp2 = lib.scale_cols(dx, w(p + "ls2"))
             lib.col_reduce(dp2, self._acc(p + "mlp.fc2.bias"))
@@ -362,7 +565,6 @@ class TrainEngine:
                                     self._acc(p + "norm1.weight"), self._acc(p + "norm1.bias"), dx=datt)
             lib.add_inplace(dxi, dxm)
             dx = dxi
-            self.launches += 24
             st.flush_group(f"vit{i}")
         # ---- embeddings ----
         e = VIT_PREFIX + "embeddings."
@@ -375,40 +577,42 @@ class TrainEngine:
             g2.add_(gw[:, : s.patch_k])
         else:
             g2.copy_(gw[:, : s.patch_k])
-        self.launches += 4
         st.flush_group("vit_emb")
 
     # ==================================================================================================
     # Qwen2 decoder stack with un-merged LoRA
     # ==================================================================================================
-    def _lora_fwd(self, x: Tensor, pre: str, y: Tensor, seed: Optional[int]):
-        """y (holding base(x)) += scale * B(A(dropout(x)))   [PEFT lora.Linear.forward]"""
+    def _lora_a(self, x: Tensor, pre: str, seed: Optional[int]):
+        """t = A dropout(x)   [first half of PEFT lora.Linear.forward]"""
         if seed is not None:
-            xd = lib.dropout(x, self.spec.lora_dropout, seed)
-            self.launches += 1
+            xd = lib.dropout(x, self.spec.lora_dropout, seed, seed_dev=self.seed_dev)
         else:
             xd = x
         t = lib.gemm(xd, self.w(pre + "lora_A.default.weight"))
-        lib.gemm(t, self.w(pre + "lora_B.default.weight"), out=y, residual=y, alpha=self.spec.lora_scale)
-        self.launches += 2
         return xd, t, seed
 
-    def _lora_bwd(self, dy: Tensor, pre: str, rec, dx: Tensor) -> None:
-        xd, t, seed = rec
-        sc = self.spec.lora_scale
-        self._wgrad(dy, t, pre + "lora_B.default.weight", alpha=sc)
-        dt = lib.gemm(dy, self.w(pre + "lora_B.default.weight"), b_t=True, alpha=sc)
-        self._wgrad(dt, xd, pre + "lora_A.default.weight")
-        if seed is None:
-            lib.gemm(dt, self.w(pre + "lora_A.default.weight"), b_t=True, out=dx, residual=dx)
-        else:
-            dxd = lib.gemm(dt, self.w(pre + "lora_A.default.weight"), b_t=True)
-            lib.dropout_add(dxd, dx, self.spec.lora_dropout, seed)
-            self.launches += 1
-        self.launches += 2
+    def _lora_b(self, rec, pre: str, y: Tensor) -> None:
+        """y (holding base(x)) += scale * B t"""
+        lib.gemm(rec[1], self.w(pre + "lora_B.default.weight"), out=y, residual=y, alpha=self.spec.lora_scale)
 
-    def llm_forward(self, inputs: Tensor, mask: Optional[Tensor], dropout: bool):
-        """inputs [B, Lt, D] bf16 -> (features after the final norm [B, Lt, D], saved)"""
+    def _lora_bwd_b(self, dy: Tensor, pre: str, rec) -> None:
+        self._wgrad(dy, rec[1], pre + "lora_B.default.weight", alpha=self.spec.lora_scale)
+
+    def _lora_bwd_a(self, dy: Tensor, pre: str, rec) -> Tensor:
+        """dA wgrad; returns the gradient w.r.t. the (dropped-out) LoRA input, to be added to the base dgrad"""
+        dt = lib.gemm(dy, self.w(pre + "lora_B.default.weight"), b_t=True, alpha=self.spec.lora_scale)
+        self._wgrad(dt, rec[0], pre + "lora_A.default.weight")
+        return lib.gemm(dt, self.w(pre + "lora_A.default.weight"), b_t=True)
+
+    def _lora_acc(self, dxd: Tensor, dx: Tensor, rec) -> None:
+        if rec[2] is None:
+            lib.add_inplace(dx, dxd)
+        else:
+            lib.dropout_add(dxd, dx, self.spec.lora_dropout, rec[2], seed_dev=self.seed_dev)
+
+    def llm_forward(self, inputs: Tensor, mask: Optional[Tensor], dropout: bool, static: bool = False):
+        """inputs [B, Lt, D] bf16 -> (features after the final norm [B, Lt, D], saved).  ``static``: no host sync on
+        the mask contents (graph capture)."""
         s, w = self.spec, self.w
         B, Lt, D = inputs.shape
         M = B * Lt
@@ -419,14 +623,14 @@ class TrainEngine:
         kc = torch.zeros((s.llm_layers, B, Hkv, lmax, hd), device=dev, dtype=bf)
         vc = torch.zeros_like(kc)
         kv_valid = None
-        if mask is not None and not bool(mask.all()):
+        if mask is not None and (static or not bool(mask.all())):
             kv_valid = torch.zeros((B, lmax), device=dev, dtype=torch.uint8)
             kv_valid[:, :Lt] = mask.to(torch.uint8)
         use_drop = dropout and s.lora_dropout > 0
-        self.seed_counter += 1
+        self.seed_dev.add_(1)  # on the device: a replayed graph draws fresh masks, backward re-reads the same value
 
         def seed(i, j):
-            return ((self.base_seed + self.seed_counter) << 16) + i * 8 + j if use_drop else None
+            return (self.base_seed << 8) + i * 8 + j if use_drop else None
 
         x = inputs.reshape(M, D).contiguous()
         frozen = self.frozen()
@@ -437,30 +641,32 @@ class TrainEngine:
             r1 = torch.empty(M, device=dev, dtype=torch.float32)
             h1 = lib.rmsnorm(x, w(p + "input_layernorm.weight"), s.rms_eps, rstd=r1)
             qkv = lib.gemm(h1, frozen[i][0], bias=frozen[i][1])
-            lq = self._lora_fwd(h1, pa + "q_proj.", qkv[:, :qd], seed(i, 0))
-            lk = self._lora_fwd(h1, pa + "k_proj.", qkv[:, qd:qd + kd], seed(i, 1))
-            lv = self._lora_fwd(h1, pa + "v_proj.", qkv[:, qd + kd:], seed(i, 2))
+            lq, lk, lv = self._par(lambda: self._lora_a(h1, pa + "q_proj.", seed(i, 0)), lambda: self._lora_a(h1, pa + "k_proj.", seed(i, 1)),
+                                   lambda: self._lora_a(h1, pa + "v_proj.", seed(i, 2)))
+            self._par(lambda: self._lora_b(lq, pa + "q_proj.", qkv[:, :qd]), lambda: self._lora_b(lk, pa + "k_proj.", qkv[:, qd:qd + kd]),
+                      lambda: self._lora_b(lv, pa + "v_proj.", qkv[:, qd + kd:]))
             lib.rope_kv_write(qkv, kc[i], vc[i], B, Lt, 0, Hq, Hkv, s.rope_theta)
             lse = torch.empty((B, Hq, Lt), device=dev, dtype=torch.float32)
             att = lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], B, Lt, 0, Hq, Hkv, key_valid=kv_valid, lse=lse)
             xm = lib.gemm(att, w(pa + "o_proj.base_layer.weight"), residual=x)
-            lo = self._lora_fwd(att, pa + "o_proj.", xm, seed(i, 3))
+            lo = self._lora_a(att, pa + "o_proj.", seed(i, 3))
+            self._lora_b(lo, pa + "o_proj.", xm)
             r2 = torch.empty(M, device=dev, dtype=torch.float32)
             h2 = lib.rmsnorm(xm, w(p + "post_attention_layernorm.weight"), s.rms_eps, rstd=r2)
             g = lib.gemm(h2, w(pm + "gate_proj.base_layer.weight"))
-            lg = self._lora_fwd(h2, pm + "gate_proj.", g, seed(i, 4))
             u = lib.gemm(h2, w(pm + "up_proj.base_layer.weight"))
-            lu = self._lora_fwd(h2, pm + "up_proj.", u, seed(i, 5))
+            lg, lu = self._par(lambda: self._lora_a(h2, pm + "gate_proj.", seed(i, 4)), lambda: self._lora_a(h2, pm + "up_proj.", seed(i, 5)))
+            self._lora_b(lg, pm + "gate_proj.", g)
+            self._lora_b(lu, pm + "up_proj.", u)
             act = lib.silu_mul(g, u)
             xo = lib.gemm(act, w(pm + "down_proj.base_layer.weight"), residual=xm)
-            ld = self._lora_fwd(act, pm + "down_proj.", xo, seed(i, 6))
+            ld = self._lora_a(act, pm + "down_proj.", seed(i, 6))
+            self._lora_b(ld, pm + "down_proj.", xo)
             layers.append(dict(x=x, r1=r1, h1=h1, qkv=qkv, lse=lse, att=att, xm=xm, r2=r2, h2=h2, g=g, u=u, act=act,
                                lora=(lq, lk, lv, lo, lg, lu, ld)))
             x = xo
-            self.launches += 10
         rf = torch.empty(M, device=dev, dtype=torch.float32)
         feats = lib.rmsnorm(x, w(LLM_PREFIX + "model.norm.weight"), s.rms_eps, rstd=rf)
-        self.launches += 1
         saved = dict(B=B, Lt=Lt, layers=layers, kc=kc, vc=vc, kv_valid=kv_valid, xf=x, rf=rf)
         return feats.view(B, Lt, D), saved
 
@@ -474,38 +680,49 @@ class TrainEngine:
         kvv = sv["kv_valid"]
         frozen = self.frozen()
         dx = lib.rmsnorm_bwd(dfeats.reshape(M, D).contiguous(), sv["xf"], w(LLM_PREFIX + "model.norm.weight"), sv["rf"])
-        self.launches += 1
         for i in reversed(range(s.llm_layers)):
             p = f"{LLM_PREFIX}model.layers.{i}."
             pa, pm = p + "self_attn.", p + "mlp."
             a = sv["layers"][i]
-            sv["layers"][i] = None
+            if "graph" not in sv:
+                sv["layers"][i] = None
             lq, lk, lv, lo, lg, lu, ld = a["lora"]
             # ---- MLP ----
             dact = lib.gemm(dx, w(pm + "down_proj.base_layer.weight"), b_t=True)
-            self._lora_bwd(dx, pm + "down_proj.", ld, dact)
+            dxd, _ = self._par(lambda: self._lora_bwd_a(dx, pm + "down_proj.", ld), lambda: self._lora_bwd_b(dx, pm + "down_proj.", ld))
+            self._lora_acc(dxd, dact, ld)
             dg, du = lib.silu_mul_bwd(a["g"], a["u"], dact)
             dh2 = lib.gemm(dg, w(pm + "gate_proj.base_layer.weight"), b_t=True)
             lib.gemm(du, w(pm + "up_proj.base_layer.weight"), b_t=True, out=dh2, residual=dh2)
-            self._lora_bwd(dg, pm + "gate_proj.", lg, dh2)
-            self._lora_bwd(du, pm + "up_proj.", lu, dh2)
+            dxg, dxu, _, _ = self._par(lambda: self._lora_bwd_a(dg, pm + "gate_proj.", lg), lambda: self._lora_bwd_a(du, pm + "up_proj.", lu),
+                                       lambda: self._lora_bwd_b(dg, pm + "gate_proj.", lg), lambda: self._lora_bwd_b(du, pm + "up_proj.", lu))
+            self._lora_acc(dxg, dh2, lg)
+            self._lora_acc(dxu, dh2, lu)
             dxm = lib.rmsnorm_bwd(dh2, a["xm"], w(p + "post_attention_layernorm.weight"), a["r2"])
             lib.add_inplace(dxm, dx)
             # ---- attention ----
             datt = lib.gemm(dxm, w(pa + "o_proj.base_layer.weight"), b_t=True)
-            self._lora_bwd(dxm, pa + "o_proj.", lo, datt)
+            dxo, _ = self._par(lambda: self._lora_bwd_a(dxm, pa + "o_proj.", lo), lambda: self._lora_bwd_b(dxm, pa + "o_proj.", lo))
+            self._lora_acc(dxo, datt, lo)
             delta = lib.attn_delta(a["att"], datt, B, Lt, Hq)
             dq, dk, dv = lib.attn_gqa_bwd(a["qkv"], s.qkv_dim, sv["kc"][i], sv["vc"][i], datt, a["lse"], delta, B, Lt, Hq, Hkv, key_valid=kvv)
             dqkv = lib.rope_bwd(dq, dk, dv, B, Lt, Hq, Hkv, s.rope_theta)
             del dq, dk, dv
             dh1 = lib.gemm(dqkv, frozen[i][0], b_t=True)
-            self._lora_bwd(dqkv[:, :qd], pa + "q_proj.", lq, dh1)
-            self._lora_bwd(dqkv[:, qd:qd + kd], pa + "k_proj.", lk, dh1)
-            self._lora_bwd(dqkv[:, qd + kd:], pa + "v_proj.", lv, dh1)
+            gq, gk, gv = dqkv[:, :qd], dqkv[:, qd:qd + kd], dqkv[:, qd + kd:]
+
+            def all_b():
+                self._lora_bwd_b(gq, pa + "q_proj.", lq)
+                self._lora_bwd_b(gk, pa + "k_proj.", lk)
+                self._lora_bwd_b(gv, pa + "v_proj.", lv)
+            dxq, dxk, dxv, _ = self._par(lambda: self._lora_bwd_a(gq, pa + "q_proj.", lq), lambda: self._lora_bwd_a(gk, pa + "k_proj.", lk),
+                                         lambda: self._lora_bwd_a(gv, pa + "v_proj.", lv), all_b)
+            self._lora_acc(dxq, dh1, lq)
+            self._lora_acc(dxk, dh1, lk)
+            self._lora_acc(dxv, dh1, lv)
             dxi = lib.rmsnorm_bwd(dh1, a["x"], w(p + "input_layernorm.weight"), a["r1"])
             lib.add_inplace(dxi, dxm)
             dx = dxi
-            self.launches += 14
             st.flush_group(f"llm{i}")
         return dx.view(B, Lt, D)
 
@@ -558,14 +775,14 @@ def _queue_finish(store: ParamStore) -> None:
 class _VisionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pixels: Tensor, anchor: Tensor, eng: TrainEngine):
-        out, saved = eng.vision_forward(pixels)
+        out, saved = eng.vision_forward_auto(pixels)
         ctx.eng, ctx.saved = eng, saved
         return out
 
     @staticmethod
     def backward(ctx, dout: Tensor):
         _queue_finish(ctx.eng.store)
-        ctx.eng.vision_backward(dout, ctx.saved)
+        ctx.eng.vision_backward_auto(dout.contiguous(), ctx.saved)
         ctx.saved = None
         return None, None, None
 
@@ -573,14 +790,14 @@ class _VisionFn(torch.autograd.Function):
 class _LLMFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inputs: Tensor, anchor: Tensor, eng: TrainEngine, mask: Optional[Tensor], dropout: bool):
-        feats, saved = eng.llm_forward(inputs, mask, dropout)
+        feats, saved = eng.llm_forward_auto(inputs.contiguous(), mask, dropout)
         ctx.eng, ctx.saved = eng, saved
         return feats
 
     @staticmethod
     def backward(ctx, dfeats: Tensor):
         _queue_finish(ctx.eng.store)
-        dx = ctx.eng.llm_backward(dfeats.to(torch.bfloat16), ctx.saved)
+        dx = ctx.eng.llm_backward_auto(dfeats.to(torch.bfloat16).contiguous(), ctx.saved)
         ctx.saved = None
         return dx, None, None, None, None
 

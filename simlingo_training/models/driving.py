@@ -147,7 +147,8 @@ class DrivingModel(_Base):
     def forward_model(self, driving_input: DrivingInput, adaptor_dict: Dict, driving_labels: DrivingLabel = None,
                       want_logits: bool = True):
         """Teacher-forced pass over [valid language | 30 queries | pads] -> (features, logits) for every position."""
-        self._engine()
+        if not torch.is_grad_enabled():
+            self._engine()  # inference kernels with LoRA folded into scratch weights; the training path runs un-merged
         adaptor_dict = self._substituted(driving_input, adaptor_dict)
         embeds = adaptor_dict["inputs"].to(dtype=self.language_model.model.dtype)
         feats, logits = _rt.llm_forward(self.language_model.model.base_model.model, embeds, adaptor_dict["inputs_mask"],

@@ -110,3 +110,25 @@ def test_dropout_training_mode_runs(setup):
         assert torch.isfinite(out.loss) and torch.isfinite(store.flat_grad.float()).all()
     finally:
         model.eval()
+
+
+def test_graph_replay_matches_eager(setup):
+    """From the second call with a given shape the engine replays CUDA graphs: same loss and gradients as the eager
+    launches (eval mode: no dropout, so the comparison is exact up to atomics ordering)."""
+    spec, case, *_, model = setup
+    ex = to_driving_example(case)
+    store = model.param_store()
+    eng = model.__dict__["_slb_train_engine"]
+    res = []
+    for mode in (False, True, True):
+        eng.graphs_enabled = mode
+        store.zero_grad()
+        r0 = eng.graph_replays
+        out, _ = model.forward_loss(ex)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        res.append((out.loss.item(), store.flat_grad.float().clone(), eng.graph_replays - r0))
+    assert res[0][2] == 0 and res[2][2] >= 4, [r[2] for r in res]   # vision fwd/bwd + decoder fwd/bwd graphs
+    for loss, grad, _ in res[1:]:
+        assert abs(loss - res[0][0]) < 1e-3 * abs(res[0][0])
+        assert relerr(grad, res[0][1]) < 2e-2

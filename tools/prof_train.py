@@ -48,3 +48,15 @@ tot = sum(e.self_device_time_total for e in ev)
 print(f"total device time {tot / 1e3:.2f} ms")
 for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:45]:
     print(f"{e.self_device_time_total / 1e3:9.3f} ms {100 * e.self_device_time_total / tot:5.1f}% n={e.count:5d} avg={e.self_device_time_total / e.count:8.1f} us  {e.key[:110]}")
+
+# ---- host-side profile of one step (python overhead) ----
+import cProfile, pstats, io
+pr = cProfile.Profile()
+torch.cuda.synchronize()
+pr.enable()
+step()
+pr.disable()
+torch.cuda.synchronize()
+sio = io.StringIO()
+pstats.Stats(pr, stream=sio).sort_stats("cumulative").print_stats(45)
+print("\n".join(l[:170] for l in sio.getvalue().splitlines()[:75]))
