@@ -341,6 +341,7 @@ def run_train(args, rank, world, local):
         return
     peaks = measured_peaks()
     teng.graphs_enabled = False  # the per-launch event timing needs the eager launches (the timed region above replays graphs)
+    store.pg, store.world = None, 1  # rank 0 alone from here on: no collectives in the roofline pass
     step(example)
     roof = gemm_roofline(model, example, peaks, step_fn=lambda: step(example))
     teng.graphs_enabled = True

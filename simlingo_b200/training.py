@@ -65,12 +65,13 @@ class ParamStore:
     every trainable ``Parameter.data`` is a view into ``flat_param`` and ``grad_view[key]`` is the matching view into
     ``flat_grad``."""
 
-    def __init__(self, root: nn.Module, prefix: str, spec: ModelSpec, bucket_bytes: int = 48 << 20):
+    def __init__(self, root: nn.Module, prefix: str, spec: ModelSpec, bucket_bytes: int = 48 << 20, allow_cpu: bool = False):
+        """``allow_cpu`` exists for the host-logic tests of the layout / bucket bookkeeping (gloo, no kernels)."""
         self.spec = spec
         params: Dict[str, nn.Parameter] = {}
         for n, p in root.named_parameters():
             if p.requires_grad:
-                if not (p.is_cuda and p.dtype == torch.bfloat16):
+                if not ((p.is_cuda or allow_cpu) and p.dtype == torch.bfloat16):
                     raise RuntimeError(f"simlingo_b200 trains bf16 CUDA parameters only (no fallback): {n} is {p.dtype} on {p.device}")
                 params[prefix + n] = p
         if not params:

@@ -141,6 +141,32 @@ g = torch.full((16,), float(rank + 1), dtype=torch.bfloat16)
 dist.all_reduce(g)
 g /= world
 assert torch.allclose(g.float(), torch.full((16,), (world + 1) / 2.0))
+# flat parameter / gradient store: layout in backward-completion order, bucketed all-reduce as groups finish
+from simlingo_b200.spec import tiny_spec, LLM_PREFIX, VIT_PREFIX
+from simlingo_b200.training import ParamStore
+from tests.helpers import build_drop_in_model
+spec = tiny_spec(2, 2, 512)
+model = build_drop_in_model(spec, "internvl2-tiny-dp", device="cpu")
+store = ParamStore(model, "", spec, bucket_bytes=8 << 20, allow_cpu=True)
+names = [g.name for g in store.groups]
+assert names == ["llm1", "llm0", "mlp1", "vit1", "vit0", "vit_emb", "other"], names
+assert all(p.data_ptr() == store.flat_param[o:o + n].data_ptr() for k, p in store.params.items() for o, n in [store.offsets[k]])
+assert all(o % 8 == 0 for o, _ in store.offsets.values())
+assert len(store._buckets) >= 3 and store._buckets[0][0] == 0 and store._buckets[-1][1] == store.numel
+store.enable_data_parallel()
+store.begin_backward()
+store.flat_grad.fill_(float(rank + 1))
+order = []
+for gi, g in enumerate(store.groups[:-1]):
+    before = store.n_allreduce
+    store.group_ready(gi)
+    order.append(store.n_allreduce - before)
+assert sum(order) == len(store._buckets) - 1, (order, store._buckets)   # the tail bucket waits for the end of backward
+store.finish_backward()
+store.wait_exchange()
+assert store.n_allreduce == len(store._buckets)
+assert torch.equal(store.flat_grad.float(), torch.full((store.numel,), float(sum(range(1, world + 1)))))
+assert all(p.grad.data_ptr() == store.grad_view[k].data_ptr() for k, p in store.params.items())
 dist.destroy_process_group()
 print("ok", rank)
 """
@@ -154,5 +180,5 @@ def test_world_size_2_gloo():
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
-        out, _ = p.communicate(timeout=120)
+        out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, out
