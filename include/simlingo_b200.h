@@ -74,16 +74,18 @@ int slb_attn_vit_fwd(const void* qkv, void* out, float* lse, int tiles, int n_to
 /* LLM: causal GQA (14 q heads / 2 kv heads x 64) over a KV cache (modeling_qwen2.py:161-204,
  * replaces flash_attention_2).  q [B, Lq, Hq*64] (row stride ldq), cache k/v [B, Hkv, Lmax, 64];
  * query i of the chunk sits at absolute position past+i and sees keys j <= past+i with
- * key_valid[b*key_valid_ld + j] != 0 (key_valid may be NULL).  out [B, Lq, Hq*64]. */
+ * key_valid[b*key_valid_ld + j] != 0 (key_valid may be NULL).  out [B, Lq, Hq*64].
+ * past_dev (nullable device int32): when given, the chunk position is read on the device instead of `past` (which then
+ * only bounds the host-side checks), so that one captured CUDA graph serves every decode step; chunks of <= 32 queries. */
 int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
-                     int key_valid_ld, void* out, float* lse, int batch, int lq, int past, int lmax, int hq, int hkv,
-                     void* stream);
+                     int key_valid_ld, void* out, float* lse, int batch, int lq, int past, const int32_t* past_dev, int lmax,
+                     int hq, int hkv, void* stream);
 
 /* ---- RoPE + KV-cache write (modeling_qwen2.py:102-146 rotate_half convention, theta 1e6) --------
  * qkv [B*Lq, (Hq+2Hkv)*64] from the fused QKV GEMM; rotates q in place, writes rotated k and v
  * into the caches at positions past..past+Lq-1 (positions are arange over the padded sequence). */
-int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, int lmax, int hq, int hkv,
-                      float theta, void* stream);
+int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, const int32_t* past_dev, int lmax,
+                      int hq, int hkv, float theta, void* stream);
 /* ---- embeddings / placeholder substitution (adaptors.py:256; internvl2_model.py:54-91,119-131) --
  * out[b,l] = table[clamp(ids[b,l],0,V-1)]; rows with ids == img_id take vit[b*n_img + rank] where
  * rank counts <IMG_CONTEXT> ids before l; rows l in [wp_start[b], wp_start[b]+wp_len) take wp[b, l-wp_start[b]]. */

@@ -264,8 +264,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 __global__ void __launch_bounds__(128)
 attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
                   const uint8_t* __restrict__ key_valid, int key_valid_ld, bf16* __restrict__ out, long long ldo, int lq, int past,
-                  int lmax, int hq, int hkv, float scale) {
+                  int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev) {
   extern __shared__ float sm[];
+  if (past_dev) past = *past_dev;  // position counter kept on the device: the same CUDA graph serves every decode step
   float* qs = sm;            // 64
   float* red = sm + 64;      // 8 + 128
   float* sc = sm + 64 + 136; // lmax
@@ -361,8 +362,8 @@ extern "C" int slb_attn_vit_fwd(const void* qkv, void* out, float* lse, int tile
 }
 
 extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
-                                int key_valid_ld, void* out, float* lse, int batch, int lq, int past, int lmax, int hq, int hkv,
-                                void* stream) {
+                                int key_valid_ld, void* out, float* lse, int batch, int lq, int past, const int32_t* past_dev, int lmax,
+                                int hq, int hkv, void* stream) {
   SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax && hq % hkv == 0, "attn_gqa: bad shape");
   SLB_CHECK_ARG((ldq % 8) == 0, "attn_gqa: ldq must be a multiple of 8");
   SLB_CHECK_ARG(past + lq <= kMaxKvBlocks * BKV, "attn_gqa: at most %d keys", kMaxKvBlocks * BKV);
@@ -372,10 +373,11 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
     const size_t smem = (64 + 136 + (size_t)lmax) * sizeof(float);
     SLB_CHECK_ARG(smem <= 48 * 1024, "attn_gqa: lmax=%d too long for the small-Lq kernel", lmax);
     attn_small_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const bf16*)q, ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid,
-                                                               key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq, hkv, scale);
+                                                               key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq, hkv, scale, past_dev);
     SLB_LAUNCH_CHECK();
     return SLB_OK;
   }
+  SLB_CHECK_ARG(past_dev == nullptr, "attn_gqa: a device-side position is only supported for chunks of <= 32 queries without lse");
   CUtensorMap tq, tk, tv;
   int rc = slb_make_tmap_3d(&tq, q, (uint64_t)ldq, (uint64_t)lq, (uint64_t)batch, (uint64_t)ldq * 2, (uint64_t)lq * ldq * 2, HD, BQ, 1);
   if (rc) return rc;

@@ -179,7 +179,8 @@ __global__ void vit_assemble_kernel(const bf16* __restrict__ patch_out, const bf
 // RoPE (rotate_half convention) on q and k + KV-cache write.  One thread per (row, head, d<32).
 // ------------------------------------------------------------------------------------------------
 __global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, int batch, int lq,
-                                     int past, int lmax, int hq, int hkv, float log2_theta) {
+                                     int past, int lmax, int hq, int hkv, float log2_theta, const int* __restrict__ past_dev) {
+  if (past_dev) past = *past_dev;
   const int heads = hq + 2 * hkv;
   const size_t total = (size_t)batch * lq * heads * 32;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -493,11 +494,11 @@ extern "C" int slb_vit_assemble(const void* patch_out, const void* cls, const vo
   return SLB_OK;
 }
 
-extern "C" int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, int lmax, int hq, int hkv,
-                                 float theta, void* stream) {
+extern "C" int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, const int32_t* past_dev, int lmax,
+                                 int hq, int hkv, float theta, void* stream) {
   SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax, "rope: batch=%d lq=%d past=%d lmax=%d", batch, lq, past, lmax);
   const size_t total = (size_t)batch * lq * (hq + 2 * hkv) * 32;
-  rope_kv_write_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq, past, lmax, hq, hkv, log2f(theta));
+  rope_kv_write_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq, past, lmax, hq, hkv, log2f(theta), past_dev);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

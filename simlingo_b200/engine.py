@@ -44,6 +44,15 @@ class Engine:
         self._packed_version = None
         self.launches = 0
         self.generation_fn = None  # set by runtime when a training ParamStore updates the weights behind torch's back
+        # CUDA graphs for the launch-bound paths (ViT on 2 tiles, batch-1 prefill, decode steps, query append): first call
+        # with a shape runs eagerly, the second captures, later ones replay.  SLB_INFER_GRAPHS=0 disables.
+        import os
+        self.graphs_enabled = os.environ.get("SLB_INFER_GRAPHS", "1") != "0"
+        self._graphs: Dict[tuple, dict] = {}
+        self._seen: Dict[tuple, int] = {}
+        self._pool = None
+        self._cap_stream = None
+        self.graph_replays = 0
         self.refresh()
 
     # ------------------------------------------------------------------------------------------
@@ -66,6 +75,8 @@ class Engine:
         ver = self._version()
         if not force and ver == self._packed_version:
             return
+        self._graphs.clear()  # captured graphs hold pointers into the scratch weights rebuilt below
+        self._seen.clear()
         s, w = self.spec, self._w
         e = VIT_PREFIX + "embeddings."
         self.has_vit = (e + "patch_embedding.weight") in self.sd
@@ -103,6 +114,59 @@ class Engine:
             self.wp_w = lib.WpWeights(*[w("wp_encoder.mlp." + k).data_ptr() for k in (
                 "0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias")])
         self._packed_version = ver
+
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph helpers
+    # ------------------------------------------------------------------------------------------
+    def _capture(self, fn):
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+            self._cap_stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.synchronize(self.dev)
+        cs = self._cap_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        l0 = lib.LAUNCHES
+        with torch.cuda.stream(cs):
+            g.capture_begin(pool=self._pool, capture_error_mode="thread_local")
+            try:
+                out = fn()
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream().wait_stream(cs)
+        return g, out, lib.LAUNCHES - l0
+
+    def _use_graph(self, key: tuple) -> bool:
+        if not self.graphs_enabled:
+            return False
+        if key in self._graphs:
+            return True
+        n = self._seen.get(key, 0)
+        self._seen[key] = n + 1
+        if n >= 1 and len(self._graphs) >= 12:   # bound the memory held by static buffers: drop the oldest shape
+            self._graphs.pop(next(iter(self._graphs)))
+        return n >= 1
+
+    def _replay(self, g, n_launches: int) -> None:
+        g.replay()
+        self.graph_replays += 1
+        self.launches += n_launches
+
+    def extract_feature_auto(self, pixels: Tensor) -> Tensor:
+        """``extract_feature`` behind a CUDA graph for small tile counts (the agent's 2 tiles are launch-bound)."""
+        T = int(pixels.shape[0])
+        key = ("vit", T)
+        if T > 8 or not self._use_graph(key):
+            return self.extract_feature(pixels)
+        rec = self._graphs.get(key)
+        if rec is None:
+            rec = dict(px=torch.empty_like(pixels))
+            rec["g"], rec["out"], rec["n"] = self._capture(lambda: self.extract_feature(rec["px"]))
+            self._graphs[key] = rec
+        rec["px"].copy_(pixels)
+        self._replay(rec["g"], rec["n"])
+        return rec["out"]
 
     # ------------------------------------------------------------------------------------------
     # InternViT + projector
@@ -198,7 +262,7 @@ class Engine:
         if pixels is not None and pixels.numel() > 0 and L != 1:
             BS, T, NP = pixels.shape[:3]
             assert T == 1, "Only one frame is supported for now"
-            vit = self.extract_feature(pixels.reshape(BS * NP, *pixels.shape[3:]))
+            vit = self.extract_feature_auto(pixels.reshape(BS * NP, *pixels.shape[3:]).contiguous())
             n_img = NP * s.tokens_per_tile
         wp = wp_start = None
         wp_len = 0
@@ -225,7 +289,7 @@ class Engine:
         return (torch.zeros(shape, device=self.dev, dtype=torch.bfloat16), torch.zeros(shape, device=self.dev, dtype=torch.bfloat16))
 
     def llm_chunk(self, x: Tensor, batch: int, lq: int, past: int, cache: Tuple[Tensor, Tensor],
-                  key_valid: Optional[Tensor] = None, collect: Optional[list] = None) -> Tensor:
+                  key_valid: Optional[Tensor] = None, collect: Optional[list] = None, past_dev: Optional[Tensor] = None) -> Tensor:
         """One pass of ``lq`` new positions per sequence through all decoder layers.
         x [B*lq, 896] (consumed in place) -> residual stream before the final norm."""
         s = self.spec
@@ -238,8 +302,9 @@ class Engine:
         for i, ly in enumerate(self.llm_layers):
             lib.rmsnorm(x, ly["ln1"], s.rms_eps, out=h)
             lib.gemm(h, ly["qkv"], out=qkv, bias=ly["bqkv"])
-            lib.rope_kv_write(qkv, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, s.rope_theta)
-            lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, key_valid=key_valid, out=att)
+            lib.rope_kv_write(qkv, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, s.rope_theta, past_dev=past_dev)
+            lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, key_valid=key_valid, out=att,
+                         past_dev=past_dev)
             lib.gemm(att, ly["o"], out=x, residual=x)
             lib.rmsnorm(x, ly["ln2"], s.rms_eps, out=h)
             lib.gemm(h, ly["gu"], out=act, swiglu=True)
@@ -262,6 +327,79 @@ class Engine:
         self.launches += 2
         return lib.driving_heads(feats30, ld_batch, self.heads_w, batch)
 
+
+    # ------------------------------------------------------------------------------------------
+    # graphed generation: prefill graph, one decode-step graph replayed per token (position counter on the device),
+    # query-append graph.  Sequences must all stop at the same step (batch 1, or EOS suppressed).
+    # ------------------------------------------------------------------------------------------
+    def _generate_graphed(self, lang_embeds: Tensor, max_new_tokens: int, eos_token_id: Optional[int]):
+        s = self.spec
+        B, L, D = lang_embeds.shape
+        nq = s.n_queries
+        key = ("gen", B, L, max_new_tokens, eos_token_id)
+        rec = self._graphs.get(key)
+        if rec is None:
+            dev = self.dev
+            lmax = L + max_new_tokens + nq
+            rec = dict(x=torch.empty_like(lang_embeds), cache=self.new_cache(B, lmax), pos=torch.zeros(1, device=dev, dtype=torch.int32),
+                       nxt=torch.zeros(B, device=dev, dtype=torch.int64), step=torch.zeros(1, device=dev, dtype=torch.int64),
+                       sampled=torch.zeros((B, max_new_tokens), device=dev, dtype=torch.int64), done=torch.zeros(B, device=dev, dtype=torch.bool),
+                       n_gen=torch.zeros(B, device=dev, dtype=torch.int64))
+            emb_w = self._w(LLM_PREFIX + "model.embed_tokens.weight")
+            lm_cap = rec["cache"][0].shape[3]
+
+            def sample(last):
+                lg = self.logits(last)
+                lib.argmax(lg, out_idx=rec["nxt"])
+                self.launches += 1
+                idx = rec["step"].view(1, 1).expand(B, 1)
+                cur = rec["sampled"].gather(1, idx)
+                rec["sampled"].scatter_(1, idx, torch.where(rec["done"][:, None], cur, rec["nxt"][:, None]))
+                rec["n_gen"].add_((~rec["done"]).long())
+                if eos_token_id is not None:
+                    rec["done"].logical_or_(rec["nxt"] == eos_token_id)
+                rec["step"].add_(1)
+
+            def prefill():
+                rec["pos"].fill_(L)
+                rec["step"].zero_(); rec["done"].zero_(); rec["n_gen"].zero_()
+                rec["sampled"].fill_(eos_token_id if eos_token_id is not None else 0)
+                x = self.llm_chunk(rec["x"].reshape(B * L, D).clone(), B, L, 0, rec["cache"], None)
+                sample(self.final_norm(x.view(B, L, D)[:, -1].contiguous()))
+
+            def decode():
+                e = lib.gather_rows(emb_w, rec["nxt"])
+                x = self.llm_chunk(e, B, 1, lm_cap - 1, rec["cache"], None, past_dev=rec["pos"])
+                rec["pos"].add_(1)
+                sample(self.final_norm(x))
+
+            def queries():
+                e = lib.gather_rows(emb_w, rec["nxt"])
+                chunk = torch.cat([e.view(B, 1, D), self.queries.unsqueeze(0).expand(B, nq, D)], 1).reshape(B * (nq + 1), D).contiguous()
+                xx = self.llm_chunk(chunk, B, nq + 1, lm_cap - nq - 1, rec["cache"], None, past_dev=rec["pos"])
+                f = self.final_norm(xx.view(B, nq + 1, D)[:, 1:].reshape(B * nq, D).contiguous())
+                return self.heads(f, B, nq * D)
+
+            l0 = self.launches
+            rec["g_pre"], _, rec["n_pre"] = self._capture(prefill)
+            rec["g_dec"], _, rec["n_dec"] = self._capture(decode)
+            rec["g_q"], rec["out"], rec["n_q"] = self._capture(queries)
+            self.launches = l0
+            self._graphs[key] = rec
+        rec["x"].copy_(lang_embeds)
+        self._replay(rec["g_pre"], rec["n_pre"])
+        steps = 1
+        for i in range(1, max_new_tokens):
+            if eos_token_id is not None and bool(rec["done"].all()):  # host sync, as llm.py:245
+                break
+            self._replay(rec["g_dec"], rec["n_dec"])
+            steps += 1
+        self._replay(rec["g_q"], rec["n_q"])
+        route, speed = rec["out"]
+        n_gen_cpu = rec["n_gen"].tolist()
+        toks = [rec["sampled"][b, : max(n_gen_cpu[b], 1)].clone() for b in range(B)]
+        return speed.clone(), route.clone(), toks
+
     # ------------------------------------------------------------------------------------------
     # DrivingModel.forward (inference): greedy decode + 30-query pass + heads
     # ------------------------------------------------------------------------------------------
@@ -279,6 +417,9 @@ class Engine:
         B, L, D = lang_embeds.shape
         nq = s.n_queries
         has_pad = valid is not None and not bool(valid.all())
+        if (not has_pad and margins is None and (B == 1 or eos_token_id is None)
+                and self._use_graph(("gen", B, L, max_new_tokens, eos_token_id))):
+            return self._generate_graphed(lang_embeds, max_new_tokens, eos_token_id)
         lmax = L + max_new_tokens + nq
         cache = self.new_cache(B, lmax)
         kv_valid = None

@@ -165,8 +165,9 @@ def attn_vit(qkv, tiles, n_tokens, heads=16, out=None, lse=None):
     return out
 
 
-def attn_gqa(q, ldq, kcache, vcache, batch, lq, past, hq=14, hkv=2, key_valid=None, out=None, lse=None):
-    """q: view into the fused qkv buffer ([B*Lq, ldq] rows, first hq*64 columns are q)."""
+def attn_gqa(q, ldq, kcache, vcache, batch, lq, past, hq=14, hkv=2, key_valid=None, out=None, lse=None, past_dev=None):
+    """q: view into the fused qkv buffer ([B*Lq, ldq] rows, first hq*64 columns are q).
+    past_dev: int32 CUDA tensor [1] holding the chunk position (overrides ``past`` on the device)."""
     _bf16(q, kcache, vcache)
     lmax = kcache.shape[2]
     assert kcache.shape == (batch, hkv, lmax, 64) and kcache.is_contiguous() and vcache.is_contiguous()
@@ -176,15 +177,15 @@ def attn_gqa(q, ldq, kcache, vcache, batch, lq, past, hq=14, hkv=2, key_valid=No
         assert key_valid.dtype == torch.uint8 and key_valid.dim() == 2 and key_valid.stride(1) == 1
         kv_ld = key_valid.stride(0)
     _check(load().slb_attn_gqa_fwd(_p(q), C.c_int64(ldq), _p(kcache), _p(vcache), _p(key_valid), kv_ld, _p(out), _p(lse),
-                                   batch, lq, past, lmax, hq, hkv, _stream()), "attn_gqa_fwd")
+                                   batch, lq, past, _p(past_dev), lmax, hq, hkv, _stream()), "attn_gqa_fwd")
     return out
 
 
-def rope_kv_write(qkv, kcache, vcache, batch, lq, past, hq=14, hkv=2, theta=1.0e6):
+def rope_kv_write(qkv, kcache, vcache, batch, lq, past, hq=14, hkv=2, theta=1.0e6, past_dev=None):
     _bf16(qkv, kcache, vcache)
     assert qkv.is_contiguous() and qkv.shape == (batch * lq, (hq + 2 * hkv) * 64)
     lmax = kcache.shape[2]
-    _check(load().slb_rope_kv_write(_p(qkv), _p(kcache), _p(vcache), batch, lq, past, lmax, hq, hkv, C.c_float(theta), _stream()),
+    _check(load().slb_rope_kv_write(_p(qkv), _p(kcache), _p(vcache), batch, lq, past, _p(past_dev), lmax, hq, hkv, C.c_float(theta), _stream()),
            "rope_kv_write")
 
 

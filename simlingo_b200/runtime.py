@@ -64,7 +64,8 @@ def extract_feature(chat_model: nn.Module, pixel_values: Tensor) -> Tensor:
     eng = engine_for(chat_model, prefix, chat_model.spec)
     px = pixel_values.to(torch.bfloat16).contiguous()
     T = px.shape[0]
-    return eng.extract_feature(px).view(T, chat_model.spec.tokens_per_tile, chat_model.spec.llm_hidden)
+    # .clone(): small tile counts come out of a CUDA graph's static buffer
+    return eng.extract_feature_auto(px).clone().view(T, chat_model.spec.tokens_per_tile, chat_model.spec.llm_hidden)
 
 
 def embedding_lookup(weight: Tensor, ids: Tensor) -> Tensor:
