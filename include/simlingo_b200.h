@@ -49,6 +49,8 @@ typedef struct {
   int32_t out_fp32;
   int32_t a_t, b_t;
   int32_t block_n;                /* 0 = auto, else 128 or 256 */
+  const void* rms_weight;         /* bf16 [K] or NULL: A rows are RMS-normalised on the fly, A' = A * rsqrt(mean(A^2) + rms_eps) * w */
+  float rms_eps;                  /*   (Qwen2RMSNorm fused into the following projection; M <= 4 weight-streaming path only) */
 } slb_gemm_args;
 int slb_gemm_bf16(const slb_gemm_args* args, void* stream);
 

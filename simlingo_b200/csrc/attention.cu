@@ -259,17 +259,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// small-Lq attention (decode / query append): block per (query, head, batch), 128 threads
+// small-Lq attention (decode / query append): block per (query, head, batch), 256 threads.
+//   phase 1: one thread per key computes q.k (16-byte loads of the key row)           -> scores in smem, block max
+//   phase 2: exp and block sum
+//   phase 3: each warp takes a contiguous chunk of keys; lanes own two output dims, so a key's V row is one coalesced
+//            128-byte warp load; 4 keys in flight; the 8 partial outputs are combined through smem
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int kSmallThreads = 1024, kSmallWarps = kSmallThreads / 32;  // one key per thread for the 545..700-key agent prompts
+__global__ void __launch_bounds__(kSmallThreads)
 attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
                   const uint8_t* __restrict__ key_valid, int key_valid_ld, bf16* __restrict__ out, long long ldo, int lq, int past,
                   int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev) {
   extern __shared__ float sm[];
   if (past_dev) past = *past_dev;  // position counter kept on the device: the same CUDA graph serves every decode step
-  float* qs = sm;            // 64
-  float* red = sm + 64;      // 8 + 128
-  float* sc = sm + 64 + 136; // lmax
+  float* qs = sm;                        // 64
+  float* red = sm + 64;                  // 2 * kSmallWarps
+  float* part = sm + 64 + 2 * kSmallWarps;                 // kSmallWarps * 64
+  float* sc = part + kSmallWarps * 64;   // lmax
   const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (hq / hkv);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -281,15 +287,17 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
   const bf16* vbase = vc + ((size_t)b * hkv + hk) * lmax * 64;
   const uint8_t* kv_ok = key_valid ? key_valid + (size_t)b * key_valid_ld : nullptr;
   float mx = -INFINITY;
-  for (int j = tid; j < nkeys; j += 128) {
+  for (int j = tid; j < nkeys; j += kSmallThreads) {
     float s = -INFINITY;
     if (!kv_ok || kv_ok[j]) {
       s = 0.f;
       const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)j * 64);
+      uint4 u[8];
+#pragma unroll
+      for (int v8 = 0; v8 < 8; ++v8) u[v8] = kr[v8];
 #pragma unroll
       for (int v8 = 0; v8 < 8; ++v8) {
-        uint4 u = kr[v8];
-        float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        float2 a = unpack_bf16(u[v8].x), bb = unpack_bf16(u[v8].y), c = unpack_bf16(u[v8].z), d = unpack_bf16(u[v8].w);
         const float* qq = qs + v8 * 8;
         s += a.x * qq[0] + a.y * qq[1] + bb.x * qq[2] + bb.y * qq[3] + c.x * qq[4] + c.y * qq[5] + d.x * qq[6] + d.y * qq[7];
       }
@@ -300,26 +308,61 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < kSmallWarps; ++w) mx = fmaxf(mx, red[w]);
   if (mx == -INFINITY) mx = 0.f;
   float sum = 0.f;
-  for (int j = tid; j < nkeys; j += 128) {
+  for (int j = tid; j < nkeys; j += kSmallThreads) {
     const float e = __expf(sc[j] - mx);
     sc[j] = e;
     sum += e;
   }
   sum = warp_sum(sum);
+  if (lane == 0) red[kSmallWarps + warp] = sum;
   __syncthreads();
-  if (lane == 0) red[4 + warp] = sum;
-  __syncthreads();
-  sum = red[4] + red[5] + red[6] + red[7];
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < kSmallWarps; ++w) sum += red[kSmallWarps + w];
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
-  const int d = tid & 63, part = tid >> 6;
-  float acc = 0.f;
-  for (int j = part; j < nkeys; j += 2) acc += sc[j] * __bfloat162float(vbase[(size_t)j * 64 + d]);
-  red[8 + tid] = acc;
+  const int chunk = (nkeys + kSmallWarps - 1) / kSmallWarps;
+  const int j0 = warp * chunk, j1 = min(nkeys, j0 + chunk);
+  float a0 = 0.f, a1 = 0.f;
+  const uint32_t* v32 = reinterpret_cast<const uint32_t*>(vbase) + lane;  // dims 2*lane, 2*lane+1 of every row (32 words per row)
+  int j = j0;
+  for (; j + 16 <= j1; j += 16) {  // 16 independent row loads in flight per lane
+    uint32_t wv[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) wv[u] = v32[(size_t)(j + u) * 32];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float2 f = unpack_bf16(wv[u]);
+      const float pj = sc[j + u];
+      a0 += pj * f.x;
+      a1 += pj * f.y;
+    }
+  }
+  for (; j + 4 <= j1; j += 4) {
+    uint32_t w0 = v32[(size_t)j * 32], w1 = v32[(size_t)(j + 1) * 32], w2 = v32[(size_t)(j + 2) * 32], w3 = v32[(size_t)(j + 3) * 32];
+    const float p0 = sc[j], p1 = sc[j + 1], p2 = sc[j + 2], p3 = sc[j + 3];
+    float2 f0 = unpack_bf16(w0), f1 = unpack_bf16(w1), f2 = unpack_bf16(w2), f3 = unpack_bf16(w3);
+    a0 += p0 * f0.x + p1 * f1.x + p2 * f2.x + p3 * f3.x;
+    a1 += p0 * f0.y + p1 * f1.y + p2 * f2.y + p3 * f3.y;
+  }
+  for (; j < j1; ++j) {
+    const float2 f = unpack_bf16(v32[(size_t)j * 32]);
+    a0 += sc[j] * f.x;
+    a1 += sc[j] * f.y;
+  }
+  part[warp * 64 + 2 * lane] = a0;
+  part[warp * 64 + 2 * lane + 1] = a1;
   __syncthreads();
-  if (tid < 64) out[((size_t)b * lq + i) * ldo + h * 64 + tid] = __float2bfloat16((red[8 + tid] + red[8 + 64 + tid]) * inv);
+  if (tid < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < kSmallWarps; ++w) o += part[w * 64 + tid];
+    out[((size_t)b * lq + i) * ldo + h * 64 + tid] = __float2bfloat16(o * inv);
+  }
 }
 
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int batch,
@@ -370,9 +413,9 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
   const float scale = 0.125f;
   if (lq <= 32 && lse == nullptr) {
     dim3 grid(lq, hq, batch);
-    const size_t smem = (64 + 136 + (size_t)lmax) * sizeof(float);
+    const size_t smem = (64 + 2 * kSmallWarps + kSmallWarps * 64 + (size_t)lmax) * sizeof(float);
     SLB_CHECK_ARG(smem <= 48 * 1024, "attn_gqa: lmax=%d too long for the small-Lq kernel", lmax);
-    attn_small_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const bf16*)q, ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid,
+    attn_small_kernel<<<grid, kSmallThreads, smem, (cudaStream_t)stream>>>((const bf16*)q, ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid,
                                                                key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq, hkv, scale, past_dev);
     SLB_LAUNCH_CHECK();
     return SLB_OK;

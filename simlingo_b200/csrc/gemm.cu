@@ -570,6 +570,8 @@ int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
 
 }  // namespace
 
+int slb_gemv_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out);  // gemv.cu
+
 extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SLB_CHECK_ARG(a != nullptr, "gemm: null args");
@@ -583,6 +585,11 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
     SLB_CHECK_ARG((a->N % 256) == 0, "gemm: swiglu needs N %% 256 == 0 (got %d)", a->N);
     SLB_CHECK_ARG(!a->bias && !a->scale_n && !a->residual && !a->act, "gemm: swiglu excludes other epilogue terms");
   }
+  if (a->block_n == 0) {  // 1..4 activation rows: weight-streaming GEMV on the CUDA cores (HBM-bound)
+    int rc = SLB_OK;
+    if (slb_gemv_try(a, stream, &rc)) return rc;
+  }
+  SLB_CHECK_ARG(a->rms_weight == nullptr, "gemm: the fused RMSNorm prologue exists only on the M <= 4 weight-streaming path");
   int bn = a->block_n;
   if (a->swiglu && bn != 2256 && bn != 256) bn = (a->M >= 4096) ? 2256 : 256;
   if (bn == 0) {

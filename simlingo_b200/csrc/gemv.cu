@@ -1,0 +1,209 @@
+// Weight-streaming GEMV for 1..4 activation rows (batch-1 decode: Qwen2 q|k|v, o, gate|up + SwiGLU, down, LM head).
+// HBM-bound: every weight row is read exactly once with 16-byte loads, the activation rows sit in shared memory,
+// products accumulate in fp32 on the CUDA cores, one warp owns 4 weight rows at a time (4 independent load streams
+// per lane), warp-shuffle reduction, same epilogue as the tcgen05 GEMM (alpha, bias, activation, column scale,
+// residual, fused SwiGLU over the 128-row interleaved gate|up layout, bf16 or fp32 output).
+// Algorithmic bytes = N*K*2 (weights) + M*K*2 + M*N*{2,4}; replaces slb_gemm_bf16's tensor-core path when M <= 4, where
+// a 128-row MMA tile would be > 96 % padding and the fixed per-launch cost of the TMA/TMEM pipeline dominates.
+#include "common.cuh"
+#include "../../include/simlingo_b200.h"
+
+namespace {
+
+struct GemvParams {
+  const bf16* A; long long lda;
+  const bf16* W; long long ldw;
+  void* out; long long ldo;
+  const bf16* bias; const bf16* scale_n;
+  const void* res; long long ldr;
+  int N, K;
+  float alpha;
+  int act, swiglu, out_fp32;
+  const bf16* rms_w; float rms_eps;
+};
+
+constexpr int kRows = 4;      // weight rows per warp step
+constexpr int kGemvWarps = 8;
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == SLB_ACT_GELU) return gelu_erf(v);
+  if (act == SLB_ACT_SILU) return silu(v);
+  if (act == SLB_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+template <int M>
+__global__ void __launch_bounds__(kGemvWarps * 32)
+gemv_bf16_kernel(GemvParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ float red[kGemvWarps];
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);  // [M][K]
+  const int K = p.K, kvec = K >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_groups = p.swiglu ? p.N / 4 : (p.N + kRows - 1) / kRows;  // groups of 4 weight rows
+
+  auto group_rows = [&](int g, int (&rows)[kRows]) {
+    if (!p.swiglu) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) rows[r] = min(g * kRows + r, p.N - 1);
+    } else {  // outputs j0, j0+1 need gate rows (256 t + w) and up rows (256 t + 128 + w)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int j = g * 2 + r, t = j >> 7, w = j & 127;
+        rows[r] = 256 * t + w;
+        rows[2 + r] = 256 * t + 128 + w;
+      }
+    }
+  };
+  // 4 k-steps x 4 rows = 16 independent 16-byte loads in flight per lane
+  auto load_w = [&](const int (&rows)[kRows], int v0, uint4 (&wv)[4][kRows]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = v0 + u * 32 + lane;
+      const int vc = v < kvec ? v : 0;
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) wv[u][r] = __ldg(reinterpret_cast<const uint4*>(p.W + (size_t)rows[r] * p.ldw) + vc);
+    }
+  };
+
+  int g = blockIdx.x * kGemvWarps + warp;
+  int rows[kRows];
+  uint4 wv[4][kRows];
+  if (g < n_groups) {  // the first weight loads do not depend on the activations: issue them before staging x
+    group_rows(g, rows);
+    load_w(rows, 0, wv);
+  }
+  for (int i = threadIdx.x; i < M * kvec; i += blockDim.x) {
+    const int m = i / kvec, v = i % kvec;
+    reinterpret_cast<uint4*>(xs)[i] = *reinterpret_cast<const uint4*>(p.A + (size_t)m * p.lda + v * 8);
+  }
+  __syncthreads();
+  if (p.rms_w) {
+    // fused Qwen2RMSNorm of the activation rows (same arithmetic as norm_fwd_kernel: x * rstd * w in fp32, one rounding)
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float s = 0.f;
+      for (int k = threadIdx.x; k < K; k += blockDim.x) { const float v = __bfloat162float(xs[(size_t)m * K + k]); s += v * v; }
+      s = warp_sum(s);
+      if (lane == 0) red[warp] = s;
+      __syncthreads();
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGemvWarps; ++w) t += red[w];
+      const float rstd = rsqrtf(t / K + p.rms_eps);
+      for (int k = threadIdx.x; k < K; k += blockDim.x)
+        xs[(size_t)m * K + k] = __float2bfloat16(__bfloat162float(xs[(size_t)m * K + k]) * rstd * __bfloat162float(p.rms_w[k]));
+      __syncthreads();
+    }
+  }
+  for (; g < n_groups; g += gridDim.x * kGemvWarps) {
+    float acc[kRows][M];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int m = 0; m < M; ++m) acc[r][m] = 0.f;
+    for (int v0 = 0; v0 < kvec; v0 += 4 * 32) {
+      if (v0 > 0) load_w(rows, v0, wv);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * 32 + lane;
+        if (v >= kvec) continue;
+        float xf[M][8];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * K)[v];
+          const float2 a = unpack_bf16(xv.x), b = unpack_bf16(xv.y), c = unpack_bf16(xv.z), d = unpack_bf16(xv.w);
+          xf[m][0] = a.x; xf[m][1] = a.y; xf[m][2] = b.x; xf[m][3] = b.y; xf[m][4] = c.x; xf[m][5] = c.y; xf[m][6] = d.x; xf[m][7] = d.y;
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const float2 a = unpack_bf16(wv[u][r].x), b = unpack_bf16(wv[u][r].y), c = unpack_bf16(wv[u][r].z), d = unpack_bf16(wv[u][r].w);
+          const float wf[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+          for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[r][m] = fmaf(wf[e], xf[m][e], acc[r][m]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int m = 0; m < M; ++m) acc[r][m] = warp_sum(acc[r][m]);
+    // lane r writes output r of the group
+    if (!p.swiglu) {
+      const int n = g * kRows + lane;
+      if (lane < kRows && n < p.N) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          float v = 0.f;
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) v = (lane == r) ? acc[r][m] : v;
+          v *= p.alpha;
+          if (p.bias) v += __bfloat162float(p.bias[n]);
+          v = act_apply(v, p.act);
+          if (p.scale_n) v *= __bfloat162float(p.scale_n[n]);
+          if (p.out_fp32) {
+            if (p.res) v += reinterpret_cast<const float*>(p.res)[(size_t)m * p.ldr + n];
+            reinterpret_cast<float*>(p.out)[(size_t)m * p.ldo + n] = v;
+          } else {
+            if (p.res) v += __bfloat162float(reinterpret_cast<const bf16*>(p.res)[(size_t)m * p.ldr + n]);
+            reinterpret_cast<bf16*>(p.out)[(size_t)m * p.ldo + n] = __float2bfloat16(v);
+          }
+        }
+      }
+    } else if (lane < 2) {
+      const int j = g * 2 + lane;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float gate = (lane == 0 ? acc[0][m] : acc[1][m]) * p.alpha, up = (lane == 0 ? acc[2][m] : acc[3][m]) * p.alpha;
+        const float v = silu(gate) * up;
+        if (p.out_fp32) reinterpret_cast<float*>(p.out)[(size_t)m * p.ldo + j] = v;
+        else reinterpret_cast<bf16*>(p.out)[(size_t)m * p.ldo + j] = __float2bfloat16(v);
+      }
+    }
+    const int gn = g + gridDim.x * kGemvWarps;
+    if (gn < n_groups) {
+      group_rows(gn, rows);
+      load_w(rows, 0, wv);
+    }
+  }
+}
+
+template <int M>
+int launch_gemv(const GemvParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)M * p.K * 2;
+  auto kern = gemv_bf16_kernel<M>;
+  if (smem > 48 * 1024) SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_groups = p.swiglu ? p.N / 4 : ceil_div(p.N, kRows);
+  int grid = ceil_div(n_groups, kGemvWarps);
+  const int cap = slb_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  kern<<<grid, kGemvWarps * 32, smem, stream>>>(p);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+}  // namespace
+
+// called by slb_gemm_bf16 for M <= 4 with K-major operands; returns 1 if it took the problem (rc in *rc_out)
+int slb_gemv_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
+  if (a->M > 4 || a->a_t || a->b_t || (a->K % 8) != 0 || (size_t)a->M * a->K * 2 > 200 * 1024) return 0;
+  if (a->swiglu && (a->N % 256) != 0) return 0;
+  if ((((uintptr_t)a->A) & 15) || (((uintptr_t)a->B) & 15) || (a->lda % 8) || (a->ldb % 8)) return 0;
+  GemvParams p;
+  p.A = (const bf16*)a->A; p.lda = a->lda;
+  p.W = (const bf16*)a->B; p.ldw = a->ldb;
+  p.out = a->out; p.ldo = a->ldo;
+  p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
+  p.res = a->residual; p.ldr = a->ldr;
+  p.N = a->N; p.K = a->K; p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
+  p.rms_w = (const bf16*)a->rms_weight; p.rms_eps = a->rms_eps;
+  switch (a->M) {
+    case 1: *rc_out = launch_gemv<1>(p, stream); break;
+    case 2: *rc_out = launch_gemv<2>(p, stream); break;
+    case 3: *rc_out = launch_gemv<3>(p, stream); break;
+    default: *rc_out = launch_gemv<4>(p, stream); break;
+  }
+  return 1;
+}

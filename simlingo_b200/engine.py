@@ -299,15 +299,22 @@ class Engine:
         qkv = torch.empty((M, s.qkv_dim), device=self.dev, dtype=torch.bfloat16)
         att = torch.empty((M, s.llm_heads * s.head_dim), device=self.dev, dtype=torch.bfloat16)
         act = torch.empty((M, s.llm_mlp), device=self.dev, dtype=torch.bfloat16)
+        fuse_norm = M <= 4  # decode: RMSNorm folded into the weight-streaming GEMVs (two launches fewer per layer)
         for i, ly in enumerate(self.llm_layers):
-            lib.rmsnorm(x, ly["ln1"], s.rms_eps, out=h)
-            lib.gemm(h, ly["qkv"], out=qkv, bias=ly["bqkv"])
+            if fuse_norm:
+                lib.gemm(x, ly["qkv"], out=qkv, bias=ly["bqkv"], rms_weight=ly["ln1"], rms_eps=s.rms_eps)
+            else:
+                lib.rmsnorm(x, ly["ln1"], s.rms_eps, out=h)
+                lib.gemm(h, ly["qkv"], out=qkv, bias=ly["bqkv"])
             lib.rope_kv_write(qkv, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, s.rope_theta, past_dev=past_dev)
             lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, key_valid=key_valid, out=att,
                          past_dev=past_dev)
             lib.gemm(att, ly["o"], out=x, residual=x)
-            lib.rmsnorm(x, ly["ln2"], s.rms_eps, out=h)
-            lib.gemm(h, ly["gu"], out=act, swiglu=True)
+            if fuse_norm:
+                lib.gemm(x, ly["gu"], out=act, swiglu=True, rms_weight=ly["ln2"], rms_eps=s.rms_eps)
+            else:
+                lib.rmsnorm(x, ly["ln2"], s.rms_eps, out=h)
+                lib.gemm(h, ly["gu"], out=act, swiglu=True)
             lib.gemm(act, ly["d"], out=x, residual=x)
             if collect is not None:
                 collect.append(x.clone())
@@ -322,6 +329,12 @@ class Engine:
         """fp32 logits of the given feature rows (lm_head is not LoRA-wrapped)."""
         self.launches += 1
         return lib.gemm(feats, self._w(LLM_PREFIX + "lm_head.weight"), out_fp32=True)
+
+    def logits_from_residual(self, x: Tensor) -> Tensor:
+        """final RMSNorm + LM head on <= 4 residual-stream rows in one weight-streaming launch (decode)."""
+        self.launches += 1
+        return lib.gemm(x, self._w(LLM_PREFIX + "lm_head.weight"), out_fp32=True, rms_weight=self._w(LLM_PREFIX + "model.norm.weight"),
+                        rms_eps=self.spec.rms_eps)
 
     def heads(self, feats30: Tensor, batch: int, ld_batch: int) -> Tuple[Tensor, Tensor]:
         self.launches += 2
@@ -348,8 +361,8 @@ class Engine:
             emb_w = self._w(LLM_PREFIX + "model.embed_tokens.weight")
             lm_cap = rec["cache"][0].shape[3]
 
-            def sample(last):
-                lg = self.logits(last)
+            def sample(last, residual=False):
+                lg = self.logits_from_residual(last) if residual else self.logits(last)
                 lib.argmax(lg, out_idx=rec["nxt"])
                 self.launches += 1
                 idx = rec["step"].view(1, 1).expand(B, 1)
@@ -371,7 +384,10 @@ class Engine:
                 e = lib.gather_rows(emb_w, rec["nxt"])
                 x = self.llm_chunk(e, B, 1, lm_cap - 1, rec["cache"], None, past_dev=rec["pos"])
                 rec["pos"].add_(1)
-                sample(self.final_norm(x))
+                if B <= 4:
+                    sample(x, residual=True)
+                else:
+                    sample(self.final_norm(x))
 
             def queries():
                 e = lib.gather_rows(emb_w, rec["nxt"])

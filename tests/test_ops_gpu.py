@@ -113,6 +113,37 @@ def test_gemm_swiglu(lib):
     assert relerr(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("M", [1, 2, 3, 4])
+def test_gemv_small_m(lib, M):
+    """M <= 4 takes the weight-streaming GEMV (decode path); same epilogue contract as the tensor-core GEMM."""
+    K, N, I = 896, 1152, 4864
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
+    bias, ls, res = rnd(N, seed=3), rnd(N, seed=4, scale=0.2), rnd(M, N, seed=5)
+    acc = a.float() @ b.float().t()
+    assert relerr(lib.gemm(a, b), acc) < 1e-2
+    assert relerr(lib.gemm(a, b, bias=bias, act=lib.ACT_GELU), F.gelu(acc + bias.float())) < 1e-2
+    assert relerr(lib.gemm(a, b, bias=bias, scale_n=ls, residual=res, alpha=0.5), res.float() + ls.float() * (0.5 * acc + bias.float())) < 1e-2
+    assert relerr(lib.gemm(a, b, out_fp32=True), acc) < 1e-5
+    # forced tensor-core path agrees
+    assert relerr(lib.gemm(a, b, block_n=128), acc) < 1e-2
+    # long K (down_proj), in-place residual, strided A (a slice of a wider buffer)
+    wide = rnd(M, I + 64, seed=6)
+    a2, w2 = wide[:, :I], rnd(K, I, seed=7, scale=0.05)
+    x = rnd(M, K, seed=8)
+    ref = x.float() + a2.float() @ w2.float().t()
+    assert relerr(lib.gemm(a2, w2, out=x, residual=x), ref) < 1e-2
+    # fused SwiGLU over the interleaved gate|up layout
+    wg, wu = rnd(I, K, seed=9, scale=0.05), rnd(I, K, seed=10, scale=0.05)
+    w = torch.stack([wg.view(I // 128, 128, K), wu.view(I // 128, 128, K)], dim=1).reshape(2 * I, K).contiguous()
+    out = lib.gemm(a, w, swiglu=True)
+    assert out.shape == (M, I)
+    assert relerr(out, F.silu(a.float() @ wg.float().t()) * (a.float() @ wu.float().t())) < 1e-2
+    # odd N (LM head), fp32 logits
+    V = 151655 if M == 1 else 4099
+    wv = rnd(V, K, seed=11, scale=0.05)
+    assert relerr(lib.gemm(a, wv, out_fp32=True), a.float() @ wv.float().t()) < 1e-5
+
+
 def test_gemm_lm_head_odd_vocab(lib):
     """N = 151655 (odd): fp32 logits with an unaligned row stride."""
     M, K, N = 3, 896, 151655
