@@ -51,6 +51,9 @@ typedef struct {
   int32_t block_n;                /* 0 = auto, else 128 or 256 */
   const void* rms_weight;         /* bf16 [K] or NULL: A rows are RMS-normalised on the fly, A' = A * rsqrt(mean(A^2) + rms_eps) * w */
   float rms_eps;                  /*   (Qwen2RMSNorm fused into the following projection; M <= 4 weight-streaming path only) */
+  void* aux; int64_t ld_aux;      /* bf16 [M,N] or NULL.  aux_mode 1: the pre-activation alpha*acc + bias is also stored there (training
+                                   *   forward of fc1: GELU input kept for backward); 2: v *= gelu'(aux[m,n]) (fc2 dgrad -> d pre-GELU) */
+  int32_t aux_mode;
 } slb_gemm_args;
 int slb_gemm_bf16(const slb_gemm_args* args, void* stream);
 

@@ -468,26 +468,31 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
   }
 }
 
-// CLS query row: one block per (tile, head), 128 threads, all n_tokens keys.
-__global__ void __launch_bounds__(128)
+// CLS query row: one block per (tile, head), 1024 threads: one key per thread for the scores, then each warp reduces a
+// contiguous chunk of keys with lanes owning two output dims (a V row = one coalesced 128-byte warp load, 16 in flight).
+constexpr int kClsThreads = 1024, kClsWarps = kClsThreads / 32;
+__global__ void __launch_bounds__(kClsThreads)
 attn_vit_cls_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int n_tokens, int heads, float scale) {
   extern __shared__ float sm[];
-  float* qs = sm;             // 64
-  float* red = sm + 64;       // 8 + 128
-  float* sc = sm + 64 + 136;  // n_tokens
+  float* qs = sm;                          // 64
+  float* red = sm + 64;                    // 2 * kClsWarps
+  float* part = sm + 64 + 2 * kClsWarps;   // kClsWarps * 64
+  float* sc = part + kClsWarps * 64;       // n_tokens
   const int h = blockIdx.x, t = blockIdx.y;
   const int C = heads * HD, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bf16* base = qkv + (size_t)t * n_tokens * 3 * C;
   if (tid < 64) qs[tid] = __bfloat162float(base[h * HD + tid]) * scale;
   __syncthreads();
   float mx = -INFINITY;
-  for (int j = tid; j < n_tokens; j += 128) {
+  for (int j = tid; j < n_tokens; j += kClsThreads) {
     const uint4* kr = reinterpret_cast<const uint4*>(base + (size_t)j * 3 * C + C + h * HD);
+    uint4 u[8];
+#pragma unroll
+    for (int v8 = 0; v8 < 8; ++v8) u[v8] = kr[v8];
     float s = 0.f;
 #pragma unroll
     for (int v8 = 0; v8 < 8; ++v8) {
-      const uint4 u = kr[v8];
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      const float2 a = unpack_bf16(u[v8].x), b = unpack_bf16(u[v8].y), c = unpack_bf16(u[v8].z), d = unpack_bf16(u[v8].w);
       const float* qq = qs + v8 * 8;
       s += a.x * qq[0] + a.y * qq[1] + b.x * qq[2] + b.y * qq[3] + c.x * qq[4] + c.y * qq[5] + d.x * qq[6] + d.y * qq[7];
     }
@@ -497,23 +502,53 @@ attn_vit_cls_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < kClsWarps; ++w) mx = fmaxf(mx, red[w]);
   float sum = 0.f;
-  for (int j = tid; j < n_tokens; j += 128) {
+  for (int j = tid; j < n_tokens; j += kClsThreads) {
     const float e = __expf(sc[j] - mx);
     sc[j] = e;
     sum += e;
   }
   sum = warp_sum(sum);
-  if (lane == 0) red[4 + warp] = sum;
+  if (lane == 0) red[kClsWarps + warp] = sum;
   __syncthreads();
-  sum = red[4] + red[5] + red[6] + red[7];
-  const int d = tid & 63, part = tid >> 6;
-  float acc = 0.f;
-  for (int j = part; j < n_tokens; j += 2) acc += sc[j] * __bfloat162float(base[(size_t)j * 3 * C + 2 * C + h * HD + d]);
-  red[8 + tid] = acc;
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < kClsWarps; ++w) sum += red[kClsWarps + w];
+  const int chunk = (n_tokens + kClsWarps - 1) / kClsWarps;
+  const int j0 = warp * chunk, j1 = min(n_tokens, j0 + chunk);
+  const size_t rs = (size_t)3 * C / 2;  // V row stride in 32-bit words
+  const uint32_t* v32 = reinterpret_cast<const uint32_t*>(base + 2 * C + h * HD) + lane;  // dims 2*lane, 2*lane+1
+  float a0 = 0.f, a1 = 0.f;
+  int j = j0;
+  for (; j + 16 <= j1; j += 16) {
+    uint32_t wv[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) wv[u] = v32[(size_t)(j + u) * rs];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float2 f = unpack_bf16(wv[u]);
+      const float pj = sc[j + u];
+      a0 += pj * f.x;
+      a1 += pj * f.y;
+    }
+  }
+  for (; j < j1; ++j) {
+    const float2 f = unpack_bf16(v32[(size_t)j * rs]);
+    a0 += sc[j] * f.x;
+    a1 += sc[j] * f.y;
+  }
+  part[warp * 64 + 2 * lane] = a0;
+  part[warp * 64 + 2 * lane + 1] = a1;
   __syncthreads();
-  if (tid < 64) out[(size_t)t * n_tokens * C + h * HD + tid] = __float2bfloat16((red[8 + tid] + red[8 + 64 + tid]) / sum);
+  if (tid < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < kClsWarps; ++w) o += part[w * 64 + tid];
+    out[(size_t)t * n_tokens * C + h * HD + tid] = __float2bfloat16(o / sum);
+  }
   if (tid == 0 && lse) lse[((size_t)t * heads + h) * n_tokens] = mx + logf(sum);
 }
 
@@ -562,8 +597,8 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
     default: e = launch(attn_vit2_kernel<0>); break;
   }
   if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_vit2 launch: %s", cudaGetErrorString(e)); return 1; }
-  const size_t smem = (64 + 136 + (size_t)n_tokens) * sizeof(float);
-  attn_vit_cls_kernel<<<dim3(heads, tiles), 128, smem, stream>>>((const bf16*)qkv, (bf16*)out, lse, n_tokens, heads, 0.125f);
+  const size_t smem = (64 + 2 * kClsWarps + kClsWarps * 64 + (size_t)n_tokens) * sizeof(float);
+  attn_vit_cls_kernel<<<dim3(heads, tiles), kClsThreads, smem, stream>>>((const bf16*)qkv, (bf16*)out, lse, n_tokens, heads, 0.125f);
   e = cudaGetLastError();
   if (e != cudaSuccess) *rc_out = slb_fail(SLB_ECUDA, "attn_vit_cls launch: %s", cudaGetErrorString(e));
   return 1;

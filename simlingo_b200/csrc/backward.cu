@@ -109,50 +109,59 @@ norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const b
 }
 
 // pixel-shuffle + LayerNorm(4096) backward: dy [T*256, 4096] -> dx scattered into the ViT stream [T*1025, 1024]
-// (CLS rows receive zero), dw/db accumulated with atomics.
+// (CLS rows receive zero).  One warp per row, grid-strided; dw / db partials are accumulated per block in shared memory
+// ([e][vec] layout: conflict-free across lanes) and flushed with one global atomic per column per block.
 __global__ void __launch_bounds__(kWarps * 32)
 pixel_shuffle_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                             const float* __restrict__ mean, const float* __restrict__ rstd, bf16* __restrict__ dx,
                             float* __restrict__ dw, float* __restrict__ db, int tiles) {
   constexpr int C = 1024, G = 32, G2 = 16, NT = 1025, COLS = 4096;
-  const int row = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  __shared__ float s_dw[COLS], s_db[COLS];
+  for (int i = threadIdx.x; i < COLS; i += blockDim.x) { s_dw[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  if (row >= tiles * 256) return;
-  const int t = row / 256, ij = row % 256, i = ij / G2, j = ij % G2;
-  const float mu = mean[row], rs = rstd[row];
-  float s1 = 0.f, s2 = 0.f;
-  // pass 1: reductions (values re-read in pass 2: the 4096-wide row does not fit in registers twice)
-  for (int vi = lane; vi < 512; vi += 32) {
-    const int q = vi >> 7, within = vi & 127;
-    const int src_tok = (2 * i + (q >> 1)) * G + (2 * j + (q & 1));
-    float dyv[8], xv[8], wv[8];
-    load8(dy + (size_t)row * COLS + vi * 8, dyv);
-    load8(x + ((size_t)t * NT + 1 + src_tok) * C + within * 8, xv);
-    load8(w + vi * 8, wv);
+  for (int row = blockIdx.x * kWarps + (threadIdx.x >> 5); row < tiles * 256; row += gridDim.x * kWarps) {
+    const int t = row / 256, ij = row % 256, i = ij / G2, j = ij % G2;
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    // pass 1: reductions (values re-read in pass 2: the 4096-wide row does not fit in registers twice)
+    for (int vi = lane; vi < 512; vi += 32) {
+      const int q = vi >> 7, within = vi & 127;
+      const int src_tok = (2 * i + (q >> 1)) * G + (2 * j + (q & 1));
+      float dyv[8], xv[8], wv[8];
+      load8(dy + (size_t)row * COLS + vi * 8, dyv);
+      load8(x + ((size_t)t * NT + 1 + src_tok) * C + within * 8, xv);
+      load8(w + vi * 8, wv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xh = (xv[e] - mu) * rs, g = dyv[e] * wv[e];
-      s1 += g;
-      s2 += g * xh;
-      atomicAdd(dw + vi * 8 + e, dyv[e] * xh);
-      atomicAdd(db + vi * 8 + e, dyv[e]);
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xv[e] - mu) * rs, g = dyv[e] * wv[e];
+        s1 += g;
+        s2 += g * xh;
+        atomicAdd(&s_dw[e * 512 + vi], dyv[e] * xh);
+        atomicAdd(&s_db[e * 512 + vi], dyv[e]);
+      }
+    }
+    s1 = warp_sum(s1) / COLS;
+    s2 = warp_sum(s2) / COLS;
+    for (int vi = lane; vi < 512; vi += 32) {
+      const int q = vi >> 7, within = vi & 127;
+      const int src_tok = (2 * i + (q >> 1)) * G + (2 * j + (q & 1));
+      float dyv[8], xv[8], wv[8], o[8];
+      load8(dy + (size_t)row * COLS + vi * 8, dyv);
+      load8(x + ((size_t)t * NT + 1 + src_tok) * C + within * 8, xv);
+      load8(w + vi * 8, wv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rs * (dyv[e] * wv[e] - s1 - (xv[e] - mu) * rs * s2);
+      store8(dx + ((size_t)t * NT + 1 + src_tok) * C + within * 8, o);
+    }
+    if (ij == 0) {  // zero the CLS row gradient of this tile
+      for (int vi = lane; vi < 128; vi += 32) *reinterpret_cast<uint4*>(dx + (size_t)t * NT * C + vi * 8) = make_uint4(0, 0, 0, 0);
     }
   }
-  s1 = warp_sum(s1) / COLS;
-  s2 = warp_sum(s2) / COLS;
-  for (int vi = lane; vi < 512; vi += 32) {
-    const int q = vi >> 7, within = vi & 127;
-    const int src_tok = (2 * i + (q >> 1)) * G + (2 * j + (q & 1));
-    float dyv[8], xv[8], wv[8], o[8];
-    load8(dy + (size_t)row * COLS + vi * 8, dyv);
-    load8(x + ((size_t)t * NT + 1 + src_tok) * C + within * 8, xv);
-    load8(w + vi * 8, wv);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = rs * (dyv[e] * wv[e] - s1 - (xv[e] - mu) * rs * s2);
-    store8(dx + ((size_t)t * NT + 1 + src_tok) * C + within * 8, o);
-  }
-  if (ij == 0) {  // zero the CLS row gradient of this tile
-    for (int vi = lane; vi < 128; vi += 32) *reinterpret_cast<uint4*>(dx + (size_t)t * NT * C + vi * 8) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = threadIdx.x; i < COLS; i += blockDim.x) {
+    atomicAdd(dw + i, s_dw[(i & 7) * 512 + (i >> 3)]);
+    atomicAdd(db + i, s_db[(i & 7) * 512 + (i >> 3)]);
   }
 }
 
@@ -442,7 +451,7 @@ extern "C" int slb_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
 extern "C" int slb_pixel_shuffle_ln_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
                                         float* dw_accum, float* db_accum, int tiles, void* stream) {
   SLB_CHECK_ARG(tiles > 0 && dw_accum && db_accum, "pixel_shuffle_ln_bwd: bad args");
-  pixel_shuffle_ln_bwd_kernel<<<ceil_div(tiles * 256, kWarps), kWarps * 32, 0, ST(stream)>>>(
+  pixel_shuffle_ln_bwd_kernel<<<min(ceil_div(tiles * 256, kWarps), slb_num_sms() * 2), kWarps * 32, 0, ST(stream)>>>(
       (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw_accum, db_accum, tiles);
   SLB_LAUNCH_CHECK();
   return SLB_OK;

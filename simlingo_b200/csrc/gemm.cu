@@ -31,6 +31,9 @@ struct EpiParams {
   int swiglu;
   int out_fp32;
   int num_m, num_n;
+  bf16* aux;        // optional second operand of the epilogue, bf16 [M, N] with row stride ld_aux
+  long long ld_aux;
+  int aux_mode;     // 1: store the pre-activation (alpha*acc + bias) there; 2: multiply by gelu'(aux) (fc2 dgrad -> d pre-GELU)
 };
 
 template <int BN>
@@ -149,6 +152,33 @@ __device__ __forceinline__ void load32_bf16(const bf16* p, int col0, int n, floa
   }
 }
 
+__device__ __forceinline__ void aux_store32(const EpiParams& p, int row, int col0, const float (&v)[32], int n) {
+  bf16* o = p.aux + (long long)row * p.ld_aux + col0;
+  if (((p.ld_aux & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && (col0 + 32 <= n)) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+      u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+      reinterpret_cast<uint4*>(o)[i] = u;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col0 + i < n) o[i] = __float2bfloat16(v[i]);
+  }
+}
+__device__ __forceinline__ void aux_gelu_grad32(const EpiParams& p, int row, int col0, float (&v)[32], int n) {
+  float a[32];
+  load32_bf16(p.aux + (long long)row * p.ld_aux, col0, n, a);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float cdf = 0.5f * (1.0f + erff(a[i] * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * a[i] * a[i]);
+    v[i] *= cdf + a[i] * pdf;
+  }
+}
+
 // Epilogue of one accumulator tile for one thread (= one output row), 32-column chunks [c_begin, c_end):
 // TMEM -> registers -> fused epilogue -> global.  Two warps share a TMEM lane quadrant and split the chunks.
 template <int BN>
@@ -173,6 +203,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += b[i];
       }
+      if (p.aux_mode == 1 && row_ok) aux_store32(p, row, col0, v, p.N);
+      if (p.aux_mode == 2 && row_ok) aux_gelu_grad32(p, row, col0, v, p.N);
       if (p.act == SLB_ACT_GELU) {  // activation switch hoisted out of the per-element loop
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
@@ -367,6 +399,7 @@ int launch_gemm(const slb_gemm_args* a, cudaStream_t stream) {
   p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
   p.res = a->residual; p.ldr = a->ldr;
   p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
+  p.aux = (bf16*)a->aux; p.ld_aux = a->ld_aux; p.aux_mode = a->aux ? a->aux_mode : 0;
   p.num_m = ceil_div(a->M, BM);
   p.num_n = ceil_div(a->N, BN);
   auto kern = gemm_bf16_kernel<BN, TA, TB>;
@@ -552,6 +585,7 @@ int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
   p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
   p.res = a->residual; p.ldr = a->ldr;
   p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
+  p.aux = (bf16*)a->aux; p.ld_aux = a->ld_aux; p.aux_mode = a->aux ? a->aux_mode : 0;
   p.num_m = ceil_div(a->M, 2 * BM);
   p.num_n = ceil_div(a->N, BN);
   auto kern = gemm2_bf16_kernel<BN>;
@@ -585,7 +619,8 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
     SLB_CHECK_ARG((a->N % 256) == 0, "gemm: swiglu needs N %% 256 == 0 (got %d)", a->N);
     SLB_CHECK_ARG(!a->bias && !a->scale_n && !a->residual && !a->act, "gemm: swiglu excludes other epilogue terms");
   }
-  if (a->block_n == 0) {  // 1..4 activation rows: weight-streaming GEMV on the CUDA cores (HBM-bound)
+  SLB_CHECK_ARG(!a->aux || (!a->swiglu && (a->aux_mode == 1 || a->aux_mode == 2)), "gemm: aux_mode must be 1 or 2 (no swiglu)");
+  if (a->block_n == 0 && !a->aux) {  // 1..4 activation rows: weight-streaming GEMV on the CUDA cores (HBM-bound)
     int rc = SLB_OK;
     if (slb_gemv_try(a, stream, &rc)) return rc;
   }

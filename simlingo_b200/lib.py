@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float), ("act", C.c_int32), ("swiglu", C.c_int32), ("out_fp32", C.c_int32),
         ("a_t", C.c_int32), ("b_t", C.c_int32), ("block_n", C.c_int32),
         ("rms_weight", C.c_void_p), ("rms_eps", C.c_float),
+        ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("aux_mode", C.c_int32),
     ]
 
 
@@ -92,7 +93,8 @@ def _bf16(*ts):
 # ------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, scale_n=None,
          residual=None, alpha: float = 1.0, act: int = ACT_NONE, swiglu: bool = False, out_fp32: bool = False,
-         a_t: bool = False, b_t: bool = False, block_n: int = 0, rms_weight=None, rms_eps: float = 0.0) -> torch.Tensor:
+         a_t: bool = False, b_t: bool = False, block_n: int = 0, rms_weight=None, rms_eps: float = 0.0, aux=None,
+         aux_mode: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * A @ B^T).  A: [M,K] (or [K,M] if a_t), B: [N,K] (or [K,N] if b_t);
     2-D, unit inner stride, arbitrary (multiple-of-8) row stride."""
     _bf16(a, b, bias, scale_n)
@@ -111,7 +113,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
                  None if bias is None else bias.data_ptr(), None if scale_n is None else scale_n.data_ptr(),
                  None if residual is None else residual.data_ptr(), 0 if residual is None else residual.stride(0),
                  alpha, act, int(swiglu), int(out_fp32), int(a_t), int(b_t), block_n,
-                 None if rms_weight is None else rms_weight.data_ptr(), rms_eps)
+                 None if rms_weight is None else rms_weight.data_ptr(), rms_eps,
+                 None if aux is None else aux.data_ptr(), 0 if aux is None else aux.stride(0), aux_mode)
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16 and aux.shape == (M, n_out) and aux.stride(1) == 1
     _check(load().slb_gemm_bf16(C.byref(g), _stream()), "gemm_bf16")
     return out
 

@@ -503,8 +503,8 @@ class TrainEngine:
             p1 = lib.gemm(att, w(p + "attn.proj.weight"), bias=w(p + "attn.proj.bias"))
             xm = lib.scale_cols_add(p1, w(p + "ls1"), x)
             h2 = lib.layernorm(xm, w(p + "norm2.weight"), w(p + "norm2.bias"), s.vit_eps, stats=st2)
-            fpre = lib.gemm(h2, w(p + "mlp.fc1.weight"), bias=w(p + "mlp.fc1.bias"))
-            fact = lib.gelu_fwd(fpre)
+            fpre = torch.empty((M, s.vit_mlp), device=dev, dtype=bf)   # GELU input, kept for backward (second epilogue output)
+            fact = lib.gemm(h2, w(p + "mlp.fc1.weight"), bias=w(p + "mlp.fc1.bias"), act=lib.ACT_GELU, aux=fpre, aux_mode=1)
             p2 = lib.gemm(fact, w(p + "mlp.fc2.weight"), bias=w(p + "mlp.fc2.bias"))
             xo = lib.scale_cols_add(p2, w(p + "ls2"), xm)
             layers.append(dict(x=x, st1=st1, h1=h1, qkv=qkv, lse=lse, att=att, p1=p1, xm=xm, st2=st2, h2=h2, fpre=fpre, fact=fact, p2=p2))
@@ -512,8 +512,8 @@ class TrainEngine:
         # projector: drop CLS + pixel shuffle + LN(4096) -> Linear -> GELU -> Linear
         stp = (f32(T * s.tokens_per_tile), f32(T * s.tokens_per_tile))
         y0 = lib.pixel_shuffle_ln(x, w(MLP1_PREFIX + "0.weight"), w(MLP1_PREFIX + "0.bias"), T, s.proj_eps, stats=stp)
-        y1p = lib.gemm(y0, w(MLP1_PREFIX + "1.weight"), bias=w(MLP1_PREFIX + "1.bias"))
-        y1 = lib.gelu_fwd(y1p)
+        y1p = torch.empty((T * s.tokens_per_tile, s.llm_hidden), device=dev, dtype=bf)
+        y1 = lib.gemm(y0, w(MLP1_PREFIX + "1.weight"), bias=w(MLP1_PREFIX + "1.bias"), act=lib.ACT_GELU, aux=y1p, aux_mode=1)
         y2 = lib.gemm(y1, w(MLP1_PREFIX + "3.weight"), bias=w(MLP1_PREFIX + "3.bias"))
         saved = dict(T=T, cols=cols, layers=layers, xv=x, stp=stp, y0=y0, y1p=y1p, y1=y1)
         return y2, saved
@@ -525,14 +525,13 @@ class TrainEngine:
         # ---- projector ----
         lib.col_reduce(dy2, self._acc(MLP1_PREFIX + "3.bias"))
         self._wgrad(dy2, sv["y1"], MLP1_PREFIX + "3.weight")
-        dy1 = lib.gemm(dy2, w(MLP1_PREFIX + "3.weight"), b_t=True)
-        dy1p = lib.gelu_bwd(sv["y1p"], dy1)
+        dy1p = lib.gemm(dy2, w(MLP1_PREFIX + "3.weight"), b_t=True, aux=sv["y1p"], aux_mode=2)
         lib.col_reduce(dy1p, self._acc(MLP1_PREFIX + "1.bias"))
         self._wgrad(dy1p, sv["y0"], MLP1_PREFIX + "1.weight")
         dy0 = lib.gemm(dy1p, w(MLP1_PREFIX + "1.weight"), b_t=True)
         dx = lib.pixel_shuffle_ln_bwd(dy0, sv["xv"], w(MLP1_PREFIX + "0.weight"), sv["stp"][0], sv["stp"][1],
                                       self._acc(MLP1_PREFIX + "0.weight"), self._acc(MLP1_PREFIX + "0.bias"), T)
-        del dy0, dy1, dy1p
+        del dy0, dy1p
         st.flush_group("mlp1")
         # ---- encoder layers ----
         for i in reversed(range(s.vit_layers)):
@@ -544,8 +543,7 @@ class TrainEngine:
             dp2 = lib.scale_cols(dx, w(p + "ls2"))
             lib.col_reduce(dp2, self._acc(p + "mlp.fc2.bias"))
             self._wgrad(dp2, a["fact"], p + "mlp.fc2.weight")
-            dfact = lib.gemm(dp2, w(p + "mlp.fc2.weight"), b_t=True)
-            dfpre = lib.gelu_bwd(a["fpre"], dfact, out=dfact)
+            dfpre = lib.gemm(dp2, w(p + "mlp.fc2.weight"), b_t=True, aux=a["fpre"], aux_mode=2)  # dgrad * gelu'(pre) in the epilogue
             lib.col_reduce(dfpre, self._acc(p + "mlp.fc1.bias"))
             self._wgrad(dfpre, a["h2"], p + "mlp.fc1.weight")
             dh2 = lib.gemm(dfpre, w(p + "mlp.fc1.weight"), b_t=True, out=dp2)

@@ -89,6 +89,21 @@ def test_gemm_epilogues(lib):
     assert relerr(out, acc + acc32) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(2050, 4096, 1024), (300, 896, 4096)])
+def test_gemm_aux_epilogues(lib, M, N, K):
+    """Training epilogues: fc1 forward also stores the GELU input; fc2 dgrad multiplies by gelu'(pre)."""
+    a, b, bias = rnd(M, K, seed=1, scale=0.5), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    pre_ref = a.float() @ b.float().t() + bias.float()
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out = lib.gemm(a, b, bias=bias, act=lib.ACT_GELU, aux=pre, aux_mode=1)
+    assert relerr(pre, pre_ref) < 1e-2 and relerr(out, F.gelu(pre_ref)) < 1e-2
+    dy, w2 = rnd(M, 256, seed=4), rnd(256, N, seed=5, scale=0.05)     # d act = dy @ W2  (W2 [out=256, in=N], b_t form)
+    got = lib.gemm(dy, w2, b_t=True, aux=pre, aux_mode=2)
+    pr = pre.float().requires_grad_()
+    F.gelu(pr).backward(dy.float() @ w2.float())
+    assert relerr(got, pr.grad) < 2e-2
+
+
 def test_gemm_strided_views(lib):
     """A as a column slice of a wider buffer (q part of the fused qkv), out as a slice."""
     M, K, N = 545, 896, 896
