@@ -13,7 +13,7 @@ namespace {
 
 constexpr int BQ = 128, BKV = 128, HD = 64;
 constexpr int ATT_THREADS = 192;
-constexpr int kMaxKvBlocks = 64;            // key-validity bitmasks in static smem: sequences up to 8192 keys
+constexpr int kMaxKvBlocks = 32;            // key-validity bitmasks in static smem (512 B: keeps two CTAs per SM): up to 4096 keys
 constexpr int kQBytes = BQ * HD * 2;        // 16 KB
 constexpr int kKVBytes = BKV * HD * 2;      // 16 KB
 constexpr int kPBytes = BQ * BKV * 2;       // 32 KB (two K-major halves of 64 columns)
@@ -22,7 +22,8 @@ constexpr int kSmemK = kSmemQ + kQBytes;            // 2 stages
 constexpr int kSmemV = kSmemK + 2 * kKVBytes;       // 2 stages
 constexpr int kSmemP = kSmemV + 2 * kKVBytes;
 constexpr int kSmemBar = kSmemP + kPBytes;
-constexpr int kSmemTotal = kSmemBar + 128;
+constexpr int kSmemMask = kSmemBar + 128;           // key-validity bitmasks, 16 B per key block
+constexpr int kSmemTotal = kSmemMask + kMaxKvBlocks * 16;
 constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)
 
 struct AttnParams {
@@ -139,7 +140,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)b * p.key_valid_ld : nullptr;
     // per key block, a 128-bit validity mask (inside the sequence and not padding), built once per CTA: the softmax
     // loops then test a register bit instead of loading key_valid per element, and unmasked blocks take the fast path
-    __shared__ uint32_t kmask[kMaxKvBlocks * 4];
+    uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + kSmemMask);
     for (int j = 0; j < nkv; ++j) {
       const int col = j * BKV + r;
       const bool ok = col < p.lkv && (!kvalid || kvalid[col] != 0);
@@ -370,6 +371,8 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   static bool attr_set = false;
   if (!attr_set) {
     SLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    // two CTAs per SM need the full 228 KB carve-out (2 x (112.6 KB + 1 KB reserved)); the default picks 132 KB = one CTA
+    SLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   dim3 grid(ceil_div(p.lq, BQ), p.hq, batch);
