@@ -366,6 +366,137 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
   }
 }
 
+// Batched decode: one block per (query, kv head, batch) serving all q heads of the GQA group, so a key / value row is
+// read once for the 7 heads that share it (the per-head kernel above re-reads it 7 times: 69 MB per layer at batch 32).
+constexpr int kGrpThreads = 512, kGrpWarps = kGrpThreads / 32, kMaxGroup = 8;
+__global__ void __launch_bounds__(kGrpThreads)
+attn_decode_group_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+                         const uint8_t* __restrict__ key_valid, int key_valid_ld, bf16* __restrict__ out, long long ldo, int lq, int past,
+                         int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev) {
+  extern __shared__ float sm[];
+  if (past_dev) past = *past_dev;
+  const int G = hq / hkv;
+  float* qs = sm;                                   // [G][64]
+  float* red = qs + kMaxGroup * 64;                 // [2][kGrpWarps][kMaxGroup]
+  float* part = red + 2 * kGrpWarps * kMaxGroup;    // [kGrpWarps][G][64]
+  float* sc = part + kGrpWarps * kMaxGroup * 64;    // [G][lmax]
+  const int i = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nkeys = past + i + 1;
+  for (int t = tid; t < G * 64; t += kGrpThreads)
+    qs[t] = __bfloat162float(q[((size_t)b * lq + i) * ldq + (hk * G + t / 64) * 64 + (t & 63)]) * scale;
+  __syncthreads();
+  const bf16* kbase = kc + ((size_t)b * hkv + hk) * lmax * 64;
+  const bf16* vbase = vc + ((size_t)b * hkv + hk) * lmax * 64;
+  const uint8_t* kv_ok = key_valid ? key_valid + (size_t)b * key_valid_ld : nullptr;
+  float mx[kMaxGroup];
+#pragma unroll
+  for (int h = 0; h < kMaxGroup; ++h) mx[h] = -INFINITY;
+  for (int j = tid; j < nkeys; j += kGrpThreads) {
+    const bool ok = !kv_ok || kv_ok[j];
+    float kf[64];
+    const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)j * 64);
+#pragma unroll
+    for (int v8 = 0; v8 < 8; ++v8) {
+      const uint4 u = kr[v8];
+      const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      kf[v8 * 8] = a.x; kf[v8 * 8 + 1] = a.y; kf[v8 * 8 + 2] = bb.x; kf[v8 * 8 + 3] = bb.y;
+      kf[v8 * 8 + 4] = c.x; kf[v8 * 8 + 5] = c.y; kf[v8 * 8 + 6] = d.x; kf[v8 * 8 + 7] = d.y;
+    }
+#pragma unroll
+    for (int h = 0; h < kMaxGroup; ++h) {
+      if (h < G) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) s += kf[e] * qs[h * 64 + e];
+        s = ok ? s : -INFINITY;
+        sc[(size_t)h * lmax + j] = s;
+        mx[h] = fmaxf(mx[h], s);
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < kMaxGroup; ++h) {
+    mx[h] = warp_max(mx[h]);
+    if (lane == 0) red[warp * kMaxGroup + h] = mx[h];
+  }
+  __syncthreads();
+  float sum[kMaxGroup];
+#pragma unroll
+  for (int h = 0; h < kMaxGroup; ++h) {
+    float m = red[h];
+    for (int w = 1; w < kGrpWarps; ++w) m = fmaxf(m, red[w * kMaxGroup + h]);
+    mx[h] = (m == -INFINITY) ? 0.f : m;
+    sum[h] = 0.f;
+  }
+  for (int j = tid; j < nkeys; j += kGrpThreads) {
+#pragma unroll
+    for (int h = 0; h < kMaxGroup; ++h) {
+      if (h < G) {
+        const float e = __expf(sc[(size_t)h * lmax + j] - mx[h]);
+        sc[(size_t)h * lmax + j] = e;
+        sum[h] += e;
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < kMaxGroup; ++h) {
+    sum[h] = warp_sum(sum[h]);
+    if (lane == 0) red[(kGrpWarps + warp) * kMaxGroup + h] = sum[h];
+  }
+  __syncthreads();
+  // weighted V: each warp a contiguous chunk of keys, lanes own dims (2 lane, 2 lane + 1), all heads of the group at once
+  const int chunk = (nkeys + kGrpWarps - 1) / kGrpWarps;
+  const int j0 = warp * chunk, j1 = min(nkeys, j0 + chunk);
+  const uint32_t* v32 = reinterpret_cast<const uint32_t*>(vbase) + lane;
+  float a0[kMaxGroup], a1[kMaxGroup];
+#pragma unroll
+  for (int h = 0; h < kMaxGroup; ++h) { a0[h] = 0.f; a1[h] = 0.f; }
+  int j = j0;
+  for (; j + 8 <= j1; j += 8) {
+    uint32_t wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) wv[u] = v32[(size_t)(j + u) * 32];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float2 f = unpack_bf16(wv[u]);
+#pragma unroll
+      for (int h = 0; h < kMaxGroup; ++h) {
+        if (h < G) {
+          const float pj = sc[(size_t)h * lmax + j + u];
+          a0[h] += pj * f.x;
+          a1[h] += pj * f.y;
+        }
+      }
+    }
+  }
+  for (; j < j1; ++j) {
+    const float2 f = unpack_bf16(v32[(size_t)j * 32]);
+#pragma unroll
+    for (int h = 0; h < kMaxGroup; ++h) {
+      if (h < G) {
+        const float pj = sc[(size_t)h * lmax + j];
+        a0[h] += pj * f.x;
+        a1[h] += pj * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < kMaxGroup; ++h) {
+    if (h < G) {
+      part[(warp * kMaxGroup + h) * 64 + 2 * lane] = a0[h];
+      part[(warp * kMaxGroup + h) * 64 + 2 * lane + 1] = a1[h];
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < G * 64; t += kGrpThreads) {
+    const int h = t / 64, d = t & 63;
+    float o = 0.f, sm_ = 0.f;
+    for (int w = 0; w < kGrpWarps; ++w) { o += part[(w * kMaxGroup + h) * 64 + d]; sm_ += red[(kGrpWarps + w) * kMaxGroup + h]; }
+    out[((size_t)b * lq + i) * ldo + (hk * G + h) * 64 + d] = __float2bfloat16(sm_ > 0.f ? o / sm_ : 0.f);
+  }
+}
+
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int batch,
                 cudaStream_t stream) {
   static bool attr_set = false;
@@ -414,6 +545,21 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
   SLB_CHECK_ARG((ldq % 8) == 0, "attn_gqa: ldq must be a multiple of 8");
   SLB_CHECK_ARG(past + lq <= kMaxKvBlocks * BKV, "attn_gqa: at most %d keys", kMaxKvBlocks * BKV);
   const float scale = 0.125f;
+  if (lq <= 32 && lse == nullptr && batch >= 4 && hq / hkv <= kMaxGroup) {
+    // batched decode / query append: one block per kv head serves its whole GQA group
+    const size_t smem = ((size_t)kMaxGroup * 64 + 2 * kGrpWarps * kMaxGroup + (size_t)kGrpWarps * kMaxGroup * 64 + (size_t)(hq / hkv) * lmax) * sizeof(float);
+    SLB_CHECK_ARG(smem <= 200 * 1024, "attn_gqa: lmax=%d too long for the grouped decode kernel", lmax);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      SLB_CUDA(cudaFuncSetAttribute(attn_decode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    attn_decode_group_kernel<<<dim3(lq, hkv, batch), kGrpThreads, smem, (cudaStream_t)stream>>>(
+        (const bf16*)q, ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax,
+        hq, hkv, scale, past_dev);
+    SLB_LAUNCH_CHECK();
+    return SLB_OK;
+  }
   if (lq <= 32 && lse == nullptr) {
     dim3 grid(lq, hq, batch);
     const size_t smem = (64 + 2 * kSmallWarps + kSmallWarps * 64 + (size_t)lmax) * sizeof(float);

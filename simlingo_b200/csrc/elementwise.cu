@@ -367,13 +367,31 @@ __device__ __forceinline__ float warp_dot_bf16(const bf16* __restrict__ wrow, co
   }
   return warp_sum(acc);
 }
-// y[j] = act(b[j] + W[j,:] . x) for j in [0, nout); all warps of the block cooperate; x, y in smem
+// y[j] = act(b[j] + W[j,:] . x) for j in [0, nout); all warps of the block cooperate; x, y in smem.  Each warp works on
+// four output rows at a time (four independent load streams) so the chain of dependent global-load latencies is
+// nout / (4 * warps) long instead of nout / warps.
 __device__ __forceinline__ void block_linear(const bf16* W, const bf16* bias, const float* x, float* y, int nin, int nout,
                                              int act) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int j = warp; j < nout; j += nw) {
-    float v = warp_dot_bf16(W + (size_t)j * nin, x, nin, lane);
-    if (lane == 0) {
+  const int nvec = nin >> 3;
+  for (int j0 = warp * 4; j0 < nout; j0 += nw * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int vi = lane; vi < nvec; vi += 32) {
+      float wv[4][8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) load8(W + (size_t)min(j0 + r, nout - 1) * nin + vi * 8, wv[r]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xv = x[vi * 8 + e];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] += wv[r][e] * xv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane < 4 && j0 + lane < nout) {
+      float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      const int j = j0 + lane;
       if (bias) v += __bfloat162float(bias[j]);
       if (act == SLB_ACT_SILU) v = silu(v);
       else if (act == SLB_ACT_RELU) v = fmaxf(v, 0.f);
@@ -384,7 +402,7 @@ __device__ __forceinline__ void block_linear(const bf16* W, const bf16* bias, co
 }
 
 // one block per (batch, query row): rows 0..19 -> route head, 20..29 -> speed head; writes pre-cumsum deltas
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 heads_kernel(const bf16* __restrict__ feats, long long ld_batch, slb_heads_weights w, float* __restrict__ delta) {
   __shared__ float x[896];
   __shared__ float h1[512];
@@ -420,7 +438,7 @@ __global__ void heads_cumsum_kernel(const float* __restrict__ delta, float* __re
 }
 
 // wp encoder: 2 -> 256 -> 512 -> 896 (ReLU); one block per point
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 wp_encoder_kernel(const float* __restrict__ coords, slb_wp_weights w, bf16* __restrict__ out) {
   __shared__ float h1[256];
   __shared__ float h2[512];
@@ -560,7 +578,7 @@ extern "C" int slb_argmax_f32(const float* logits, int64_t ld, int rows, int col
 extern "C" int slb_driving_heads(const void* feats, int64_t ld_batch, const slb_heads_weights* w, float* route, float* speed,
                                  float* delta_ws, int batch, void* stream) {
   SLB_CHECK_ARG(batch > 0 && w && delta_ws, "driving_heads: bad args");
-  heads_kernel<<<batch * 30, 256, 0, ST(stream)>>>((const bf16*)feats, ld_batch, *w, delta_ws);
+  heads_kernel<<<batch * 30, 1024, 0, ST(stream)>>>((const bf16*)feats, ld_batch, *w, delta_ws);
   SLB_LAUNCH_CHECK();
   heads_cumsum_kernel<<<ceil_div(batch * 2, 64), 64, 0, ST(stream)>>>(delta_ws, route, speed, batch);
   SLB_LAUNCH_CHECK();
@@ -569,7 +587,7 @@ extern "C" int slb_driving_heads(const void* feats, int64_t ld_batch, const slb_
 
 extern "C" int slb_wp_encoder(const float* coords, const slb_wp_weights* w, void* out, int n_points, void* stream) {
   SLB_CHECK_ARG(n_points > 0 && w, "wp_encoder: bad args");
-  wp_encoder_kernel<<<n_points, 256, 0, ST(stream)>>>(coords, *w, (bf16*)out);
+  wp_encoder_kernel<<<n_points, 1024, 0, ST(stream)>>>(coords, *w, (bf16*)out);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

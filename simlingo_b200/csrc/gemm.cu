@@ -604,7 +604,8 @@ int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
 
 }  // namespace
 
-int slb_gemv_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out);  // gemv.cu
+int slb_gemv_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out);    // gemv.cu
+int slb_skinny_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out);  // gemv.cu
 
 extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -623,6 +624,7 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
   if (a->block_n == 0 && !a->aux) {  // 1..4 activation rows: weight-streaming GEMV on the CUDA cores (HBM-bound)
     int rc = SLB_OK;
     if (slb_gemv_try(a, stream, &rc)) return rc;
+    if (slb_skinny_try(a, stream, &rc)) return rc;  // 5..32 rows (batched decode): mma.sync weight streaming
   }
   SLB_CHECK_ARG(a->rms_weight == nullptr, "gemm: the fused RMSNorm prologue exists only on the M <= 4 weight-streaming path");
   int bn = a->block_n;

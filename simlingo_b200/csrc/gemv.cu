@@ -207,3 +207,146 @@ int slb_gemv_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
   }
   return 1;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Skinny GEMM for 4 < M <= 32 activation rows (batched decode): weight-streaming on mma.sync.m16n8k16 (bf16, fp32 acc).
+// A 128-row tcgen05 tile would be >= 75 % padding here and the whole problem is HBM-bound on the weights, so the goal is
+// the same as for the GEMV: read every weight row once with 16-byte loads, many CTAs.  CTA = 8 warps = 16 weight rows
+// (two n8 tiles; for SwiGLU: 8 gate rows + their 8 up rows); the warps split K in interleaved 32-element chunks and
+// their partial tiles are summed through shared memory.  Within a chunk, lane (g = lane/4, q = lane%4) loads the 8
+// consecutive k values k0 + 8q .. 8q+7 of weight row g (one uint4) and of activation rows g, g+8 (+16, +24): a fixed
+// permutation of k applied to both operands, so the two MMAs of the chunk see consistent fragments without any shuffles.
+// Activations (<= 32 x K bf16) are read through L1.  Same epilogue contract as the GEMV.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int MT, int NT>  // 16-row activation tiles (M <= 16 * MT), n8 weight tiles per CTA (8 * NT weight rows)
+__global__ void __launch_bounds__(256)
+skinny_gemm_kernel(GemvParams p, int M) {
+  __shared__ float part[8][MT * 16][NT * 8 + 1];  // per-warp partial tiles (padded rows)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int tile = blockIdx.x;
+  // weight rows of the n8 tiles.  SwiGLU: tiles [0, NT/2) are gate rows, [NT/2, NT) the matching up rows
+  const uint4* wrow[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    int row;
+    if (!p.swiglu) {
+      row = min(tile * (8 * NT) + nt * 8 + g, p.N - 1);
+    } else {
+      const int j = tile * (4 * NT) + (nt % (NT / 2)) * 8 + g, t = j >> 7, w = j & 127;
+      row = 256 * t + (nt >= NT / 2 ? 128 : 0) + w;
+    }
+    wrow[nt] = reinterpret_cast<const uint4*>(p.W + (size_t)row * p.ldw) + q;
+  }
+  const uint4* arow[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    arow[mt][0] = reinterpret_cast<const uint4*>(p.A + (size_t)min(mt * 16 + g, M - 1) * p.lda) + q;
+    arow[mt][1] = reinterpret_cast<const uint4*>(p.A + (size_t)min(mt * 16 + 8 + g, M - 1) * p.lda) + q;
+  }
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+  const int nchunks = p.K >> 5;
+#pragma unroll(NT <= 2 ? 4 : 2)
+  for (int c = warp; c < nchunks; c += 8) {
+    uint4 bw[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) bw[nt] = __ldg(wrow[nt] + c * 4);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint4 lo = __ldg(arow[mt][0] + c * 4), hi = __ldg(arow[mt][1] + c * 4);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mma_bf16_16816(acc[mt][nt], lo.x, hi.x, lo.y, hi.y, bw[nt].x, bw[nt].y);
+        mma_bf16_16816(acc[mt][nt], lo.z, hi.z, lo.w, hi.w, bw[nt].z, bw[nt].w);
+      }
+    }
+  }
+  // C fragment: c0,c1 -> (row g, cols 2q, 2q+1), c2,c3 -> (row g+8, same cols)
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      part[warp][mt * 16 + g][nt * 8 + 2 * q] = acc[mt][nt][0];
+      part[warp][mt * 16 + g][nt * 8 + 2 * q + 1] = acc[mt][nt][1];
+      part[warp][mt * 16 + 8 + g][nt * 8 + 2 * q] = acc[mt][nt][2];
+      part[warp][mt * 16 + 8 + g][nt * 8 + 2 * q + 1] = acc[mt][nt][3];
+    }
+  __syncthreads();
+  if (!p.swiglu) {
+    for (int i = threadIdx.x; i < MT * 16 * NT * 8; i += blockDim.x) {
+      const int m = i / (NT * 8), c = i % (NT * 8), n = tile * (NT * 8) + c;
+      if (m >= M || n >= p.N) continue;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += part[w][m][c];
+      v *= p.alpha;
+      if (p.bias) v += __bfloat162float(p.bias[n]);
+      v = act_apply(v, p.act);
+      if (p.scale_n) v *= __bfloat162float(p.scale_n[n]);
+      if (p.out_fp32) {
+        if (p.res) v += reinterpret_cast<const float*>(p.res)[(size_t)m * p.ldr + n];
+        reinterpret_cast<float*>(p.out)[(size_t)m * p.ldo + n] = v;
+      } else {
+        if (p.res) v += __bfloat162float(reinterpret_cast<const bf16*>(p.res)[(size_t)m * p.ldr + n]);
+        reinterpret_cast<bf16*>(p.out)[(size_t)m * p.ldo + n] = __float2bfloat16(v);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < MT * 16 * NT * 4; i += blockDim.x) {
+      const int m = i / (NT * 4), c = i % (NT * 4), j = tile * (NT * 4) + c;
+      if (m >= M) continue;
+      float gate = 0.f, up = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { gate += part[w][m][c]; up += part[w][m][NT * 4 + c]; }
+      const float v = silu(gate * p.alpha) * (up * p.alpha);
+      if (p.out_fp32) reinterpret_cast<float*>(p.out)[(size_t)m * p.ldo + j] = v;
+      else reinterpret_cast<bf16*>(p.out)[(size_t)m * p.ldo + j] = __float2bfloat16(v);
+    }
+  }
+}
+
+}  // namespace
+
+// called by slb_gemm_bf16 for 4 < M <= 32 with K-major operands; returns 1 if it took the problem
+int slb_skinny_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
+  if (a->M <= 4 || a->M > 32 || a->a_t || a->b_t || (a->K % 32) != 0 || a->rms_weight || a->aux) return 0;
+  if (a->swiglu && (a->N % 256) != 0) return 0;
+  if ((((uintptr_t)a->A) & 15) || (((uintptr_t)a->B) & 15) || (a->lda % 8) || (a->ldb % 8)) return 0;
+  GemvParams p;
+  p.A = (const bf16*)a->A; p.lda = a->lda;
+  p.W = (const bf16*)a->B; p.ldw = a->ldb;
+  p.out = a->out; p.ldo = a->ldo;
+  p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
+  p.res = a->residual; p.ldr = a->ldr;
+  p.N = a->N; p.K = a->K; p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
+  p.rms_w = nullptr; p.rms_eps = 0.f;
+  // 32 weight rows per CTA (the activations are re-read from L2 by every CTA: wider tiles halve that traffic); 16 for the
+  // small projections so that they still spread over > 50 CTAs
+  const bool wide = a->N >= 4096;
+  const int rows_per_cta = wide ? 32 : 16;
+  const int grid = a->swiglu ? a->N / rows_per_cta : ceil_div(a->N, rows_per_cta);
+  if (a->M <= 16) {
+    if (wide) skinny_gemm_kernel<1, 4><<<grid, 256, 0, stream>>>(p, a->M);
+    else skinny_gemm_kernel<1, 2><<<grid, 256, 0, stream>>>(p, a->M);
+  } else {
+    if (wide) skinny_gemm_kernel<2, 4><<<grid, 256, 0, stream>>>(p, a->M);
+    else skinny_gemm_kernel<2, 2><<<grid, 256, 0, stream>>>(p, a->M);
+  }
+  cudaError_t e = cudaGetLastError();
+  *rc_out = (e == cudaSuccess) ? SLB_OK : slb_fail(SLB_ECUDA, "skinny gemm launch: %s", cudaGetErrorString(e));
+  return 1;
+}

@@ -128,9 +128,10 @@ def test_gemm_swiglu(lib):
     assert relerr(out, ref) < 1e-2
 
 
-@pytest.mark.parametrize("M", [1, 2, 3, 4])
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 16, 17, 31, 32])
 def test_gemv_small_m(lib, M):
-    """M <= 4 takes the weight-streaming GEMV (decode path); same epilogue contract as the tensor-core GEMM."""
+    """M <= 4 takes the weight-streaming GEMV, 4 < M <= 32 the mma.sync skinny GEMM (decode paths); same epilogue
+    contract as the tcgen05 GEMM."""
     K, N, I = 896, 1152, 4864
     a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
     bias, ls, res = rnd(N, seed=3), rnd(N, seed=4, scale=0.2), rnd(M, N, seed=5)
@@ -253,7 +254,8 @@ def _gqa_ref(q, k, v, past, valid):
 
 
 @pytest.mark.parametrize("B,lq,past,use_valid", [(1, 545, 0, False), (2, 200, 0, True), (2, 30, 549, False),
-                                                 (3, 1, 577, True), (1, 130, 64, False)])
+                                                 (3, 1, 577, True), (1, 130, 64, False),
+                                                 (6, 1, 600, True), (5, 31, 560, False)])  # batch >= 4: GQA-grouped decode kernel
 def test_attn_gqa_and_rope(lib, B, lq, past, use_valid):
     Hq, Hkv, lmax = 14, 2, 704
     qkv = rnd(B * lq, (Hq + 2 * Hkv) * 64, seed=1)
