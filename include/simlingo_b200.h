@@ -151,6 +151,9 @@ int slb_scale_cols_add(const void* x, const void* s, const void* res, void* out,
 /* acc[c] += alpha * sum_r a[r,c] * (b ? b[r,c] : 1)   (bias / layer-scale / norm-weight gradients) */
 int slb_col_reduce(const void* a, int64_t lda, const void* b, int64_t ldb, float* acc, int rows, int cols, float alpha,
                    void* stream);
+/* layer-scale residual backward in one pass: dbranch = dx * ls;  dls += colsum(dx * branch);  dbias += colsum(dbranch) */
+int slb_layerscale_bwd(const void* dx, const void* branch, const void* ls, void* dbranch, float* dls_accum, float* dbias_accum,
+                       int rows, int cols, void* stream);
 int slb_vit_assemble_bwd(const void* dx, void* dpatch_out, float* dcls_accum, float* dpos_accum, int tiles, void* stream);
 /* packs attention gradients (dq fp32 [B*L, Hq*64], dk/dv fp32 [B, Hkv, L, 64]) into the fused-QKV gradient
  * [B*L, (Hq+2Hkv)*64] bf16, rotating dq/dk back (theta <= 1: no rotation, the ViT case) */

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "../../include/simlingo_b200.h"
 
+long long* slb_debug_trace_ptr();  // attention_vit.cu (slb_debug_set_trace)
+
 namespace {
 
 constexpr int HD = 64, BQ = 128, BKV = 128;
@@ -30,7 +32,23 @@ constexpr int kSmdQ = kSmdS + 2 * kTile;    // [128 rows x 64 bf16] staging of t
 constexpr int kSmBar = kSmdQ + kTile;
 constexpr int kSmTotal = kSmBar + 256;
 
+// optional timeline trace (debug): CTA (0,0,0) records (tag, clock64) pairs per role; enabled by slb_debug_set_trace()
+constexpr int kTraceMax = 256;
+struct Trace {
+  long long* buf;  // [8 roles][kTraceMax][2]
+  int role;
+  int n;
+  __device__ __forceinline__ void rec(int tag) {
+    if (buf && n < kTraceMax) {
+      buf[((size_t)role * kTraceMax + n) * 2] = tag;
+      buf[((size_t)role * kTraceMax + n) * 2 + 1] = clock64();
+      ++n;
+    }
+  }
+};
+
 struct BwdParams {
+  long long* trace;
   int lq, lkv, past, causal;
   int hq, group;
   int q_col0, k_col0, v_col0;
@@ -144,6 +162,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint64_t dp_mn = umma_desc_mnmajor_sw128(sp, kTile), dds_mn = umma_desc_mnmajor_sw128(sds, kTile);
     const uint64_t dds_k0 = umma_desc_kmajor_sw128(sds), dds_k1 = umma_desc_kmajor_sw128(sds + kTile);
     mbar_wait(kv_full, 0);
+    Trace tr{(blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace : nullptr, 0, 0};
     auto issue_sdp = [&](int it) {
       const int s = it % kQS;
       mbar_wait(&qdo_full[s], (it / kQS) & 1);
@@ -164,11 +183,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int s = it % kQS;
       const uint32_t sq = smem_u32(smem + kSmQ + s * kTile), sdo = smem_u32(smem + kSmdO + s * kTile);
       const uint64_t dq_mn = umma_desc_mnmajor_sw128(sq, kTile), ddo_mn = umma_desc_mnmajor_sw128(sdo, kTile);
+      tr.rec(10 + 4 * it);
       mbar_wait(p_ready, it & 1);   // P / dS of item `it` are in smem and its S / dP have been read out of TMEM
+      tr.rec(11 + 4 * it);
       tc_fence_after();
       // S / dP of the next item first: the softmax warps start on them while dV / dK / dQ of this item are running
       if (it + 1 < n_items) issue_sdp(it + 1);
+      tr.rec(12 + 4 * it);
       if (it > 0) mbar_wait(dq_free, (it - 1) & 1);
+      tr.rec(13 + 4 * it);
       tc_fence_after();
       if (elect_one_sync()) {
 #pragma unroll
@@ -206,8 +229,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const bool cols_all = (cmask0 & cmask1) == 0xffffffffu;
 
     // partial dQ tile of item `jt` (this warpgroup's 32 columns): TMEM -> bf16 -> swizzled smem staging -> TMA store
-    auto dq_out = [&](int jt) {
-      const int hh = hk * p.group + jt / n_i, ii = i_first + jt % n_i;
+    auto dq_out = [&](int hh, int ii) {
       uint32_t o[32];
       tmem_ld_32x32(tm_dq + lane_off + wg * 32, o);
       tmem_ld_wait();
@@ -234,8 +256,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tma_store_commit();
       }
     };
-    auto load_stats = [&](int jt, float& l, float& d) {
-      const int hh = hk * p.group + jt / n_i, ii = i_first + jt % n_i;
+    // (head, query block) of an item advance incrementally: a runtime integer division costs ~500 cycles here
+    auto load_stats = [&](int jt, int hh, int ii, float& l, float& d) {
       const int row = ii * BQ + r;
       l = -INFINITY; d = 0.f;
       if (jt < n_items && row < p.lq) {
@@ -244,19 +266,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     };
     float l_next, d_next;
-    load_stats(0, l_next, d_next);
+    int h_cur = hk * p.group, i_cur = i_first, h_prev = 0, i_prev = 0;
+    load_stats(0, h_cur, i_cur, l_next, d_next);
+    Trace ts{(blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && quad == 2) ? p.trace : nullptr, 1 + wg, 0};
 
     for (int it = 0; it < n_items; ++it) {
-      const int i = i_first + it % n_i;
+      const int i = i_cur;
       const int row = i * BQ + r;
       // rows past the end / fully masked rows carry lse = -inf: P = exp2(-inf) = 0
       const float lse2 = (l_next == -INFINITY) ? INFINITY : l_next * lg2e, dlt = d_next;
-      load_stats(it + 1, l_next, d_next);  // prefetch: the global-load latency hides behind this item's math
+      int h_nxt = h_cur, i_nxt = i_cur + 1;
+      if (i_nxt == i_first + n_i) { i_nxt = i_first; ++h_nxt; }
+      load_stats(it + 1, h_nxt, i_nxt, l_next, d_next);  // prefetch: the global-load latency hides behind this item's math
       const float neg_lse2 = -lse2, neg_dlt_s = -dlt * p.scale;
       const int qmax = p.causal ? p.past + row : 0x7fffffff;
       // warp-uniform: does any (row, column) of this tile need the mask?
       const bool masked = !cols_all || (p.causal && (k0 + BKV - 1 > p.past + i * BQ));
+      ts.rec(10 + 6 * it);
       mbar_wait(sdp_full, it & 1);
+      ts.rec(11 + 6 * it);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < 64; cc += 32) {
@@ -270,7 +298,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         else softmax_chunk<false>(sr, dpr, pk, dk16, p.scale_log2, neg_lse2, p.scale, neg_dlt_s, 0u, 0, 0);
         if (cc == 0 && it > 0) {
           // dV / dK / dQ of the previous item have completed: P / dS smem is free again and its dQ tile is in TMEM
+          ts.rec(12 + 6 * it);
           mbar_wait(dq_full, (it - 1) & 1);
+          ts.rec(13 + 6 * it);
           tc_fence_after();
         }
         const int chunk0 = cc >> 3;
@@ -285,12 +315,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      if (it > 0) dq_out(it - 1);  // overlaps with S / dP of the next item and dV / dK / dQ of this one
+      ts.rec(14 + 6 * it);
+      if (it > 0) dq_out(h_prev, i_prev);  // overlaps with S / dP of the next item and dV / dK / dQ of this one
+      ts.rec(15 + 6 * it);
+      h_prev = h_cur; i_prev = i_cur;
+      h_cur = h_nxt; i_cur = i_nxt;
     }
     if (n_items > 0) {
       mbar_wait(dq_full, (n_items - 1) & 1);  // the last commit covers every MMA issued
       tc_fence_after();
-      dq_out(n_items - 1);
+      dq_out(h_prev, i_prev);
     }
     if (issuer) tma_store_wait<0>();
     // dK_j / dV_j: thread <-> key row (all MMAs have completed: dq_full of the last item was awaited above)
@@ -379,6 +413,7 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
   int rc = slb_make_tmap_3d(&tdq, workspace, (uint64_t)C, (uint64_t)p.lq, (uint64_t)nkb * batch, (uint64_t)C * 2, (uint64_t)p.lq * C * 2, HD, BQ, 1);
   if (rc) return rc;
   p.batch = batch;
+  p.trace = slb_debug_trace_ptr();
   static bool attr_set = false;
   if (!attr_set) {
     SLB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));

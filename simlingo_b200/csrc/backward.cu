@@ -311,6 +311,44 @@ col_reduce_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, float*
   }
 }
 
+// Layer-scale residual backward (x_out = x + ls * branch, branch = Linear(..) + bias) in one pass:
+//   dbranch = dx * ls (bf16 out);  dls[c] += sum_r dx * branch;  dbias[c] += sum_r dbranch
+// (replaces col_reduce(dx, branch) + scale_cols + col_reduce(dbranch): three passes over [rows, cols])
+__global__ void __launch_bounds__(256)
+layerscale_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ branch, const bf16* __restrict__ ls, bf16* __restrict__ dbranch,
+                      float* __restrict__ dls, float* __restrict__ dbias, int rows, int cols, int rows_per_block) {
+  __shared__ float sh[2][8][64];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * rows_per_block;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = c0 + tx * 2;
+  float s0 = 0.f, s1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (c < cols) {
+    const float2 lv = unpack_bf16(*reinterpret_cast<const uint32_t*>(ls + c));
+    const int r1 = min(rows, r0 + rows_per_block);
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const float2 dv = unpack_bf16(*reinterpret_cast<const uint32_t*>(dx + (size_t)r * cols + c));
+      const float2 pv = unpack_bf16(*reinterpret_cast<const uint32_t*>(branch + (size_t)r * cols + c));
+      const uint32_t o = pack_bf16(dv.x * lv.x, dv.y * lv.y);
+      *reinterpret_cast<uint32_t*>(dbranch + (size_t)r * cols + c) = o;
+      const float2 ov = unpack_bf16(o);  // the bias gradient sums what the wgrad / dgrad GEMMs will see
+      s0 += dv.x * pv.x; s1 += dv.y * pv.y;
+      b0 += ov.x; b1 += ov.y;
+    }
+  }
+  sh[0][ty][tx * 2] = s0; sh[0][ty][tx * 2 + 1] = s1;
+  sh[1][ty][tx * 2] = b0; sh[1][ty][tx * 2 + 1] = b1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, cc = threadIdx.x & 63;
+    if (c0 + cc < cols) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += sh[which][k][cc];
+      atomicAdd((which ? dbias : dls) + c0 + cc, s);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ViT embedding backward: dpatch_out[t*1024+p] = dx[t, 1+p]; dcls += sum_t dx[t,0]; dpos[tok] += sum_t dx[t,tok]
 // ------------------------------------------------------------------------------------------------
@@ -520,6 +558,17 @@ extern "C" int slb_col_reduce(const void* a, int64_t lda, const void* b, int64_t
   rpb = max(rpb, 64);
   dim3 grid(ceil_div(cols, 64), ceil_div(rows, rpb));
   col_reduce_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, acc, rows, cols, lda, ldb, rpb, alpha);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+extern "C" int slb_layerscale_bwd(const void* dx, const void* branch, const void* ls, void* dbranch, float* dls_accum, float* dbias_accum,
+                                  int rows, int cols, void* stream) {
+  SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 2) == 0 && dls_accum && dbias_accum, "layerscale_bwd: %d x %d", rows, cols);
+  int rpb = ceil_div(rows, max(1, (slb_num_sms() * 4) / ceil_div(cols, 64)));
+  rpb = max(rpb, 64);
+  dim3 grid(ceil_div(cols, 64), ceil_div(rows, rpb));
+  layerscale_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)dx, (const bf16*)branch, (const bf16*)ls, (bf16*)dbranch, dls_accum, dbias_accum,
+                                                    rows, cols, rpb);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

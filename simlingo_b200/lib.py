@@ -374,6 +374,16 @@ def col_reduce(a, acc, b=None, alpha=1.0):
     return acc
 
 
+def layerscale_bwd(dx, branch, ls, dls_acc, dbias_acc, out=None):
+    """-> dbranch = dx * ls (bf16); dls_acc += colsum(dx * branch); dbias_acc += colsum(dbranch)"""
+    _bf16(dx, branch, ls); _f32(dls_acc, dbias_acc)
+    assert dx.is_contiguous() and branch.is_contiguous() and dx.shape == branch.shape
+    out = torch.empty_like(dx) if out is None else out
+    _check(load().slb_layerscale_bwd(_p(dx), _p(branch), _p(ls), _p(out), _p(dls_acc), _p(dbias_acc), dx.shape[0], dx.shape[1], _stream()),
+           "layerscale_bwd")
+    return out
+
+
 def vit_assemble_bwd(dx, dcls_acc, dpos_acc, tiles, dpatch=None):
     _bf16(dx); _f32(dcls_acc, dpos_acc)
     dpatch = torch.empty((tiles * 1024, 1024), device=dx.device, dtype=torch.bfloat16) if dpatch is None else dpatch

@@ -266,9 +266,11 @@ class TrainEngine:
         self.graphs_enabled = os.environ.get("SLB_TRAIN_GRAPHS", "1") != "0"
         self._pool = None
         self._cap_stream = None
-        self._recs: Dict[tuple, dict] = {}
+        self._recs: Dict[tuple, dict] = {}   # insertion-ordered: least recently used first
         self._seen: Dict[tuple, int] = {}
         self.graph_replays = 0
+        # every captured shape pins its activations in the graph pool (~2.6 GB per sample at the 1B config): keep few
+        self.max_graph_shapes = int(os.environ.get("SLB_TRAIN_GRAPH_SHAPES", "4"))
 
     # ---- weights ---------------------------------------------------------------------------------------
     def w(self, key: str) -> Tensor:
@@ -384,10 +386,18 @@ class TrainEngine:
             del self._recs[key]
             rec = None
         if rec is not None:
+            self._recs[key] = self._recs.pop(key)  # mark as most recently used
             return True
         n = self._seen.get(key, 0)
         self._seen[key] = n + 1
-        return n >= 1
+        if n < 1:
+            return False
+        same_kind = [k for k in self._recs if k[0] == key[0]]
+        if len(same_kind) >= self.max_graph_shapes:   # evict the least recently used shape of this kind
+            old = self._recs.pop(same_kind[0])
+            old.get("saved", {}).pop("graph", None)
+            old.clear()
+        return True
 
     def vision_forward_auto(self, pixels: Tensor):
         key = ("vis", int(pixels.shape[0]))
@@ -539,9 +549,7 @@ class TrainEngine:
             a = sv["layers"][i]
             if "graph" not in sv:
                 sv["layers"][i] = None  # eager: release the layer's activations as soon as they are consumed
-            lib.col_reduce(dx, self._acc(p + "ls2"), a["p2"])
-            dp2 = lib.scale_cols(dx, w(p + "ls2"))
-            lib.col_reduce(dp2, self._acc(p + "mlp.fc2.bias"))
+            dp2 = lib.layerscale_bwd(dx, a["p2"], w(p + "ls2"), self._acc(p + "ls2"), self._acc(p + "mlp.fc2.bias"))
             self._wgrad(dp2, a["fact"], p + "mlp.fc2.weight")
             dfpre = lib.gemm(dp2, w(p + "mlp.fc2.weight"), b_t=True, aux=a["fpre"], aux_mode=2)  # dgrad * gelu'(pre) in the epilogue
             lib.col_reduce(dfpre, self._acc(p + "mlp.fc1.bias"))
@@ -550,9 +558,7 @@ class TrainEngine:
             dxm = lib.layernorm_bwd(dh2, a["xm"], w(p + "norm2.weight"), a["st2"][0], a["st2"][1],
                                     self._acc(p + "norm2.weight"), self._acc(p + "norm2.bias"))
             lib.add_inplace(dxm, dx)
-            lib.col_reduce(dxm, self._acc(p + "ls1"), a["p1"])
-            dp1 = lib.scale_cols(dxm, w(p + "ls1"), out=dx)
-            lib.col_reduce(dp1, self._acc(p + "attn.proj.bias"))
+            dp1 = lib.layerscale_bwd(dxm, a["p1"], w(p + "ls1"), self._acc(p + "ls1"), self._acc(p + "attn.proj.bias"), out=dx)
             self._wgrad(dp1, a["att"], p + "attn.proj.weight")
             datt = lib.gemm(dp1, w(p + "attn.proj.weight"), b_t=True, out=dh2)
             delta = lib.attn_delta(a["att"], datt, T, s.vit_tokens, s.vit_heads)

@@ -97,6 +97,15 @@ def test_col_reduce_and_scale(lib):
     assert relerr(c, a.float() + b.float()) < 1e-2
 
 
+def test_layerscale_bwd(lib):
+    dx, br, ls = rnd(2050, 1024, seed=1), rnd(2050, 1024, seed=2), rnd(1024, seed=3, scale=0.2)
+    dls, db = torch.zeros(1024, device="cuda"), torch.zeros(1024, device="cuda")
+    out = lib.layerscale_bwd(dx, br, ls, dls, db)
+    assert relerr(out, dx.float() * ls.float()) < 1e-2
+    assert relerr(dls, (dx.float() * br.float()).sum(0)) < 1e-3
+    assert relerr(db, out.float().sum(0)) < 1e-3
+
+
 def test_vit_assemble_bwd(lib):
     T = 3
     dx = rnd(T * 1025, 1024, seed=1)
