@@ -12,6 +12,7 @@
 // key-padding mask).  Warps: 0 = TMA producer, 1 = MMA issuer, 2-5 / 6-9 = two softmax warpgroups that split the
 // 128 key columns of S / dP (and the 64 dQ columns) between them.  The MMA warp issues S/dP of item i+1 right behind
 // dV/dK/dQ of item i, so the tensor pipe only idles while the softmax of one tile runs.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/simlingo_b200.h"
 
@@ -20,7 +21,8 @@ long long* slb_debug_trace_ptr();  // attention_vit.cu (slb_debug_set_trace)
 namespace {
 
 constexpr int HD = 64, BQ = 128, BKV = 128;
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_THREADS = 576;  // TMA warp, MMA warp, 4 softmax warpgroups (32 key columns of S / dP each)
+constexpr int kSoftmaxThreads = BWD_THREADS - 64;
 constexpr int kTile = 128 * HD * 2;  // 16 KB
 constexpr int kSmK = 0, kSmV = kTile;
 constexpr int kQS = 3;                      // Q / dO ring depth
@@ -49,6 +51,7 @@ struct Trace {
 
 struct BwdParams {
   long long* trace;
+  int variant;  // SLB_BWD_VARIANT (timing experiments only, results are wrong): 1 no dV MMAs, 2 no dK, 4 no dQ, 8 no softmax math
   int lq, lkv, past, causal;
   int hq, group;
   int q_col0, k_col0, v_col0;
@@ -117,9 +120,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(kv_full, 1);
     for (int s = 0; s < kQS; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(p_ready, 8);
+    mbar_init(p_ready, kSoftmaxThreads / 32);
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, 8);
+    mbar_init(dq_free, kSoftmaxThreads / 32);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -195,9 +198,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_after();
       if (elect_one_sync()) {
 #pragma unroll
+        if (!(p.variant & 1))
+#pragma unroll
         for (int k = 0; k < BQ / 16; ++k) tc_mma_bf16(tm_dv, dp_mn + (uint64_t)k * 128, ddo_mn + (uint64_t)k * 128, idesc_kv, (it | k) != 0);
+        if (!(p.variant & 2))
 #pragma unroll
         for (int k = 0; k < BQ / 16; ++k) tc_mma_bf16(tm_dk, dds_mn + (uint64_t)k * 128, dq_mn + (uint64_t)k * 128, idesc_kv, (it | k) != 0);
+        if (!(p.variant & 4))
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
           tc_mma_bf16(tm_dq, (k < 4 ? dds_k0 : dds_k1) + 2 * (k & 3), dk_mn + (uint64_t)k * 128, idesc_dq, k != 0);
@@ -208,49 +215,48 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else {
     const int quad = warp & 3;
-    const int wg = (warp - 2) >> 2;  // 0: key columns 0..63 / dQ columns 0..31, 1: the other half
+    const int wg = (warp - 2) >> 2;  // 0..3: key columns 32 wg .. 32 wg + 31 of S / dP, columns 16 wg .. + 15 of dQ / dK / dV
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    uint8_t* prow = smem + kSmP + wg * kTile + r * 128;
-    uint8_t* dsrow = smem + kSmdS + wg * kTile + r * 128;
+    uint8_t* prow = smem + kSmP + (wg >> 1) * kTile + r * 128;
+    uint8_t* dsrow = smem + kSmdS + (wg >> 1) * kTile + r * 128;
     uint8_t* dqstage = smem + kSmdQ;
     const int rsw = r & 7;
     const bool issuer = (warp == 2) && (lane == 0);
     const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)b * p.key_valid_ld : nullptr;
     const float lg2e = 1.4426950408889634f;
-    // validity of this warpgroup's 64 key columns (fixed for the whole CTA): inside the sequence and not padding
-    uint32_t cmask0 = 0u, cmask1 = 0u;
+    // validity of this warpgroup's 32 key columns (fixed for the whole CTA): inside the sequence and not padding
+    uint32_t cmask0 = 0u;
 #pragma unroll 1
     for (int c = 0; c < 32; ++c) {
-      const int col = k0 + wg * 64 + c;
+      const int col = k0 + wg * 32 + c;
       cmask0 |= ((col < p.lkv && (!kvalid || kvalid[col] != 0)) ? 1u : 0u) << c;
-      cmask1 |= ((col + 32 < p.lkv && (!kvalid || kvalid[col + 32] != 0)) ? 1u : 0u) << c;
     }
-    const bool cols_all = (cmask0 & cmask1) == 0xffffffffu;
+    const bool cols_all = cmask0 == 0xffffffffu;
 
     // partial dQ tile of item `jt` (this warpgroup's 32 columns): TMEM -> bf16 -> swizzled smem staging -> TMA store
     auto dq_out = [&](int hh, int ii) {
-      uint32_t o[32];
-      tmem_ld_32x32(tm_dq + lane_off + wg * 32, o);
+      uint32_t o[16];
+      tmem_ld_32x16(tm_dq + lane_off + wg * 16, o);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
       if (issuer) tma_store_wait_read<0>();  // the previous store has finished reading the staging tile
       __syncwarp();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, kSoftmaxThreads);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         uint4 v;
         v.x = pack_bf16(__uint_as_float(o[8 * j]), __uint_as_float(o[8 * j + 1]));
         v.y = pack_bf16(__uint_as_float(o[8 * j + 2]), __uint_as_float(o[8 * j + 3]));
         v.z = pack_bf16(__uint_as_float(o[8 * j + 4]), __uint_as_float(o[8 * j + 5]));
         v.w = pack_bf16(__uint_as_float(o[8 * j + 6]), __uint_as_float(o[8 * j + 7]));
-        *reinterpret_cast<uint4*>(dqstage + r * 128 + (((4 * wg + j) ^ rsw) << 4)) = v;
+        *reinterpret_cast<uint4*>(dqstage + r * 128 + (((2 * wg + j) ^ rsw) << 4)) = v;
       }
       fence_proxy_async_smem();
       __syncwarp();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, kSoftmaxThreads);
       if (issuer) {
         tma_store_3d(&tmap_dq, dqstage, hh * HD, ii * BQ, jb * p.batch + b);
         tma_store_commit();
@@ -268,7 +274,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     float l_next, d_next;
     int h_cur = hk * p.group, i_cur = i_first, h_prev = 0, i_prev = 0;
     load_stats(0, h_cur, i_cur, l_next, d_next);
-    Trace ts{(blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && quad == 2) ? p.trace : nullptr, 1 + wg, 0};
+    Trace ts{(blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && quad == 2 && wg < 2) ? p.trace : nullptr, 1 + wg, 0};
 
     for (int it = 0; it < n_items; ++it) {
       const int i = i_cur;
@@ -286,24 +292,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(sdp_full, it & 1);
       ts.rec(11 + 6 * it);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 32) {
-        const int c = wg * 64 + cc;
+      {
+        const int c = wg * 32;
         uint32_t sr[32], dpr[32];
         tmem_ld_32x32(tm_s + lane_off + c, sr);
         tmem_ld_32x32(tm_dp + lane_off + c, dpr);
         tmem_ld_wait();
         uint32_t pk[16], dk16[16];
-        if (masked) softmax_chunk<true>(sr, dpr, pk, dk16, p.scale_log2, neg_lse2, p.scale, neg_dlt_s, cc ? cmask1 : cmask0, k0 + c, qmax);
+        if (p.variant & 8) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { pk[e] = sr[e]; dk16[e] = dpr[e]; }
+        } else if (masked) softmax_chunk<true>(sr, dpr, pk, dk16, p.scale_log2, neg_lse2, p.scale, neg_dlt_s, cmask0, k0 + c, qmax);
         else softmax_chunk<false>(sr, dpr, pk, dk16, p.scale_log2, neg_lse2, p.scale, neg_dlt_s, 0u, 0, 0);
-        if (cc == 0 && it > 0) {
+        if (it > 0) {
           // dV / dK / dQ of the previous item have completed: P / dS smem is free again and its dQ tile is in TMEM
           ts.rec(12 + 6 * it);
           mbar_wait(dq_full, (it - 1) & 1);
           ts.rec(13 + 6 * it);
           tc_fence_after();
         }
-        const int chunk0 = cc >> 3;
+        const int chunk0 = (c & 63) >> 3;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int off = ((chunk0 + q4) ^ rsw) << 4;
@@ -331,20 +339,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int key = k0 + r;
     const bool key_ok = key < p.lkv;
     {
-      const int c = wg * 32;
-      uint32_t a[32], bb[32];
+      const int c = wg * 16;
+      uint32_t a[16], bb[16];
       if (n_items > 0) {  // warp-uniform: the TMEM loads stay convergent for partially valid warps
-        tmem_ld_32x32(tm_dk + lane_off + c, a);
-        tmem_ld_32x32(tm_dv + lane_off + c, bb);
+        tmem_ld_32x16(tm_dk + lane_off + c, a);
+        tmem_ld_32x16(tm_dv + lane_off + c, bb);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) { a[e] = 0; bb[e] = 0; }
+        for (int e = 0; e < 16; ++e) { a[e] = 0; bb[e] = 0; }
       }
       if (key_ok && p.dkv_bf16) {
         bf16* base = p.dkv_bf16 + ((size_t)b * p.lkv + key) * p.dkv_ld + hk * HD + c;
 #pragma unroll
-        for (int e = 0; e < 32; e += 8) {
+        for (int e = 0; e < 16; e += 8) {
           uint4 vk, vv;
           vk.x = pack_bf16(__uint_as_float(a[e]), __uint_as_float(a[e + 1])); vk.y = pack_bf16(__uint_as_float(a[e + 2]), __uint_as_float(a[e + 3]));
           vk.z = pack_bf16(__uint_as_float(a[e + 4]), __uint_as_float(a[e + 5])); vk.w = pack_bf16(__uint_as_float(a[e + 6]), __uint_as_float(a[e + 7]));
@@ -357,7 +365,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         float* dkrow = p.dk + (((size_t)b * (p.hq / p.group) + hk) * p.lkv + key) * HD;
         float* dvrow = p.dv + (((size_t)b * (p.hq / p.group) + hk) * p.lkv + key) * HD;
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
+        for (int e = 0; e < 16; e += 4) {
           *reinterpret_cast<float4*>(dkrow + c + e) = make_float4(__uint_as_float(a[e]), __uint_as_float(a[e + 1]), __uint_as_float(a[e + 2]), __uint_as_float(a[e + 3]));
           *reinterpret_cast<float4*>(dvrow + c + e) = make_float4(__uint_as_float(bb[e]), __uint_as_float(bb[e + 1]), __uint_as_float(bb[e + 2]), __uint_as_float(bb[e + 3]));
         }
@@ -414,6 +422,9 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
   if (rc) return rc;
   p.batch = batch;
   p.trace = slb_debug_trace_ptr();
+  static int variant = -1;
+  if (variant < 0) { const char* ev = getenv("SLB_BWD_VARIANT"); variant = ev ? atoi(ev) : 0; }
+  p.variant = variant;
   static bool attr_set = false;
   if (!attr_set) {
     SLB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
