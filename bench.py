@@ -40,6 +40,11 @@ FRAMES_PER_GPU = 64
 PROMPT_LEN = 545
 
 
+def _pin(t):
+    """pinned host memory for the H2D legs (plain memory on a box without a driver: the reference arm runs there too)"""
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -127,7 +132,7 @@ def host_batch(spec, batch, seed):
     frames = S.synth_frames(spec, 1, seed, dtype=torch.bfloat16).expand(batch, -1, -1, -1, -1, -1).contiguous()
     valid = torch.ones_like(ids, dtype=torch.bool)
     ph = S.synth_placeholders(spec, batch, seed)
-    return dict(ids=ids.pin_memory(), frames=frames.pin_memory(), valid=valid.pin_memory(), placeholders=ph)
+    return dict(ids=_pin(ids), frames=_pin(frames), valid=_pin(valid), placeholders=ph)
 
 
 def make_example(hb, device):
@@ -219,8 +224,8 @@ def host_train_batch(spec, batch, seed):
     lm = torch.zeros_like(valid)
     lm[:, -ANSWER_LEN:] = True
     wps, path = S.synth_labels(spec, batch, seed)
-    return dict(ids=ids.pin_memory(), frames=frames.pin_memory(), valid=valid.pin_memory(), loss_masking=lm.pin_memory(),
-                wps=wps.pin_memory(), path=path.pin_memory(), placeholders=S.synth_placeholders(spec, batch, seed))
+    return dict(ids=_pin(ids), frames=_pin(frames), valid=_pin(valid), loss_masking=_pin(lm),
+                wps=_pin(wps), path=_pin(path), placeholders=S.synth_placeholders(spec, batch, seed))
 
 
 def make_train_example(hb, device):
@@ -402,7 +407,7 @@ def host_agent_batch(spec, batch, seed, n_gen):
         ids[:, -1] = (spec.eos_id - n_gen * S.LMHEAD_SHIFT) % spec.vocab   # greedy decoding emits n_gen tokens, the last one EOS
     frames = S.synth_frames(spec, batch, seed, dtype=torch.bfloat16)
     valid = torch.ones_like(ids, dtype=torch.bool)
-    return dict(ids=ids.pin_memory(), frames=frames.pin_memory(), valid=valid.pin_memory(), placeholders=S.synth_placeholders(spec, batch, seed))
+    return dict(ids=_pin(ids), frames=_pin(frames), valid=_pin(valid), placeholders=S.synth_placeholders(spec, batch, seed))
 
 
 def run_agent(args, rank, world, local):
@@ -486,9 +491,28 @@ def run_language(args, rank, world, local):
                        "+ 30-query pass (BASELINE configs[4])", "batch_per_gpu": B, "parallelism": f"dp{world} batch-sharded, no data-path collective",
            "l2": "weights + KV cache exceed the 126 MB L2"}
     if args.impl == "reference":
-        if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "the no-cache reference formulation needs ~64 full 600-token fp32 passes per sample on CPU "
-                              "(minutes per sample); run --workload offline64 / agent for the CPU arm"}), flush=True)
+        if rank != 0:
+            return
+        # bounded sample of the same workload: 1 sample, 4 greedy tokens, in the reference's own formulation (no KV cache:
+        # every token re-forwards the whole sequence, llm.py:217-235)
+        from oracle import model as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = S.init_state_dict(spec, seed=0)
+        hb = host_agent_batch(spec, 1, 500, None)
+        n_tok = 4
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.driving_forward(sd, spec, hb["frames"].float(), hb["ids"], hb["valid"], hb["placeholders"], max_new_tokens=n_tok, eos_token_id=None)
+        t = time.perf_counter() - t0
+        tps = n_tok / t
+        line = {"impl": "reference", "metric": "language_generated_tokens_per_s", "value": round(tps, 4), "unit": "tokens/s", "n_gpus": args.gpus,
+                "steps": 1, "warmup": 0, "ms_per_step": round(t * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": round(tps, 4), "unit": "tokens/s", "cores": cores, "kind": "port",
+                                 "sample": "1 sample, ViT + 4 greedy tokens (no KV cache, as the reference) + 30-query pass, fp32 oracle, single run"},
+                "e2e": {"value": round(tps, 4), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
         return
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
