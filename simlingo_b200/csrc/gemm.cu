@@ -5,6 +5,7 @@
 //   warp 1     TMEM allocator + MMA issuer (one elected lane)
 //   warps 2-5  epilogue (warp w reads TMEM lanes 32*(w%4) .. +31 = accumulator rows)
 // Covers K1,K3,K5,K7,K10,K13,K14 of SURVEY.md section 2.2 and their dgrad/wgrad (a_t / b_t operands).
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/simlingo_b200.h"
 
@@ -16,6 +17,12 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+
+static int slb_gemm_res_prefetch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SLB_GEMM_NO_RESPF"); v = (e && atoi(e)) ? 0 : 1; }
+  return v;
+}
 
 struct EpiParams {
   long long* dbg;  // optional [16] int64: wait-cycle counters of cluster 0 (slb_debug_set_trace), else null
@@ -33,6 +40,7 @@ struct EpiParams {
   int num_m, num_n;
   bf16* aux;        // optional second operand of the epilogue, bf16 [M, N] with row stride ld_aux
   long long ld_aux;
+  int res_prefetch; // 0 disables the residual prefetch (SLB_GEMM_NO_RESPF=1, A/B timing only)
   int aux_mode;     // 1: store the pre-activation (alpha*acc + bias) there; 2: multiply by gelu'(aux) (fc2 dgrad -> d pre-GELU)
 };
 
@@ -179,10 +187,35 @@ __device__ __forceinline__ void aux_gelu_grad32(const EpiParams& p, int row, int
   }
 }
 
+// Residual prefetch (bf16, 16-byte aligned rows, full 32-column chunk): the residual row segment of the NEXT chunk is
+// requested before the current chunk is processed - and the first one before the accumulator barrier is awaited - so
+// its DRAM latency (one ~1 us stall per chunk otherwise: the layer-scale residual GEMMs sat at 51 % tensor-pipe
+// utilisation) overlaps with TMEM loads, math and stores.
+struct ResPrefetch {
+  uint4 v[4];
+  bool valid;
+};
+__device__ __forceinline__ bool res_vec_ok(const EpiParams& p) {
+  return p.res_prefetch && p.res && !p.out_fp32 && !p.swiglu && ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+}
+__device__ __forceinline__ void res_prefetch(const EpiParams& p, int row, int col0, ResPrefetch& r) {
+  r.valid = row < p.M && col0 + 32 <= p.N;
+  if (r.valid) {
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (long long)row * p.ldr + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.v[i] = src[i];
+  }
+}
+template <int BN>
+__device__ __forceinline__ int epi_first_chunk(int half) {
+  constexpr int kChunks = BN / 32, kFirst = (kChunks + 1) / 2;
+  return half ? kFirst * 32 : 0;
+}
+
 // Epilogue of one accumulator tile for one thread (= one output row), 32-column chunks [c_begin, c_end):
 // TMEM -> registers -> fused epilogue -> global.  Two warps share a TMEM lane quadrant and split the chunks.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr, int row, int n0, int half) {
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr, int row, int n0, int half, ResPrefetch& pre, bool use_pre) {
   const bool row_ok = row < p.M;
   if (!p.swiglu) {
     constexpr int kChunks = BN / 32, kFirst = (kChunks + 1) / 2;
@@ -190,6 +223,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
       if (n0 + c >= p.N) break;  // warp-uniform
+      ResPrefetch cur = pre;
+      if (use_pre && c + 32 < c_end) res_prefetch(p, row, n0 + c + 32, pre);
       uint32_t r[32];
       tmem_ld_32x32(taddr + c, r);
       tmem_ld_wait();
@@ -222,7 +257,16 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
         for (int i = 0; i < 32; ++i) v[i] *= sc[i];
       }
       if (row_ok) {
-        if (p.res) add_residual32(p, row, col0, v, p.N);
+        if (use_pre && cur.valid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 a = unpack_bf16(cur.v[i].x), b = unpack_bf16(cur.v[i].y), c2 = unpack_bf16(cur.v[i].z), d = unpack_bf16(cur.v[i].w);
+            v[8 * i + 0] += a.x; v[8 * i + 1] += a.y; v[8 * i + 2] += b.x; v[8 * i + 3] += b.y;
+            v[8 * i + 4] += c2.x; v[8 * i + 5] += c2.y; v[8 * i + 6] += d.x; v[8 * i + 7] += d.y;
+          }
+        } else if (p.res) {
+          add_residual32(p, row, col0, v, p.N);
+        }
         store_row32(p, row, col0, v, p.N);
       }
     }
@@ -361,11 +405,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n) * BM;
       const int n0 = (tile % p.num_n) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool use_pre = res_vec_ok(p);
+      ResPrefetch pre;
+      pre.valid = false;
+      if (use_pre) res_prefetch(p, row, n0 + epi_first_chunk<BN>((warp - 2) >> 2), pre);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      epilogue_tile<BN>(p, taddr, row, n0, (warp - 2) >> 2);
+      epilogue_tile<BN>(p, taddr, row, n0, (warp - 2) >> 2, pre, use_pre);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -400,6 +448,7 @@ int launch_gemm(const slb_gemm_args* a, cudaStream_t stream) {
   p.res = a->residual; p.ldr = a->ldr;
   p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
   p.aux = (bf16*)a->aux; p.ld_aux = a->ld_aux; p.aux_mode = a->aux ? a->aux_mode : 0;
+  p.res_prefetch = slb_gemm_res_prefetch();
   p.num_m = ceil_div(a->M, BM);
   p.num_n = ceil_div(a->N, BN);
   auto kern = gemm_bf16_kernel<BN, TA, TB>;
@@ -547,13 +596,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m0 = (tile / p.num_n) * (2 * BM) + rank * BM;
       const int n0 = (tile % p.num_n) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool use_pre = res_vec_ok(p);
+      ResPrefetch pre;
+      pre.valid = false;
+      if (use_pre) res_prefetch(p, row, n0 + epi_first_chunk<BN>((warp - 2) >> 2), pre);
       const long long c0 = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase);
       w_tfull += clock64() - c0;
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
-      epilogue_tile<BN>(p, taddr, row, n0, (warp - 2) >> 2);
+      epilogue_tile<BN>(p, taddr, row, n0, (warp - 2) >> 2, pre, use_pre);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
@@ -586,6 +639,7 @@ int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
   p.res = a->residual; p.ldr = a->ldr;
   p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
   p.aux = (bf16*)a->aux; p.ld_aux = a->ld_aux; p.aux_mode = a->aux ? a->aux_mode : 0;
+  p.res_prefetch = slb_gemm_res_prefetch();
   p.num_m = ceil_div(a->M, 2 * BM);
   p.num_n = ceil_div(a->N, BN);
   auto kern = gemm2_bf16_kernel<BN>;
