@@ -461,21 +461,29 @@ def run_agent(args, rank, world, local):
             dev_ms.append(e0.elapsed_time(e1))
         launches = (lib.LAUNCHES - l0) // steps
         host_out = torch.empty((30, 2), dtype=torch.float32).pin_memory()
-        for _ in range(steps):
+        # end to end as the agent sees it (agent_simlingo.py:470-502, 796-797): the cropped uint8 camera frame (359 x 1024)
+        # leaves pinned host memory, is resized / tiled / normalised on the GPU (slb_preprocess_frames) and goes through
+        # DrivingModel.forward; the 30 predicted waypoints come back to the host
+        from simlingo_b200.preprocess import preprocess_frames
+        cam_host = _pin(torch.from_numpy(S.synth_camera(359, 1024, 3 + rank))[None])
+        for _ in range(steps + 3):
             t0 = time.perf_counter()
             ex2 = make_example(hb, device)
+            cam = preprocess_frames(cam_host.to(device, non_blocking=True)).view(1, 1, 2, 3, 448, 448)
+            ex2 = ex2._replace(camera_images=cam)
             sp, rt, lang = model(ex2)
             host_out[:20].copy_(rt[0].float(), non_blocking=True)
             host_out[20:].copy_(sp[0].float(), non_blocking=True)
             torch.cuda.current_stream().synchronize()
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        e2e_ms = e2e_ms[3:]
         q = lambda v, p: sorted(v)[min(len(v) - 1, int(p * len(v)))]
         out[G] = dict(p50=round(q(dev_ms, 0.5), 3), p90=round(q(dev_ms, 0.9), 3), e2e_p50=round(q(e2e_ms, 0.5), 3), e2e_p90=round(q(e2e_ms, 0.9), 3),
                       launches=launches, tflops=round((S.flops_frame(spec, PROMPT_LEN + 30) + G * 2 * 0.494e9 + (G + 1) * 2 * spec.llm_hidden * spec.vocab) / 1e12, 3))
     if rank != 0:
         return
     hb = host_agent_batch(spec, 1, 99, 1)
-    h2d = hb["frames"].numel() * 2 + hb["ids"].numel() * 8 + hb["valid"].numel()
+    h2d = 3 * 359 * 1024 + hb["ids"].numel() * 8 + hb["valid"].numel()
     line = {"metric": "agent_step_latency_ms_p50", "value": out[1]["p50"], "unit": "ms", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": out[1]["p50"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": cfg, "e2e": {"value": out[1]["e2e_p50"], "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 240},

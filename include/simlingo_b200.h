@@ -101,6 +101,15 @@ int slb_gather_rows(const void* src, const int64_t* idx, void* dst, int n, int c
 /* dst[idx[i]] = src[i] (the `inputs_embeds[selected] = vit_embeds` scatter of internvl2_model.py:124) */
 int slb_scatter_rows(void* dst, const int64_t* idx, const void* src, int n, int cols, int64_t dst_rows, void* stream);
 
+/* ---- camera-frame pre-processing (the step in front of the path: internvl2_utils.py:179-267, agent_simlingo.py:483-502)
+ * uint8 RGB frames [B,3,H,W] -> PIL-compatible bicubic resize to (448*grid_h, 448*grid_w) -> grid_w*grid_h tiles of
+ * 448x448 -> (u8/255 - mean)/std -> bf16 [B, tiles, 3, 448, 448].  The resampling tables (first input index, tap count,
+ * 22-bit fixed-point taps [out, ksize] per output index; device pointers) are Pillow's precompute_coeffs /
+ * normalize_coeffs_8bpc evaluated on the host.  tmp: uint8 [B,3,H,448*grid_w] scratch. */
+typedef struct { const int32_t* first; const int32_t* count; const int32_t* taps; int32_t ksize; } slb_resample_table;
+int slb_preprocess_frames(const uint8_t* frames, uint8_t* tmp, const slb_resample_table* horiz, const slb_resample_table* vert,
+                          void* tiles_out, int batch, int height, int width, int grid_w, int grid_h, void* stream);
+
 /* ---- elementwise helpers ---- */
 int slb_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);
 int slb_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);

@@ -333,6 +333,19 @@ def synth_frames(spec: ModelSpec, batch: int, seed: int, dtype=torch.float32) ->
     return x.clamp_(-2.2, 2.7).to(torch.bfloat16).to(dtype)
 
 
+def synth_camera(h: int, w: int, seed: int):
+    """Deterministic uint8 [3, h, w] camera-like test image (numpy): smooth gradients + edges + noise, so that a
+    resampler sees clipping and ringing.  h, w = 359, 1024 is the agent's cropped front camera
+    (512 - 512 * 4.8 // 16 rows of a 1024 x 512 frame, reference agent_simlingo.py:470)."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.stack([127 + 120 * np.sin(x / 37.0 + c) * np.cos(y / 23.0 - c) for c in range(3)])
+    img += (((x // 16 + y // 16) % 2) * 90 - 45)[None]
+    img += rs.randn(3, h, w) * 20
+    return np.clip(np.round(img), 0, 255).astype(np.uint8)
+
+
 def synth_placeholders(spec: ModelSpec, batch: int, seed: int):
     """``list[dict[token_id -> ndarray[2,2]]]`` as built at agent_simlingo.py:566-580."""
     g = torch.Generator().manual_seed(seed + 202)

@@ -1,0 +1,71 @@
+"""Camera-frame pre-processing (the step in front of the hot path).
+
+CPU: the numpy oracle (``oracle/preprocess.py``) against the golden fixture produced by the reference's own
+``preprocess_image_batch`` (Pillow + torchvision, ``tests/golden/make_golden_preprocess.py``) - bit-exact uint8 tiles
+(SHA-256 over all pixels), identical normalised float32 values, and the host-side tables of the product.
+GPU: ``simlingo_b200.preprocess`` / the drop-in ``simlingo_training.utils.internvl2_utils.preprocess_image_batch``
+against the oracle - bit-exact (integer resampling; the fp32 normalisation uses torch's operation order and is rounded
+once to bf16)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import preprocess as P
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "preprocess.npz")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize("name", list(P.CASES))
+def test_oracle_matches_reference_run(golden, name):
+    h, w, seed = P.CASES[name]
+    tiles = P.preprocess_tiles_u8(P.synth_camera(h, w, seed))
+    assert tiles.shape == (2, 3, 448, 448)
+    assert np.array_equal(tiles[:, :, ::5, ::5], golden[name + "_sub5"])
+    digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(tiles).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(digest, golden[name + "_sha256"]), "oracle tiles differ from the reference's Pillow output"
+    assert np.array_equal(P.normalize(tiles)[:, :, 0, :16], golden[name + "_norm_row0"])
+    assert golden[name + "_image_sizes"].tolist() == [[h, w]]
+
+
+def test_tile_grid_and_tables_of_the_product_match_oracle():
+    from simlingo_b200.preprocess import resample_table, tile_grid
+    for (w, h) in [(1024, 359), (1024, 512), (203, 101), (448, 448), (300, 900), (896, 448)]:
+        assert tile_grid(w, h) == P.tile_grid(w, h)
+    for (i, o) in [(1024, 896), (359, 448), (512, 448), (203, 896), (101, 448), (2000, 448)]:
+        a, b = resample_table(i, o), P.resample_coeffs(i, o)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    f, c, t = resample_table(448, 448)
+    assert f.tolist() == list(range(448)) and set(c.tolist()) == {1} and set(t.ravel().tolist()) == {1 << 22}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(P.CASES) + ["noop_448x896", "tall_700x300"])
+def test_gpu_preprocess_is_bit_exact(name):
+    from simlingo_training.utils.internvl2_utils import preprocess_image_batch
+    h, w, seed = P.CASES.get(name, {"noop_448x896": (448, 896, 21), "tall_700x300": (700, 300, 22)}.get(name))
+    imgs = [P.synth_camera(h, w, seed + k) for k in range(3)]
+    res = preprocess_image_batch([torch.from_numpy(i) for i in imgs], input_size=448, use_global_img=False, max_num_grid=2)
+    pv = res["pixel_values"]
+    assert pv.is_cuda and pv.dtype == torch.bfloat16 and pv.shape == (3, 2, 3, 448, 448)
+    assert res["image_sizes"].tolist() == [[h, w]] * 3
+    for k, img in enumerate(imgs):
+        ref = torch.from_numpy(P.normalize(P.preprocess_tiles_u8(img))).to(torch.bfloat16)
+        assert torch.equal(pv[k].cpu(), ref), f"{name}[{k}]: {(pv[k].cpu().float() - ref.float()).abs().max().item()}"
+
+
+@pytest.mark.gpu
+def test_gpu_preprocess_feeds_the_model():
+    """pixel_values plug straight into DrivingInput.camera_images ([B, 1, tiles, 3, 448, 448], agent_simlingo.py:497-502)."""
+    from simlingo_b200.preprocess import preprocess_frames
+    x = torch.from_numpy(np.stack([P.synth_camera(359, 1024, 5)])).cuda()
+    pv = preprocess_frames(x)
+    cam = pv.view(1, 1, 2, 3, 448, 448)
+    assert cam.dtype == torch.bfloat16 and float(cam.float().abs().max()) < 3.0
