@@ -113,3 +113,28 @@ def test_driving_forward_batched_ragged_and_padded(setup):
                                       eos_token_id=eos, ids_cpu=ids)
     assert [t.cpu().tolist() for t in tok] == [t.tolist() for t in tok_ref]
     assert relerr(sp, sp_ref) < TOL and relerr(rt, rt_ref) < TOL
+
+
+def test_cuda_graph_generation_equals_eager_launches(setup):
+    """From the second call with a shape the engine replays CUDA graphs (ViT on few tiles, prefill, one decode-step graph
+    per token with the position counter on the device, query append): tokens identical and waypoints equal to the
+    eagerly launched kernels, for the agent case (batch 1, stops at EOS) and the language case (batch 3, EOS suppressed)."""
+    spec, sd, eng = setup
+    eos = spec.eos_id
+    for B, G, use_eos, max_new in [(1, 5, True, 9), (3, 6, False, 6)]:
+        ids = synth_prompt_ids(spec, B, seed=31)
+        ids[:, -1] = (eos - G * LMHEAD_SHIFT) % spec.vocab
+        valid = torch.ones_like(ids, dtype=torch.bool)
+        fr, ph = synth_frames(spec, B, 31).to("cuda", torch.bfloat16), synth_placeholders(spec, B, 31)
+        run = lambda: eng.driving_forward(fr, ids.cuda(), valid.cuda(), ph, max_new_tokens=max_new, eos_token_id=eos if use_eos else None,
+                                          ids_cpu=ids)
+        eng.graphs_enabled = False
+        sp0, rt0, tok0 = run()
+        eng.graphs_enabled = True
+        r0 = eng.graph_replays
+        for _ in range(3):   # eager sighting, capture + replay, replay
+            sp, rt, tok = run()
+        assert eng.graph_replays - r0 >= 2 * (2 + (G if use_eos else max_new) - 1)
+        assert [t.cpu().tolist() for t in tok] == [t.cpu().tolist() for t in tok0]
+        assert len(tok[0]) == (G if use_eos else max_new)
+        assert torch.equal(sp, sp0) and torch.equal(rt, rt0)
