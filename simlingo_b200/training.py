@@ -750,6 +750,9 @@ def attach(module: nn.Module, eng: TrainEngine) -> None:
 def ensure_store(root: nn.Module, spec: ModelSpec) -> ParamStore:
     """Builds (once) the flat parameter / gradient store over the whole model and shares its engine with the
     sub-modules that can also be entered on their own (``extract_feature``, ``Qwen2ForCausalLM``)."""
+    cached = root.__dict__.get(_KEY)
+    if cached is not None:
+        return cached.store
     eng = engine_for(root, "", spec)
     for m in root.modules():
         if hasattr(m, "spec") and m is not root and type(m).__name__ in ("InternVLChatModel", "Qwen2ForCausalLM"):

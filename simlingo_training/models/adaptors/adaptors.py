@@ -208,13 +208,29 @@ class LanguageAdaptor(nn.Module):
         label = driving_input.prompt_inference if inference else driving_input.prompt
         ids = label.phrase_ids.long()
         inputs = self.embed_tokens(ids.clamp(min=0, max=self.embed_tokens.num_embeddings - 1))
-        return {"inputs": inputs, "inputs_mask": label.phrase_valid, "_ids": ids, "_ids_mask": label.loss_masking}
+        out = {"inputs": inputs, "inputs_mask": label.phrase_valid, "_ids": ids, "_ids_mask": label.loss_masking}
+        if not inference and torch.is_grad_enabled() and ids.is_cuda and label.loss_masking is not None:
+            # flat indices of the positions that carry a next-token label, taken now (one device sync while the GPU is
+            # idle) instead of after the decoder pass: compute_loss can then be queued without waiting for the forward
+            lab = torch.where(label.loss_masking, ids, -1)[:, 1:]
+            out["_label_rows"] = lab.reshape(-1).ne(-1).nonzero().squeeze(1)
+        return out
 
     def compute_loss(self, adaptor_features: Tensor, adaptor_logits: Tensor, inputs: Dict[str, Tensor],
                      example: DrivingExample) -> Dict[str, Tuple[Tensor, Tensor]]:
         """Per-token CE of position t against id t+1 where ``loss_masking`` is set (ignore elsewhere)."""
         del example
         labels = torch.where(inputs["_ids_mask"], inputs["_ids"], -1)[:, 1:]
+        if adaptor_logits is None and inputs.get("_label_rows") is not None:
+            # fused, sync-free path: label rows were located before the forward pass was queued
+            idx = inputs["_label_rows"]
+            rows = labels.ne(-1)
+            loss = torch.zeros(labels.numel(), device=labels.device, dtype=torch.float32)
+            if idx.numel() > 0:
+                feats = adaptor_features[:, :-1].reshape(-1, adaptor_features.shape[-1]).index_select(0, idx)
+                from simlingo_b200 import training as _tr
+                loss = loss.index_put((idx,), _tr.lm_head_ce(feats, self.lm_head.weight, labels.reshape(-1).index_select(0, idx)))
+            return {"language_loss": (loss.view_as(labels), rows)}
         if adaptor_logits is None:
             # fused path: logits only for the rows that carry a label (never materialises [B, L, vocab])
             rows = labels.ne(-1)

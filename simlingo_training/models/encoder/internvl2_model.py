@@ -70,11 +70,14 @@ class LingoInternVLModel(nn.Module):
                 inputs_embeds = _scatter_rows(inputs_embeds.reshape(batch * seq_len, hidden), rows, wp).view(batch, seq_len, hidden)
 
         # ---- image features -------------------------------------------------------------------------------
+        # host-visible indices first (each is a device sync): taken before the vision tower is queued, so the CPU never
+        # waits on the heavy kernels and can queue the whole forward + loss + backward behind them
+        starts = adaptor_dict["perm"][:, 0].tolist()
         if pixel_values is not None and seq_len != 1 and pixel_values.size(0) > 0:
             BS, T, NP, C, H, W = pixel_values.shape
             assert T == 1, "Only one frame is supported for now"
-            vit_embeds = self.model.extract_feature(pixel_values.reshape(BS * NP, C, H, W)).reshape(-1, hidden)
             rows = (input_ids.reshape(-1) == self.img_context_token_id).nonzero().squeeze(1)
+            vit_embeds = self.model.extract_feature(pixel_values.reshape(BS * NP, C, H, W)).reshape(-1, hidden)
             if rows.numel() != vit_embeds.shape[0]:
                 print(f"warning: {rows.numel()} <IMG_CONTEXT> tokens but {vit_embeds.shape[0]} image features")
                 n = min(rows.numel(), vit_embeds.shape[0])
@@ -84,7 +87,6 @@ class LingoInternVLModel(nn.Module):
 
         adaptor_dict["language_inputs"] = inputs_embeds
         # language tokens sit at the front of the permuted stream; a left-padded row starts at its first valid token
-        starts = adaptor_dict["perm"][:, 0].tolist()
         full = adaptor_dict["inputs"]
         if not (torch.is_grad_enabled() and inputs_embeds.requires_grad):
             for b, i in enumerate(starts):
