@@ -37,6 +37,8 @@ import torch  # noqa: E402
 from simlingo_b200 import spec as S  # noqa: E402
 
 FRAMES_PER_GPU = 64
+# (0.275+0.760 + 0.540+0.230 + 0.279+1.030 + 1.640+0.258) GB / 4 launches, measured once with `ncu --set full` (profiles/)
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 1.253e9
 PROMPT_LEN = 545
 
 
@@ -181,7 +183,10 @@ def gemm_roofline(model, example, peaks, step_fn=None):
     secs = sum(a.elapsed_time(b) for _, a, b in rec) * 1e-3
     ach = flops / secs / 1e12
     return {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(ach, 1), "peak": peaks["tflops"],
-            "unit": "TFLOP/s", "frac": round(ach / peaks["tflops"], 4), "traffic": None, "launches_per_step": len(rec),
+            "unit": "TFLOP/s", "frac": round(ach / peaks["tflops"], 4), "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH,
+            "traffic_note": "dram read+write bytes per launch, mean over the 4 GEMMs of one InternViT layer at M=131200 (qkv, proj, fc1, fc2) from "
+                            "profiles/r01_ncu_gemm2_offline64_summary.txt (ncu --set full); algorithmic bytes of the same 4 launches: 1.216e9",
+            "launches_per_step": len(rec),
             "gemm_flops_per_step": flops, "gemm_ms_per_step": round(secs * 1e3, 3), "peak_source": peaks["src"] + " (sustained cuBLAS bf16)"}
 
 
