@@ -157,7 +157,7 @@ def offline_step(model, example):
     return pred["route"], pred["speed_wps"]
 
 
-def gemm_roofline(model, example, peaks, step_fn=None):
+def gemm_roofline(model, example, peaks, step_fn=None, traffic=None):
     """Times every launch of the tcgen05 GEMM kernel inside one step with CUDA events (on the launch stream)."""
     from simlingo_b200 import lib
     orig = lib.gemm
@@ -183,9 +183,10 @@ def gemm_roofline(model, example, peaks, step_fn=None):
     secs = sum(a.elapsed_time(b) for _, a, b in rec) * 1e-3
     ach = flops / secs / 1e12
     return {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(ach, 1), "peak": peaks["tflops"],
-            "unit": "TFLOP/s", "frac": round(ach / peaks["tflops"], 4), "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH,
-            "traffic_note": "dram read+write bytes per launch, mean over the 4 GEMMs of one InternViT layer at M=131200 (qkv, proj, fc1, fc2) from "
-                            "profiles/r01_ncu_gemm2_offline64_summary.txt (ncu --set full); algorithmic bytes of the same 4 launches: 1.216e9",
+            "unit": "TFLOP/s", "frac": round(ach / peaks["tflops"], 4), "traffic": traffic,
+            "traffic_note": None if traffic is None else
+            "dram read+write bytes per launch, mean over the 4 GEMMs of one InternViT layer at M=131200 (qkv, proj, fc1, fc2) from "
+            "profiles/r01_ncu_gemm2_offline64_summary.txt (ncu --set full); algorithmic bytes of the same 4 launches: 1.216e9",
             "launches_per_step": len(rec),
             "gemm_flops_per_step": flops, "gemm_ms_per_step": round(secs * 1e3, 3), "peak_source": peaks["src"] + " (sustained cuBLAS bf16)"}
 
@@ -694,7 +695,7 @@ def main():
     if rank != 0:
         return
     peaks = measured_peaks()
-    roof = gemm_roofline(model, example, peaks)
+    roof = gemm_roofline(model, example, peaks, traffic=NCU_GEMM_DRAM_BYTES_PER_LAUNCH if args.frames == FRAMES_PER_GPU else None)
     flops_step = B * S.flops_frame(spec, PROMPT_LEN + 30)
     line = {"metric": "vla_forward_frames_per_s", "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
