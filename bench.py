@@ -42,6 +42,25 @@ NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 1.253e9
 PROMPT_LEN = 545
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to file descriptor 1 (constructor banners, NCCL's
+    version line printed from C) is sent to stderr; emit() writes the line to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _pin(t):
     """pinned host memory for the H2D legs (plain memory on a box without a driver: the reference arm runs there too)"""
     return t.pin_memory() if torch.cuda.is_available() else t
@@ -273,7 +292,7 @@ def run_train(args, rank, world, local):
                 "cpu_baseline": {"value": round(sps, 5), "unit": "samples/s", "cores": cores, "kind": "port",
                                  "sample": "1 sample fwd+bwd (fp32 oracle under torch autograd), single run"},
                 "e2e": {"value": round(sps, 5), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -370,7 +389,7 @@ def run_train(args, rank, world, local):
         sps, cores, t = cpu_oracle_train_samples_per_s()
         line["cpu_baseline"] = {"value": round(sps, 5), "unit": "samples/s", "cores": cores, "kind": "port",
                                 "sample": "1 sample fwd+bwd of the same workload (fp32 oracle under torch autograd), single run"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -440,7 +459,7 @@ def run_agent(args, rank, world, local):
                 "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": round(t, 1), "unit": "ms", "cores": cores, "kind": "port", "sample": "one agent step with G=1, fp32 oracle (no KV cache, as the reference)"},
                 "e2e": {"value": round(t, 1), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -494,7 +513,7 @@ def run_agent(args, rank, world, local):
             "ms_per_step": out[1]["p50"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": cfg, "e2e": {"value": out[1]["e2e_p50"], "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 240},
             "gpu_launches": out[1]["launches"] * steps, "latency": {"G=1": out[1], "G=25": out[25]}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_language(args, rank, world, local):
@@ -526,7 +545,7 @@ def run_language(args, rank, world, local):
                 "cpu_baseline": {"value": round(tps, 4), "unit": "tokens/s", "cores": cores, "kind": "port",
                                  "sample": "1 sample, ViT + 4 greedy tokens (no KV cache, as the reference) + 30-query pass, fp32 oracle, single run"},
                 "e2e": {"value": round(tps, 4), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -582,7 +601,7 @@ def run_language(args, rank, world, local):
             "e2e": {"value": round(val2, 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * G * 8,
                     "ms_per_step": round(ms2.item() / args.steps, 2)},
             "gpu_launches": launches, "samples_per_s": round(world * B * args.steps / (ms.item() * 1e-3), 2)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -599,6 +618,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -625,7 +645,7 @@ def main():
                 "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "1 frame per step (2 tiles + 575-token Qwen2 pass), fp32 oracle, median"},
                 "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -709,7 +729,7 @@ def main():
         fps, cores, t = cpu_oracle_frames_per_s(2, 1)
         line["cpu_baseline"] = {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "1 frame (2 tiles + 575-token Qwen2 pass) of the same workload, fp32 oracle, median of 2 after 1 warm-up"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
