@@ -123,6 +123,8 @@ class Engine:
         if self._pool is None:
             self._pool = torch.cuda.graph_pool_handle()
             self._cap_stream = torch.cuda.Stream(device=self.dev)
+        import gc
+        gc.collect()  # as torch.cuda.graph does: no CUDA object may be finalised while the stream is capturing
         torch.cuda.synchronize(self.dev)
         cs = self._cap_stream
         cs.wait_stream(torch.cuda.current_stream())

@@ -349,6 +349,8 @@ class TrainEngine:
             if eng._pool is None:
                 eng._pool = torch.cuda.graph_pool_handle()
                 eng._cap_stream = torch.cuda.Stream(device=eng.dev)
+            import gc
+            gc.collect()  # as torch.cuda.graph does: no CUDA object may be finalised while the stream is capturing
             torch.cuda.synchronize(eng.dev)
             cs = eng._cap_stream
             cs.wait_stream(torch.cuda.current_stream())
@@ -383,7 +385,7 @@ class TrainEngine:
             return False
         rec = self._recs.get(key)
         if rec is not None and rec["version"] != self.store.layout_version:
-            del self._recs[key]
+            self._drop(self._recs.pop(key))
             rec = None
         if rec is not None:
             self._recs[key] = self._recs.pop(key)  # mark as most recently used
@@ -394,10 +396,15 @@ class TrainEngine:
             return False
         same_kind = [k for k in self._recs if k[0] == key[0]]
         if len(same_kind) >= self.max_graph_shapes:   # evict the least recently used shape of this kind
-            old = self._recs.pop(same_kind[0])
-            old.get("saved", {}).pop("graph", None)
-            old.clear()
+            self._drop(self._recs.pop(same_kind[0]))
         return True
+
+    @staticmethod
+    def _drop(rec: dict) -> None:
+        """Release a captured shape now (the record references itself through saved['graph']; left to the cyclic GC it
+        could be torn down in the middle of a later capture, which invalidates that capture)."""
+        rec.get("saved", {}).pop("graph", None)
+        rec.clear()
 
     def vision_forward_auto(self, pixels: Tensor):
         key = ("vis", int(pixels.shape[0]))

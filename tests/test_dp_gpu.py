@@ -1,0 +1,79 @@
+"""Data-parallel training step on 2 GPUs (skipped on a single-GPU box): with the SAME batch on both ranks the bucketed
+NCCL all-reduce + 1/world prescale must reproduce the single-GPU update - every range of the flat gradient buffer is
+reduced exactly once (a range reduced twice would double, a missed range would halve), through the eager launches and
+through the CUDA-graph replays whose backward graphs are split at the bucket boundaries."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from simlingo_b200.optim import FusedAdamW
+from simlingo_b200.spec import tiny_spec
+from tests.helpers import build_drop_in_model, make_case_inputs, to_driving_example
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+spec = tiny_spec(2, 2, 4096)
+model = build_drop_in_model(spec, "internvl2-tiny-dp2", device=f"cuda:{{rank}}").eval()   # eval: no dropout, deterministic
+ex = to_driving_example(make_case_inputs(spec, 2, seed=5, answer_len=16), f"cuda:{{rank}}")
+store = model.param_store()
+store.bucket_bytes = 4 << 20            # several buckets on the tiny model
+store._make_buckets()
+assert len(store._buckets) >= 3, store._buckets
+p0 = store.flat_param.clone()
+
+def run(steps, dp):
+    store.flat_param.copy_(p0)
+    if dp:
+        store.enable_data_parallel()
+    else:
+        store.pg, store.world = None, 1
+        store.layout_version += 1
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], store, lr=1e-3, weight_decay=0.1, max_grad_norm=0.3)
+    for _ in range(steps):
+        opt.zero_grad()
+        model.training_step(ex)["loss"].backward()
+        opt.step()
+    torch.cuda.synchronize()
+    return opt.master.clone(), store.flat_grad.float().clone()
+
+eng = model.__dict__["_slb_train_engine"]
+ref_p, ref_g = run(3, dp=False)          # eager, capture, replay on one GPU
+r0 = eng.graph_replays
+got_p, got_g = run(3, dp=True)           # same with the exchange (graphs re-captured, split at the buckets)
+assert eng.graph_replays > r0 and store.n_allreduce == 3 * len(store._buckets), (eng.graph_replays - r0, store.n_allreduce)
+rel = lambda a, b: ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+for g in store.groups:   # every group separately: a range reduced twice / not at all would show up as 4x / 1x
+    a, b = got_g[g.start:g.end], ref_g[g.start:g.end]
+    assert rel(a, 2 * b) < 2e-2, (g.name, rel(a, 2 * b))
+assert rel(got_g, 2 * ref_g) < 2e-2, rel(got_g, 2 * ref_g)                 # summed over two identical ranks
+# Adam normalises every element to ~lr, so elements whose gradient is rounding noise may flip sign between the two runs:
+# compare the update directions instead of element-wise maxima
+du, dr = got_p - p0.float(), ref_p - p0.float()
+cos = (du * dr).sum() / (du.norm() * dr.norm())
+assert cos > 0.98, cos.item()
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_step_matches_single_gpu():
+    port = 29600 + (os.getpid() % 300)
+    code = _WORKER.format(root=ROOT, port=port)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, out[:600] + ' ..... ' + out[-2500:]
