@@ -132,3 +132,26 @@ def test_graph_replay_matches_eager(setup):
     for loss, grad, _ in res[1:]:
         assert abs(loss - res[0][0]) < 1e-3 * abs(res[0][0])
         assert relerr(grad, res[0][1]) < 2e-2
+
+
+def test_many_shapes_evict_captured_graphs(setup):
+    """Real batches change their padded length: every shape is captured on its second sighting and at most
+    ``max_graph_shapes`` of them stay resident (least recently used evicted) - losses must stay equal to the eager ones."""
+    spec, _, _, _, _, _, model = setup
+    store = model.param_store()
+    eng = model.__dict__["_slb_train_engine"]
+    eng.max_graph_shapes = 2
+    losses = {}
+    for rnd_ in range(3):
+        for ans in (8, 10, 12, 14):
+            ex = to_driving_example(make_case_inputs(spec, 1, seed=40 + ans, answer_len=ans))
+            store.zero_grad()
+            out, _ = model.forward_loss(ex)
+            out.loss.backward()
+            torch.cuda.synchronize()
+            assert torch.isfinite(out.loss) and torch.isfinite(store.flat_grad.float()).all()
+            losses.setdefault(ans, []).append(out.loss.item())
+    assert sum(1 for k in eng._recs if k[0] == "llm") <= 2 and sum(1 for k in eng._recs if k[0] == "vis") <= 2
+    for ans, ls in losses.items():   # eager (1st), captured (2nd), replayed or re-captured (3rd) agree
+        assert max(ls) - min(ls) < 1e-3 * abs(ls[0]), (ans, ls)
+    eng.max_graph_shapes = 4
