@@ -176,37 +176,54 @@ __global__ void vit_assemble_kernel(const bf16* __restrict__ patch_out, const bf
 }
 
 // ------------------------------------------------------------------------------------------------
-// RoPE (rotate_half convention) on q and k + KV-cache write.  One thread per (row, head, d<32).
+// RoPE (rotate_half convention) on q and k + KV-cache write.  One thread per (row, group of 8 rotation pairs): the 8
+// sin / cos values depend on the position only and are reused for every head, all traffic is 16-byte vectors
+// (x[d..d+7] and its rotation partner x[d+32..d+39]); q is rotated in place, rotated k and plain v go to the caches.
 // ------------------------------------------------------------------------------------------------
 __global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, int batch, int lq,
                                      int past, int lmax, int hq, int hkv, float log2_theta, const int* __restrict__ past_dev) {
   if (past_dev) past = *past_dev;
   const int heads = hq + 2 * hkv;
-  const size_t total = (size_t)batch * lq * heads * 32;
+  const size_t total = (size_t)batch * lq * 4;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int d = (int)(idx & 31);
-    const int h = (int)((idx >> 5) % heads);
-    const size_t row = (idx >> 5) / heads;  // b*lq + i
+    const int c = (int)(idx & 3);          // dims 8c .. 8c+7 (and +32)
+    const size_t row = idx >> 2;           // b*lq + i
     const int i = (int)(row % lq), b = (int)(row / lq);
-    bf16* src = qkv + row * (size_t)(heads * 64) + h * 64;
-    const float x0 = __bfloat162float(src[d]), x1 = __bfloat162float(src[d + 32]);
-    if (h < hq + hkv) {
-      const float inv_freq = exp2f(-(float)(2 * d) / 64.0f * log2_theta);
-      float sn, cs;
-      sincosf((float)(past + i) * inv_freq, &sn, &cs);
-      const float o0 = x0 * cs - x1 * sn, o1 = x1 * cs + x0 * sn;
-      if (h < hq) {
-        src[d] = __float2bfloat16(o0);
-        src[d + 32] = __float2bfloat16(o1);
-      } else {
-        bf16* dst = kc + (((size_t)b * hkv + (h - hq)) * lmax + past + i) * 64;
-        dst[d] = __float2bfloat16(o0);
-        dst[d + 32] = __float2bfloat16(o1);
+    float sn[8], cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float inv_freq = exp2f(-(float)(2 * (c * 8 + e)) / 64.0f * log2_theta);
+      sincosf((float)(past + i) * inv_freq, &sn[e], &cs[e]);
+    }
+    bf16* rowp = qkv + row * (size_t)(heads * 64);
+    for (int h = 0; h < heads; ++h) {
+      bf16* src = rowp + h * 64 + c * 8;
+      const uint4 lo = *reinterpret_cast<const uint4*>(src), hi = *reinterpret_cast<const uint4*>(src + 32);
+      if (h >= hq + hkv) {  // v: plain copy into the cache
+        bf16* dst = vc + (((size_t)b * hkv + (h - hq - hkv)) * lmax + past + i) * 64 + c * 8;
+        *reinterpret_cast<uint4*>(dst) = lo;
+        *reinterpret_cast<uint4*>(dst + 32) = hi;
+        continue;
       }
-    } else {
-      bf16* dst = vc + (((size_t)b * hkv + (h - hq - hkv)) * lmax + past + i) * 64;
-      dst[d] = src[d];
-      dst[d + 32] = src[d + 32];
+      float x0[8], x1[8];
+      {
+        const float2 a = unpack_bf16(lo.x), bb = unpack_bf16(lo.y), cc = unpack_bf16(lo.z), d = unpack_bf16(lo.w);
+        x0[0] = a.x; x0[1] = a.y; x0[2] = bb.x; x0[3] = bb.y; x0[4] = cc.x; x0[5] = cc.y; x0[6] = d.x; x0[7] = d.y;
+        const float2 a2 = unpack_bf16(hi.x), b2 = unpack_bf16(hi.y), c2 = unpack_bf16(hi.z), d2 = unpack_bf16(hi.w);
+        x1[0] = a2.x; x1[1] = a2.y; x1[2] = b2.x; x1[3] = b2.y; x1[4] = c2.x; x1[5] = c2.y; x1[6] = d2.x; x1[7] = d2.y;
+      }
+      float o0[8], o1[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        o0[e] = x0[e] * cs[e] - x1[e] * sn[e];
+        o1[e] = x1[e] * cs[e] + x0[e] * sn[e];
+      }
+      uint4 r0, r1;
+      r0.x = pack_bf16(o0[0], o0[1]); r0.y = pack_bf16(o0[2], o0[3]); r0.z = pack_bf16(o0[4], o0[5]); r0.w = pack_bf16(o0[6], o0[7]);
+      r1.x = pack_bf16(o1[0], o1[1]); r1.y = pack_bf16(o1[2], o1[3]); r1.z = pack_bf16(o1[4], o1[5]); r1.w = pack_bf16(o1[6], o1[7]);
+      bf16* dst = (h < hq) ? src : kc + (((size_t)b * hkv + (h - hq)) * lmax + past + i) * 64 + c * 8;
+      *reinterpret_cast<uint4*>(dst) = r0;
+      *reinterpret_cast<uint4*>(dst + 32) = r1;
     }
   }
 }
@@ -515,8 +532,8 @@ extern "C" int slb_vit_assemble(const void* patch_out, const void* cls, const vo
 extern "C" int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, const int32_t* past_dev, int lmax,
                                  int hq, int hkv, float theta, void* stream) {
   SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax, "rope: batch=%d lq=%d past=%d lmax=%d", batch, lq, past, lmax);
-  const size_t total = (size_t)batch * lq * (hq + 2 * hkv) * 32;
-  rope_kv_write_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq, past, lmax, hq, hkv, log2f(theta), past_dev);
+  const size_t total = (size_t)batch * lq * 4;
+  rope_kv_write_kernel<<<grid_for(total, 128), 128, 0, ST(stream)>>>((bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq, past, lmax, hq, hkv, log2f(theta), past_dev);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
