@@ -69,3 +69,32 @@ def test_gpu_preprocess_feeds_the_model():
     pv = preprocess_frames(x)
     cam = pv.view(1, 1, 2, 3, 448, 448)
     assert cam.dtype == torch.bfloat16 and float(cam.float().abs().max()) < 3.0
+
+
+def test_resample_table_properties():
+    """Size-independent properties of the Pillow tables for arbitrary sizes: taps of an output sample sum to one (22-bit
+    fixed point, within the rounding of its taps), windows stay inside the input and move monotonically."""
+    from hypothesis import given, settings, strategies as st
+    from simlingo_b200.preprocess import resample_table, tile_grid
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(8, 1500), st.sampled_from([448, 896]))
+    def check(in_size, out_size):
+        first, count, taps = resample_table(in_size, out_size)
+        assert first.shape == (out_size,) and taps.shape[0] == out_size
+        assert (count >= 1).all() and (first >= 0).all() and (first + count <= in_size).all()
+        assert (np.diff(first) >= 0).all()
+        used = np.arange(taps.shape[1])[None, :] < count[:, None]
+        assert (taps[~used] == 0).all()
+        assert np.abs(taps.sum(1) - (1 << 22)).max() <= taps.shape[1]
+        assert np.array_equal(first, P.resample_coeffs(in_size, out_size)[0])
+
+    check()
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(16, 2000), st.integers(16, 2000))
+    def grid(w, h):
+        gw, gh = tile_grid(w, h)
+        assert (gw, gh) == P.tile_grid(w, h) and 1 <= gw * gh <= 2
+
+    grid()
