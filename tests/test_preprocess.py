@@ -77,7 +77,7 @@ def test_resample_table_properties():
     from hypothesis import given, settings, strategies as st
     from simlingo_b200.preprocess import resample_table, tile_grid
 
-    @settings(max_examples=40, deadline=None)
+    @settings(max_examples=40, deadline=None, derandomize=True)
     @given(st.integers(8, 1500), st.sampled_from([448, 896]))
     def check(in_size, out_size):
         first, count, taps = resample_table(in_size, out_size)
@@ -87,11 +87,17 @@ def test_resample_table_properties():
         used = np.arange(taps.shape[1])[None, :] < count[:, None]
         assert (taps[~used] == 0).all()
         assert np.abs(taps.sum(1) - (1 << 22)).max() <= taps.shape[1]
-        assert np.array_equal(first, P.resample_coeffs(in_size, out_size)[0])
+        if in_size != out_size:  # equal sizes: Pillow skips the pass, the product table is the identity
+            ofirst, ocount, otaps = P.resample_coeffs(in_size, out_size)
+            assert np.array_equal(first, ofirst) and np.array_equal(count, ocount) and np.array_equal(taps, otaps)
+        else:
+            assert np.array_equal(first, np.arange(out_size)) and (count == 1).all()
 
     check()
+    check.hypothesis.inner_test(448, 448)
+    check.hypothesis.inner_test(1024, 896)
 
-    @settings(max_examples=60, deadline=None)
+    @settings(max_examples=60, deadline=None, derandomize=True)
     @given(st.integers(16, 2000), st.integers(16, 2000))
     def grid(w, h):
         gw, gh = tile_grid(w, h)
