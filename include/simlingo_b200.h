@@ -110,6 +110,28 @@ typedef struct { const int32_t* first; const int32_t* count; const int32_t* taps
 int slb_preprocess_frames(const uint8_t* frames, uint8_t* tmp, const slb_resample_table* horiz, const slb_resample_table* vert,
                           void* tiles_out, int batch, int height, int width, int grid_w, int grid_h, void* stream);
 
+/* ---- post-processing behind the path ------------------------------------------------------------
+ * What the reference computes on the host from the predicted route [B,n_route,2] / speed waypoints [B,n_wps,2] (fp32)
+ * before its PID controllers run (team_code/agent_simlingo.py:915-1003, team_code/nav_planner.py:113-130):
+ *   desired speed = 2 * |wps[wp_a] - wps[wp_b]|                              (agent_simlingo.py:944-946, float32)
+ *   aim point     = PchipInterpolator(arc length, origin-prefixed route) sampled every sample_step metres, at index
+ *                   min(int(clip(lookahead_scale * speed*3.6 + lookahead_offset, lookahead_min, lookahead_max)), M-1);
+ *                   the last waypoint when the route is shorter than one step            (agent_simlingo.py:960-1003)
+ *   heading error = wrap(atan2(aim.y, aim.x)) * 180 / pi / 90                            (nav_planner.py:123-130)
+ * out: float64 [B,8] = {desired speed, heading error, aim.x, aim.y, M, look-ahead index, speed, 0} (one 64-byte row per
+ * sample: everything the host-side PID needs in a single read-back).  The PID windows (state) stay on the host
+ * (simlingo_b200/postprocess.py).  speed: fp32 [B] (m/s). */
+typedef struct {
+  int32_t wp_a, wp_b;
+  float lookahead_scale, lookahead_offset, lookahead_min, lookahead_max;
+  double sample_step;
+} slb_control_params;
+int slb_control_inputs(const float* route, const float* speed_wps, const float* speed, int batch, int n_route, int n_wps,
+                       const slb_control_params* params, double* out, void* stream);
+/* DrivingModel.equal_spacing_route (simlingo_training/models/driving.py:330-342) for a whole batch: the origin-prefixed
+ * route re-sampled by linear interpolation at arc lengths 0,1,..,n_out-1 (np.interp semantics).  out: float64 [B,n_out,2] */
+int slb_equal_spacing_route(const float* route, int batch, int n_route, int n_out, double* out, void* stream);
+
 /* ---- elementwise helpers ---- */
 int slb_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);
 int slb_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);

@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libsimlingo_b200.so"
-SOURCES = ["api.cu", "gemm.cu", "gemv.cu", "attention.cu", "attention_vit.cu", "elementwise.cu", "backward.cu", "attention_bwd.cu", "optim_comm.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "gemm.cu", "gemv.cu", "attention.cu", "attention_vit.cu", "elementwise.cu", "backward.cu", "attention_bwd.cu", "optim_comm.cu", "preprocess.cu", "postprocess.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",

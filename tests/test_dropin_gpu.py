@@ -3,6 +3,7 @@ signatures / state_dict keys as the reference) against the committed golden fixt
 own code (tests/golden/make_golden.py).  Tolerance: tokens identical; waypoints / route / loss max rel err 2e-2."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -91,3 +92,25 @@ def test_submodule_entry_points(model):
     with torch.no_grad():
         t_ref, g_ref = O.greedy_sample(sd, spec, x.float(), 3, spec.eos_id, torch.ones(1, 40, dtype=torch.bool))
     assert toks.cpu().tolist() == t_ref.tolist() and grown.shape == g_ref.shape
+
+
+def test_predict_step_resamples_route_like_the_reference(model, golden):
+    """predict_step (reference driving.py:285-328): forward + per-item ``equal_spacing_route`` — here one kernel for the
+    batch (``slb_equal_spacing_route``); the record it keeps must equal the numpy restatement applied to forward's route"""
+    from oracle.postprocess import equal_spacing_route
+    from simlingo_training.utils.custom_types import DrivingExample, DrivingLabel
+    spec, m = model
+    case = [c for c in golden["cases"] if c["kind"] == "forward"][2]   # ragged B=3
+    inp = make_case_inputs(spec, case["B"], case["seed"], case["G_list"], pad_rows=[tuple(p) for p in case["pads"]])
+    di = to_driving_input(inp, "cuda", torch.bfloat16)
+    B = case["B"]
+    run_id = torch.zeros(B, 8, dtype=torch.uint8)
+    run_id[:, :3] = torch.tensor(list(b"r01"), dtype=torch.uint8)
+    label = DrivingLabel(torch.zeros(B, 10, 2), torch.zeros(B, 20, 2), di.prompt, torch.zeros(1), {"k": [0] * B})
+    m.prediction = {}
+    sp, rt, lang, sp_gt, rt_gt, lang_gt = m.predict_step(DrivingExample(di, label, run_id, None))
+    assert rt.dtype == torch.float64 and rt.shape == (B, 20, 2) and rt.is_cuda and lang == case["language"]
+    raw = m.route.float().cpu().numpy()                                  # what forward produced (fp32)
+    want = np.stack([equal_spacing_route(r) for r in raw])
+    np.testing.assert_allclose(rt.cpu().numpy(), want, rtol=0, atol=1e-12)
+    assert m.prediction["path"] == ["r01"] * B and len(m.prediction["route"]) == 1
