@@ -486,21 +486,22 @@ def run_agent(args, rank, world, local):
             torch.cuda.synchronize()
             dev_ms.append(e0.elapsed_time(e1))
         launches = (lib.LAUNCHES - l0) // steps
-        host_out = torch.empty((30, 2), dtype=torch.float32).pin_memory()
-        # end to end as the agent sees it (agent_simlingo.py:470-502, 796-797): the cropped uint8 camera frame (359 x 1024)
-        # leaves pinned host memory, is resized / tiled / normalised on the GPU (slb_preprocess_frames) and goes through
-        # DrivingModel.forward; the 30 predicted waypoints come back to the host
+        # end to end as the agent sees it (agent_simlingo.py:470-502, 796-797, 878): the cropped uint8 camera frame (359 x 1024)
+        # leaves pinned host memory, is resized / tiled / normalised on the GPU (slb_preprocess_frames), goes through
+        # DrivingModel.forward, and the predictions are turned into (steer, throttle, brake) by control_pid: geometry on the
+        # GPU (slb_control_inputs), one 64-byte row back to the host, PID windows on the host
+        from simlingo_b200.postprocess import ControlPID
         from simlingo_b200.preprocess import preprocess_frames
         cam_host = _pin(torch.from_numpy(S.synth_camera(359, 1024, 3 + rank))[None])
+        speed_host = _pin(torch.tensor([4.0]))
+        pid = ControlPID()
         for _ in range(steps + 3):
             t0 = time.perf_counter()
             ex2 = make_example(hb, device)
             cam = preprocess_frames(cam_host.to(device, non_blocking=True)).view(1, 1, 2, 3, 448, 448)
             ex2 = ex2._replace(camera_images=cam)
             sp, rt, lang = model(ex2)
-            host_out[:20].copy_(rt[0].float(), non_blocking=True)
-            host_out[20:].copy_(sp[0].float(), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            steer, throttle, brake = pid.control_pid(rt, speed_host, sp)   # ends with the read-back + stream synchronize
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
         e2e_ms = e2e_ms[3:]
         q = lambda v, p: sorted(v)[min(len(v) - 1, int(p * len(v)))]
@@ -509,10 +510,11 @@ def run_agent(args, rank, world, local):
     if rank != 0:
         return
     hb = host_agent_batch(spec, 1, 99, 1)
-    h2d = 3 * 359 * 1024 + hb["ids"].numel() * 8 + hb["valid"].numel()
+    h2d = 3 * 359 * 1024 + hb["ids"].numel() * 8 + hb["valid"].numel() + 4
     line = {"metric": "agent_step_latency_ms_p50", "value": out[1]["p50"], "unit": "ms", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": out[1]["p50"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": cfg, "e2e": {"value": out[1]["e2e_p50"], "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 240},
+            "config": cfg, "e2e": {"value": out[1]["e2e_p50"], "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
+                             "ends_at": "steer / throttle / brake (control_pid)"},
             "gpu_launches": out[1]["launches"] * steps, "latency": {"G=1": out[1], "G=25": out[25]}}
     emit(line)
 
