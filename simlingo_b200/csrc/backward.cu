@@ -406,20 +406,30 @@ __global__ void rope_bwd_kernel(const float* __restrict__ dq, const float* __res
   }
 }
 
-// delta[b, h, i] = sum_d dO[b*L+i, h*64+d] * O[...]  (one warp per (row, head))
+// delta[b, h, i] = sum_d dO[b*L+i, h*64+d] * O[...]  (8 lanes per (row, head): one 16-byte load of each operand per lane)
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta, int batch, int lq,
                                   int heads) {
   const size_t total = (size_t)batch * lq * heads;
-  const int lane = threadIdx.x & 31;
-  for (size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; w < total; w += ((size_t)gridDim.x * blockDim.x) >> 5) {
-    const int h = (int)(w % heads);
-    const size_t row = w / heads;
-    const size_t off = row * (size_t)(heads * 64) + h * 64 + lane * 2;
-    const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + off));
-    const float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + off));
-    const float s = warp_sum(a.x * b.x + a.y * b.y);
-    const int i = (int)(row % lq), bb = (int)(row / lq);
-    if (lane == 0) delta[((size_t)bb * heads + h) * lq + i] = s;
+  const size_t warp_units = (total + 3) / 4;  // a warp covers 4 consecutive (row, head) units; the tail is masked, not skipped
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  for (size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; w < warp_units; w += ((size_t)gridDim.x * blockDim.x) >> 5) {
+    const size_t u = w * 4 + grp;
+    const bool live = u < total;
+    const int h = live ? (int)(u % heads) : 0;
+    const size_t row = live ? u / heads : 0;
+    float s = 0.f;
+    if (live) {
+      const size_t off = row * (size_t)(heads * 64) + h * 64 + sub * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(o + off);
+      const uint4 b = *reinterpret_cast<const uint4*>(dout + off);
+      const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+      const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+      s = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) + (a3.x * b3.x + a3.y * b3.y);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (live && sub == 0) delta[((size_t)(row / lq) * heads + h) * lq + (row % lq)] = s;
   }
 }
 
@@ -588,7 +598,8 @@ extern "C" int slb_rope_bwd(const float* dq, const float* dk, const float* dv, v
 }
 extern "C" int slb_attn_delta(const void* o, const void* dout, float* delta, int batch, int lq, int heads, void* stream) {
   SLB_CHECK_ARG(batch > 0 && lq > 0 && heads > 0, "attn_delta: bad shape");
-  attn_delta_kernel<<<grid_for((size_t)batch * lq * heads * 32, 256), 256, 0, ST(stream)>>>((const bf16*)o, (const bf16*)dout, delta, batch, lq, heads);
+  SLB_CHECK_ARG(o && dout && delta && (((uintptr_t)o | (uintptr_t)dout) & 15) == 0, "attn_delta: operands must be 16-byte aligned");
+  attn_delta_kernel<<<grid_for((size_t)batch * lq * heads * 8, 256), 256, 0, ST(stream)>>>((const bf16*)o, (const bf16*)dout, delta, batch, lq, heads);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

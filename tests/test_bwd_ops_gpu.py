@@ -199,3 +199,15 @@ def test_ce_and_adamw(lib):
         coef = min(1.0, 0.3 / (g.float().norm().item() + 1e-6))
         q, qm, qv = adamw_step(q, g.float() * coef, qm, qv, step, 3e-3)
         assert relerr(master, q) < 1e-5 and relerr(pb, q) < 1e-2
+
+
+@pytest.mark.parametrize("B,L,H", [(1, 5, 3), (2, 1025, 16), (3, 7, 14)])
+def test_attn_delta_rowwise_dot(lib, B, L, H):
+    """delta[b, h, i] = <dO, O> per (row, head); totals that are not a multiple of the 4 units a warp covers"""
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + L)
+    o = torch.randn(B * L, H * 64, device="cuda", generator=g).bfloat16()
+    do = torch.randn(B * L, H * 64, device="cuda", generator=g).bfloat16()
+    got = lib.attn_delta(o, do, B, L, H)
+    want = (o.float() * do.float()).view(B, L, H, 64).sum(-1).permute(0, 2, 1)
+    assert got.shape == (B, H, L)
+    assert (got - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
