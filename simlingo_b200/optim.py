@@ -24,10 +24,14 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         # torch's LR schedulers with cycle_momentum look for 'betas' in defaults: present above
         self.store = store
-        known = {id(p) for p in store.params.values()}
-        missing = [p for p in params if id(p) not in known]
+        key_of = {id(p): k for k, p in store.params.items()}
+        missing = [p for p in params if p.requires_grad and id(p) not in key_of]
         if missing:
             raise RuntimeError(f"{len(missing)} parameters handed to FusedAdamW are not in the flat parameter store")
+        # (index in param_groups order, flat offset, numel, shape) of every trainable parameter.  Frozen parameters may be
+        # passed too (the reference hands AdamW all of ``self.parameters()``, driving.py:718): they keep their index, so
+        # that state_dict() lines up with a torch.optim.AdamW built the reference's way, and never get any state.
+        self._slices = [(i, *store.offsets[key_of[id(p)]], p.shape) for i, p in enumerate(params) if id(p) in key_of]
         self.max_grad_norm = float(max_grad_norm)
         n = store.numel
         dev = store.flat_param.device
@@ -74,15 +78,49 @@ class FusedAdamW(torch.optim.Optimizer):
         return float(self.sqnorm.sqrt().item()) / self.store.world
 
     def state_dict(self):
-        d = super().state_dict()
-        d["slb"] = dict(master=self.master, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, step=self.step_count)
-        return d
+        """``torch.optim.AdamW`` layout: ``state[i] = {step, exp_avg, exp_avg_sq}`` per parameter index (views into the flat
+        fp32 moment buffers) + ``param_groups``, so Lightning's checkpoint connector — or the reference's own optimizer —
+        can resume from it.  The fp32 master weights travel as an extra ``master`` entry per parameter, which
+        ``torch.optim.Optimizer.load_state_dict`` carries along untouched."""
+        groups = [{**{k: v for k, v in g.items() if k != "params"}, "params": list(range(len(g["params"])))} for g in self.param_groups]
+        state = {}
+        if self.step_count > 0:
+            for i, o, n, shape in self._slices:
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[o:o + n].view(shape),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(shape), "master": self.master[o:o + n].view(shape)}
+        return {"state": state, "param_groups": groups}
 
-    def load_state_dict(self, state_dict):
-        slb = state_dict.pop("slb", None)
-        super().load_state_dict(state_dict)
-        if slb is not None:
-            self.master.copy_(slb["master"]); self.exp_avg.copy_(slb["exp_avg"]); self.exp_avg_sq.copy_(slb["exp_avg_sq"])
-            self.step_count = int(slb["step"])
-            lib.load()
+    @torch.no_grad()
+    def load_state_dict(self, state_dict) -> None:
+        """Accepts its own ``state_dict()`` or one written by ``torch.optim.AdamW`` over the same parameter list (then the
+        master weights are taken from the model's current parameters)."""
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.param_groups[0]["params"]):
+            raise ValueError("optimizer state does not match: expected one parameter group over the same parameter list")
+        for k in ("lr", "betas", "eps", "weight_decay", "initial_lr", "max_lr", "min_lr", "base_momentum", "max_momentum"):
+            if k in groups[0]:
+                self.param_groups[0][k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]
+        state = state_dict["state"]
+        if not state:
+            self.step_count = 0
+            self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+            self.resync_master()
+            return
+        steps = {int(float(state[i]["step"])) for i, *_ in self._slices if i in state}
+        absent = [i for i, *_ in self._slices if i not in state]
+        if absent or len(steps) != 1:
+            raise ValueError(f"optimizer state does not match: {len(absent)} trainable parameters without state, step counts {sorted(steps)}")
+        self.step_count = steps.pop()
+        have_master = all("master" in state[i] for i, *_ in self._slices)
+        for i, o, n, shape in self._slices:
+            e = state[i]
+            if tuple(e["exp_avg"].shape) != tuple(shape):
+                raise ValueError(f"optimizer state does not match: parameter {i} has shape {tuple(shape)}, state {tuple(e['exp_avg'].shape)}")
+            self.exp_avg[o:o + n].view(shape).copy_(e["exp_avg"])
+            self.exp_avg_sq[o:o + n].view(shape).copy_(e["exp_avg_sq"])
+            if have_master:
+                self.master[o:o + n].view(shape).copy_(e["master"])
+        if have_master:
             self.store.flat_param.copy_(self.master)
+        else:
+            self.resync_master()

@@ -236,7 +236,9 @@ class DrivingModel(_Base):
         """AdamW(lr, weight_decay, betas) over all parameters + per-step OneCycleLR (reference :718-732), realised
         by the fused multi-tensor AdamW kernel with fp32 master weights."""
         from simlingo_b200.optim import FusedAdamW
-        optimizer = FusedAdamW([p for p in self.parameters() if p.requires_grad], self.param_store(), lr=self.lr,
+        # all parameters, frozen ones included, exactly as the reference does: the optimizer state indices then line up with a
+        # torch.optim.AdamW checkpoint of the reference (FusedAdamW.state_dict / load_state_dict use that layout)
+        optimizer = FusedAdamW(list(self.parameters()), self.param_store(), lr=self.lr,
                                weight_decay=self.weight_decay, betas=tuple(self.betas),
                                max_grad_norm=float(getattr(self, "gradient_clip_val", 0.0) or 0.0))
         trainer = self.trainer

@@ -182,3 +182,63 @@ def test_world_size_2_gloo():
     for p in procs:
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, out
+
+
+def test_fused_adamw_state_dict_interoperates_with_torch_adamw():
+    """Checkpoint / resume: FusedAdamW.state_dict() has torch.optim.AdamW's layout over the reference's parameter list
+    (all of ``self.parameters()``, frozen ones included: driving.py:718), so either optimizer can resume from the other.
+    Host logic only (CPU store, no kernels)."""
+    from simlingo_b200.optim import FusedAdamW
+    from simlingo_b200.spec import tiny_spec
+    from simlingo_b200.training import ParamStore
+    from tests.helpers import build_drop_in_model
+    spec = tiny_spec(2, 2, 512)
+    model = build_drop_in_model(spec, "internvl2-tiny-optim", device="cpu")
+    store = ParamStore(model, "", spec, bucket_bytes=8 << 20, allow_cpu=True)
+    params = list(model.parameters())
+    trainable = [i for i, p in enumerate(params) if p.requires_grad]
+    assert 0 < len(trainable) < len(params)
+    opt = FusedAdamW(params, store, lr=3e-5, weight_decay=0.1, betas=(0.9, 0.999), max_grad_norm=0.3)
+    assert opt.state_dict()["state"] == {}                       # like torch before the first step
+
+    # a torch AdamW the reference's way (fp32 copies of the same parameter list), two real steps on the trainable ones
+    g = torch.Generator().manual_seed(0)
+    ref_params = [torch.nn.Parameter(p.detach().float().clone(), requires_grad=p.requires_grad) for p in params]
+    ref = torch.optim.AdamW(ref_params, lr=3e-5, weight_decay=0.1, betas=(0.9, 0.999))
+    for _ in range(2):
+        for p in ref_params:
+            p.grad = torch.randn(p.shape, generator=g) if p.requires_grad else None
+        ref.step()
+    sd = ref.state_dict()
+    assert sorted(sd["state"].keys()) == trainable
+
+    opt.load_state_dict(sd)                                      # torch -> fused
+    assert opt.step_count == 2
+    for i, o, n, shape in opt._slices:
+        assert torch.equal(opt.exp_avg[o:o + n].view(shape), sd["state"][i]["exp_avg"])
+        assert torch.equal(opt.exp_avg_sq[o:o + n].view(shape), sd["state"][i]["exp_avg_sq"])
+        assert torch.equal(opt.master[o:o + n].view(shape), params[i].detach().float())   # no master in a torch checkpoint
+
+    out = opt.state_dict()                                       # fused -> torch
+    assert sorted(out["state"].keys()) == trainable and out["param_groups"][0]["params"] == list(range(len(params)))
+    ref2 = torch.optim.AdamW([torch.nn.Parameter(p.detach().float().clone(), requires_grad=p.requires_grad) for p in params], lr=1.0)
+    ref2.load_state_dict(out)
+    assert ref2.param_groups[0]["lr"] == 3e-5 and ref2.param_groups[0]["weight_decay"] == 0.1
+    for i in trainable:
+        st = ref2.state[ref2.param_groups[0]["params"][i]]
+        assert float(st["step"]) == 2.0 and torch.equal(st["exp_avg"], sd["state"][i]["exp_avg"])
+
+    # fused -> fused round trip keeps the fp32 master weights (they differ from the bf16 parameters after real steps)
+    opt.master.add_(1e-4)
+    snap = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in opt.state_dict()["state"][trainable[0]].items()}
+    opt2_model = build_drop_in_model(spec, "internvl2-tiny-optim", device="cpu")
+    opt2 = FusedAdamW(list(opt2_model.parameters()), ParamStore(opt2_model, "", spec, bucket_bytes=8 << 20, allow_cpu=True), lr=1.0)
+    opt2.load_state_dict(opt.state_dict())
+    assert opt2.step_count == 2 and torch.equal(opt2.master, opt.master) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+    assert torch.equal(opt2.store.flat_param, opt.master.bfloat16()) and opt2.param_groups[0]["lr"] == 3e-5
+    assert torch.equal(snap["master"], opt2.state_dict()["state"][trainable[0]]["master"])
+
+    with pytest.raises(ValueError, match="does not match"):
+        bad = ref.state_dict()
+        bad["param_groups"][0]["params"] = bad["param_groups"][0]["params"][:-1]
+        opt.load_state_dict(bad)
