@@ -42,6 +42,16 @@ class FusedAdamW(torch.optim.Optimizer):
         self.step_count = 0
         self.launches = 0
 
+    def check_attached(self) -> None:
+        """The parameters must still live in the flat buffers this optimizer updates.  ``model.load_state_dict`` / ``.to()``
+        rebuild the engines (and with them the flat store), so an optimizer created *before* them would silently update
+        orphaned buffers: create it after loading the weights (the reference's order, train.py:104-111 then trainer.fit)."""
+        flat = self.store.flat_param
+        p = next(iter(self.store.params.values()))
+        if not flat.data_ptr() <= p.data_ptr() < flat.data_ptr() + flat.numel() * flat.element_size():
+            raise RuntimeError("FusedAdamW: the model's parameters no longer live in this optimizer's flat store (the model was re-loaded or "
+                               "moved after the optimizer was created); build the optimizer after load_state_dict / .to()")
+
     def resync_master(self) -> None:
         """After ``load_state_dict`` on the model: take the bf16 parameters as the new fp32 master copy."""
         self.master.copy_(self.store.flat_param)
@@ -56,6 +66,7 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         st = self.store
+        self.check_attached()
         st.wait_exchange()
         g = self.param_groups[0]
         self.step_count += 1

@@ -238,6 +238,12 @@ def test_fused_adamw_state_dict_interoperates_with_torch_adamw():
     assert torch.equal(opt2.store.flat_param, opt.master.bfloat16()) and opt2.param_groups[0]["lr"] == 3e-5
     assert torch.equal(snap["master"], opt2.state_dict()["state"][trainable[0]]["master"])
 
+    # an optimizer whose store no longer backs the parameters (the model was re-flattened behind it) must say so
+    opt.check_attached()
+    ParamStore(model, "", spec, bucket_bytes=8 << 20, allow_cpu=True)          # what a re-load does: a new flat store takes the parameters
+    with pytest.raises(RuntimeError, match="no longer live"):
+        opt.check_attached()
+
     with pytest.raises(ValueError, match="does not match"):
         bad = ref.state_dict()
         bad["param_groups"][0]["params"] = bad["param_groups"][0]["params"][:-1]
