@@ -52,7 +52,6 @@ def test_postprocess_rejects_host_tensors():
         postprocess.equal_spacing_route(torch.zeros(1, 20, 2))
 
 
-# ---------------------------------------------------------------------------------------------- GPU (through the C ABI)
 def _random_routes(n, seed, n_pts=20):
     g = np.random.default_rng(seed)
     ang = np.cumsum(g.normal(0, 0.08, (n, n_pts)), 1) + g.uniform(-np.pi, np.pi, (n, 1))
@@ -61,6 +60,50 @@ def _random_routes(n, seed, n_pts=20):
     return np.cumsum(np.stack([step * np.cos(ang), step * np.sin(ang)], -1), 1).astype(np.float32)
 
 
+def test_oracle_pchip_matches_scipy_on_random_routes():
+    """the restated Fritsch-Carlson / end-rule / power-form evaluation against scipy's PchipInterpolator itself (the
+    third-party piece the reference calls, agent_simlingo.py:986), on 300 seeded routes incl. repeated points, flat
+    segments, reversals and 2- / 5-point polylines"""
+    from scipy.interpolate import PchipInterpolator
+    worst = 0.0
+    for n_pts, n, seed in ((20, 200, 10), (5, 50, 11), (2, 50, 12)):
+        for r in _random_routes(n, seed, n_pts):
+            poly, arc = O.arc_length(r)
+            q = np.arange(0.1, arc[-1], 0.1)
+            if q.shape[0] == 0:
+                assert np.array_equal(O.interpolate_waypoints(r), poly[None, -1])
+                continue
+            want = PchipInterpolator(arc, poly, axis=0)(q)
+            got = O.interpolate_waypoints(r)
+            assert got.shape == want.shape
+            worst = max(worst, float(np.abs(got - want).max()))
+    assert worst <= 1e-12, worst
+
+
+def test_oracle_geometry_properties():
+    """size-independent properties: a straight, already equally spaced route is a fixed point of the resampling; the
+    aim point of a straight route lies on it at the look-ahead arc length; rotating the route rotates the heading error"""
+    straight = np.stack([np.arange(1, 21, dtype=np.float32), np.zeros(20, np.float32)], 1)
+    eq = O.equal_spacing_route(straight)
+    np.testing.assert_allclose(eq[1:], straight[:19] * (1 - 1e-4), atol=3e-3)      # the 1e-4 * k offset shifts samples by < 2 mm
+    assert np.array_equal(eq[0], [0.0, 0.0])
+    wps = np.cumsum(np.full((10, 2), [1.0, 0.0], np.float32), 0)
+    desired, heading, aim = O.control_inputs(straight, wps, np.float32(3.0))
+    assert float(desired) == 4.0 and abs(heading) < 1e-12 and abs(aim[0] - 2.5) < 1e-3 and abs(aim[1]) < 1e-12
+    g = np.random.default_rng(3)
+    ang = np.cumsum(np.full(20, 0.03))
+    base = np.cumsum(np.stack([np.cos(ang), np.sin(ang)], 1), 0).astype(np.float32)   # gentle left curve, 1 m steps
+    _, h0, aim0 = O.control_inputs(base, wps, np.float32(3.0))
+    for theta in g.uniform(-0.5, 0.5, 8):
+        c, s_ = np.cos(theta), np.sin(theta)
+        rot = (base.astype(np.float64) @ np.array([[c, s_], [-s_, c]])).astype(np.float32)
+        _, h, aim = O.control_inputs(rot, wps, np.float32(3.0))
+        assert abs(np.hypot(*aim) - np.hypot(*aim0)) < 1e-4
+        d = (h - h0) * np.pi / 2 - theta                                            # heading error is yaw / (pi / 2)
+        assert abs((d + np.pi) % (2 * np.pi) - np.pi) < 1e-4, (theta, h, h0)
+
+
+# ---------------------------------------------------------------------------------------------- GPU (through the C ABI)
 @pytest.mark.gpu
 def test_control_inputs_kernel_matches_reference_golden():
     from simlingo_b200 import postprocess
