@@ -33,6 +33,20 @@ def test_invalid_arguments_return_error_codes_not_crashes():
     assert L.slb_gemm_bf16(ctypes.byref(g), None) != 0
     assert b"bad shape" in L.slb_last_error()
     assert L.slb_layernorm_fwd(None, None, None, None, 4, 7, ctypes.c_float(1e-6), None, None, None) != 0  # cols % 8
+    # post-processing entry points: argument validation happens before any CUDA call
+    from simlingo_b200.postprocess import ControlParams
+    buf = (ctypes.c_double * 64)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    prm = ControlParams(0, 2, 1.0, 2.0, 24.0, 105.0, 0.1)
+    assert L.slb_control_inputs(ptr, ptr, ptr, 1, 1, 10, ctypes.byref(prm), ptr, None) != 0      # a route needs >= 2 points
+    assert b"route needs" in L.slb_last_error()
+    assert L.slb_control_inputs(ptr, ptr, ptr, 1, 20, 2, ctypes.byref(prm), ptr, None) != 0      # wp_b = 2 outside 2 waypoints
+    assert b"indices out of range" in L.slb_last_error()
+    bad = ControlParams(0, 2, 1.0, 2.0, 24.0, 105.0, 0.0)
+    assert L.slb_control_inputs(ptr, ptr, ptr, 1, 20, 10, ctypes.byref(bad), ptr, None) != 0     # zero sampling step
+    assert L.slb_equal_spacing_route(ptr, 0, 20, 20, ptr, None) != 0 and L.slb_equal_spacing_route(ptr, 1, 64, 20, ptr, None) != 0
+    assert L.slb_attn_delta(ctypes.c_void_p(ptr.value + 2), ptr, ptr, 1, 1, 1, None) != 0          # operands must be 16-byte aligned
+    assert b"16-byte" in L.slb_last_error()
 
 
 def test_state_dict_schema_matches_dropin_module_tree():
