@@ -262,3 +262,26 @@ def test_fused_adamw_state_dict_interoperates_with_torch_adamw():
         bad = ref.state_dict()
         bad["param_groups"][0]["params"] = bad["param_groups"][0]["params"][:-1]
         opt.load_state_dict(bad)
+
+
+def test_every_entry_point_survives_null_arguments():
+    """C-ABI robustness: each declared function called with all-zero arguments must return (an error code, or 0 for an
+    empty job) instead of dereferencing; run in a child process so a crash is a test failure, not a dead test run"""
+    code = r'''
+import ctypes, os, re
+root = {root!r}
+header = open(os.path.join(root, "include", "simlingo_b200.h")).read()
+so = ctypes.CDLL(os.path.join(root, "simlingo_b200", "libsimlingo_b200.so"))
+names = sorted(set(re.findall(r"\b(slb_[a-z0-9_]+)\s*\(", header)) - {{"slb_last_error", "slb_version", "slb_num_sms"}})
+zeros = [ctypes.c_void_p(0)] * 16
+bad = []
+for n in names:
+    f = getattr(so, n); f.restype = ctypes.c_int32
+    rc = f(*zeros)
+    if rc > 0: bad.append((n, rc))
+print("OK", len(names), bad)
+'''.format(root=ROOT)
+    from simlingo_b200 import build
+    build.build()
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("OK") and r.stdout.strip().endswith("[]"), (r.returncode, r.stdout[-300:], r.stderr[-300:])
