@@ -122,3 +122,46 @@ def test_adamw_and_onecycle_match_torch():
         sched.step()
         q, m, v = O.adamw_step(q, g, m, v, step, lr, beta1=beta1)
         assert torch.allclose(q, p.detach(), atol=2e-6, rtol=0)
+
+
+def _grad_summary(key, g):
+    h = 0
+    for ch in key:
+        h = (h * 131 + ord(ch)) % 1000003
+    gen = torch.Generator().manual_seed(h % (2 ** 31))
+    r = torch.randn(g.numel(), generator=gen)
+    return float(g.norm()), float((g.flatten().double() * r.double()).sum()), g.flatten()[:4]
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_oracle_backward_matches_reference_run(tiny, idx, monkeypatch):
+    """autograd through the oracle vs autograd through the reference's own forward_loss (tests/golden/
+    make_golden_grads.py): driving heads / queries / waypoint encoder, every LoRA A / B, and the gradient entering the
+    ViT.  Each gradient is compared through its norm, a seeded random projection and its first values (fp32, 1e-3)."""
+    from simlingo_b200.spec import trainable
+    spec, sd0 = tiny
+    case = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_grads.pt"), weights_only=False)["cases"][idx]
+    sd = {k: v.clone().requires_grad_(trainable(k)) for k, v in sd0.items()}
+    inp = make_case_inputs(spec, case["B"], case["seed"], None, answer_len=16, pad_rows=[tuple(p) for p in case["pads"]])
+    wps, path = inp["labels"]
+    captured = []
+    real = O.extract_feature
+
+    def capture(*a, **k):
+        out = real(*a, **k)
+        out.retain_grad()
+        captured.append(out)
+        return out
+
+    monkeypatch.setattr(O, "extract_feature", capture)
+    loss, _, _ = O.forward_loss(sd, spec, inp["frames"], inp["ids"], inp["valid"], inp["loss_masking"], inp["placeholders"], wps, path)
+    loss.backward()
+    assert torch.allclose(loss.detach(), case["loss"], rtol=1e-5) and len(captured) == 1
+    got = {k: v.grad for k, v in sd.items() if v.grad is not None}
+    got["dvit_embeds"] = captured[0].grad
+    assert len(case["grads"]) == 45
+    for key, ref in case["grads"].items():
+        norm, proj, head = _grad_summary(key, got[key])
+        assert norm == pytest.approx(ref["norm"], rel=1e-3), key
+        assert abs(proj - ref["proj"]) <= 2e-3 * ref["norm"] + 1e-9, key
+        assert torch.allclose(head, ref["head"], rtol=1e-3, atol=1e-3 * ref["norm"] / max(1.0, got[key].numel() ** 0.5) + 1e-12), key
