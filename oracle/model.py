@@ -8,7 +8,15 @@ PARITY PINNING.  The reference ships no tests, golden vectors or fixtures for th
 (SURVEY.md sections 4 and 8c: "parity unpinned"), and its arithmetic lives in third-party code
 that is absent from ``/root/reference`` (HF-Hub ``OpenGVLab/InternVL2-1B`` remote code at an
 unpinned revision, ``transformers==4.46.3``, ``peft==0.13.2``).  The restatement below is
-therefore pinned against the independent implementations that *are* present in this image:
+therefore pinned against outputs of the REFERENCE'S OWN CODE run in the authoring container and against the independent
+implementations that *are* present in this image:
+
+* ``driving.py`` / ``adaptors.py`` / ``internvl2_model.py`` / ``llm.py`` / ``utils.py`` of the reference, imported unmodified by
+  ``tests/golden/make_golden.py`` / ``make_golden_grads.py`` -> ``tests/golden/reference_run.pt`` (forward, greedy tokens,
+  losses) and ``reference_grads.pt`` (gradients) -> ``tests/test_oracle_pinning.py``.
+* InternViT-300M + pixel-shuffle + ``mlp1``  <-> transformers' HF-native InternVL port (``InternVLVisionModel``,
+  ``InternVLModel.pixel_shuffle``, ``InternVLMultiModalProjector``; weights mapped key by key)
+  (``test_oracle_vit_and_projector_match_hf_internvl_port``).
 
 * Qwen2 decoder  <-> ``transformers.Qwen2ForCausalLM`` 5.5.0, eager attention
   (``tests/test_oracle_pinning.py::test_llm_matches_hf_qwen2``) - this is the very class the
