@@ -167,55 +167,90 @@ def test_oracle_backward_matches_reference_run(tiny, idx, monkeypatch):
         assert torch.allclose(head, ref["head"], rtol=1e-3, atol=1e-3 * ref["norm"] / max(1.0, got[key].numel() ** 0.5) + 1e-12), key
 
 
-def test_oracle_vit_and_projector_match_hf_internvl_port(tiny):
-    """InternViT + pixel-shuffle + mlp1 have no reference-side implementation offline (HF-Hub remote code).  An
-    independent one exists in this image: transformers' HF-native InternVL port (``InternVLVisionModel``,
-    ``InternVLModel.pixel_shuffle``, ``InternVLMultiModalProjector`` — different module tree and key names, same
-    architecture; the conversion of OpenGVLab/InternVL2-1B uses ``use_mean_pooling=True`` = no final LayerNorm,
-    ``attention_bias=True``, ``use_qk_norm=False``).  The synthetic weights are mapped key by key and both are run."""
+def _hf_internvl(spec, sd):
+    """transformers' HF-native InternVL vision tower + projector carrying the synthetic weights (mapped key by key);
+    returns (vision model, projector, {reference key: HF parameter})"""
     from transformers.models.internvl import modeling_internvl as M
     from transformers.models.internvl.configuration_internvl import InternVLConfig, InternVLVisionConfig
-    from simlingo_b200.spec import MLP1_PREFIX, VIT_PREFIX, synth_frames
-    spec, sd = tiny
+    from simlingo_b200.spec import MLP1_PREFIX, VIT_PREFIX
     vcfg = InternVLVisionConfig(hidden_size=spec.vit_hidden, num_hidden_layers=spec.vit_layers, num_attention_heads=spec.vit_heads,
                                 intermediate_size=spec.vit_mlp, attention_bias=True, use_qk_norm=False, norm_type="layer_norm",
                                 layer_norm_eps=spec.vit_eps, image_size=(448, 448), patch_size=(14, 14), hidden_act="gelu",
                                 use_mean_pooling=True, attn_implementation="eager")
     hf = M.InternVLVisionModel(vcfg).eval().float()
     E, L = VIT_PREFIX + "embeddings.", VIT_PREFIX + "encoder.layers."
-    m = {"embeddings.cls_token": sd[E + "class_embedding"], "embeddings.position_embeddings": sd[E + "position_embedding"],
-         "embeddings.patch_embeddings.projection.weight": sd[E + "patch_embedding.weight"],
-         "embeddings.patch_embeddings.projection.bias": sd[E + "patch_embedding.bias"]}
+    m = {"embeddings.cls_token": E + "class_embedding", "embeddings.position_embeddings": E + "position_embedding",
+         "embeddings.patch_embeddings.projection.weight": E + "patch_embedding.weight",
+         "embeddings.patch_embeddings.projection.bias": E + "patch_embedding.bias"}
     H = spec.vit_hidden
+    split = {}
     for i in range(spec.vit_layers):
         s_, d_ = f"{L}{i}.", f"encoder.layer.{i}."
         for j, n in enumerate("qkv"):
-            m[d_ + f"attention.{n}_proj.weight"] = sd[s_ + "attn.qkv.weight"][j * H:(j + 1) * H]
-            m[d_ + f"attention.{n}_proj.bias"] = sd[s_ + "attn.qkv.bias"][j * H:(j + 1) * H]
+            split[d_ + f"attention.{n}_proj.weight"] = (s_ + "attn.qkv.weight", j)
+            split[d_ + f"attention.{n}_proj.bias"] = (s_ + "attn.qkv.bias", j)
         for a, b in (("attn.proj", "attention.projection_layer"), ("mlp.fc1", "mlp.fc1"), ("mlp.fc2", "mlp.fc2"),
                      ("norm1", "layernorm_before"), ("norm2", "layernorm_after")):
-            m[d_ + b + ".weight"], m[d_ + b + ".bias"] = sd[s_ + a + ".weight"], sd[s_ + a + ".bias"]
-        m[d_ + "lambda_1"], m[d_ + "lambda_2"] = sd[s_ + "ls1"], sd[s_ + "ls2"]
-    missing = hf.load_state_dict({k: v.float() for k, v in m.items()}, strict=False)
+            m[d_ + b + ".weight"], m[d_ + b + ".bias"] = s_ + a + ".weight", s_ + a + ".bias"
+        m[d_ + "lambda_1"], m[d_ + "lambda_2"] = s_ + "ls1", s_ + "ls2"
+    state = {k: sd[v].detach().float() for k, v in m.items()}
+    state.update({k: sd[v].detach().float()[j * H:(j + 1) * H] for k, (v, j) in split.items()})
+    missing = hf.load_state_dict(state, strict=False)
     assert not missing.unexpected_keys and all(k.startswith("layernorm.") for k in missing.missing_keys), missing
-    assert isinstance(hf.layernorm, torch.nn.Identity)
+    assert isinstance(hf.layernorm, torch.nn.Identity)        # the InternVL2-1B conversion: no final LayerNorm
+    pcfg = InternVLConfig(vision_config=vcfg.to_dict(), text_config=dict(model_type="qwen2", hidden_size=spec.llm_hidden, num_hidden_layers=1,
+                                                                          num_attention_heads=spec.llm_heads, vocab_size=128),
+                          downsample_ratio=0.5, projector_hidden_act="gelu")
+    proj = M.InternVLMultiModalProjector(pcfg).eval().float()
+    pm = {"layer_norm.weight": "0.weight", "layer_norm.bias": "0.bias", "linear_1.weight": "1.weight", "linear_1.bias": "1.bias",
+          "linear_2.weight": "3.weight", "linear_2.bias": "3.bias"}
+    proj.load_state_dict({k: sd[MLP1_PREFIX + v].detach().float() for k, v in pm.items()})
+    named = dict(hf.named_parameters())
+    back = {v: named[k] for k, v in m.items()}
+    back.update({MLP1_PREFIX + v: p for (k, v), p in zip(pm.items(), (dict(proj.named_parameters())[k] for k in pm))})
+    qkv = {k: (named[k], v, j) for k, (v, j) in split.items()}
+
+    def features(px):
+        last = hf(pixel_values=px).last_hidden_state
+        f = M.InternVLModel.pixel_shuffle(None, last[:, 1:].reshape(px.shape[0], 32, 32, -1), scale_factor=0.5)
+        return last, proj(f.reshape(px.shape[0], -1, f.shape[-1]))
+
+    return features, back, qkv
+
+
+def test_oracle_vit_and_projector_match_hf_internvl_port(tiny):
+    """InternViT + pixel-shuffle + mlp1 have no reference-side implementation offline (HF-Hub remote code).  An
+    independent one exists in this image: transformers' HF-native InternVL port (``InternVLVisionModel``,
+    ``InternVLModel.pixel_shuffle``, ``InternVLMultiModalProjector`` — different module tree and key names, same
+    architecture; the conversion of OpenGVLab/InternVL2-1B uses ``use_mean_pooling=True`` = no final LayerNorm,
+    ``attention_bias=True``, ``use_qk_norm=False``).  The synthetic weights are mapped key by key and both are run,
+    forward and backward (gradient of a fixed random functional of the projected tokens w.r.t. every parameter)."""
+    from simlingo_b200.spec import synth_frames, trainable
+    spec, sd0 = tiny
+    features, back, qkv = _hf_internvl(spec, sd0)
     px = synth_frames(spec, 1, 3).flatten(0, 2).float()                   # [2, 3, 448, 448]
-    with torch.no_grad():
-        want = hf(pixel_values=px).last_hidden_state                      # [2, 1025, 1024]
-        got = O.vit_forward(sd, spec, px)
-        assert got.shape == want.shape
-        assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
-        # projector: drop CLS, 32 x 32 grid, HF pixel_shuffle, LayerNorm(4096) -> Linear -> GELU -> Linear
-        pcfg = InternVLConfig(vision_config=vcfg.to_dict(), text_config=dict(model_type="qwen2", hidden_size=spec.llm_hidden, num_hidden_layers=1,
-                                                                              num_attention_heads=spec.llm_heads, vocab_size=128),
-                              downsample_ratio=0.5, projector_hidden_act="gelu")
-        proj = M.InternVLMultiModalProjector(pcfg).eval().float()
-        proj.load_state_dict({"layer_norm.weight": sd[MLP1_PREFIX + "0.weight"].float(), "layer_norm.bias": sd[MLP1_PREFIX + "0.bias"].float(),
-                              "linear_1.weight": sd[MLP1_PREFIX + "1.weight"].float(), "linear_1.bias": sd[MLP1_PREFIX + "1.bias"].float(),
-                              "linear_2.weight": sd[MLP1_PREFIX + "3.weight"].float(), "linear_2.bias": sd[MLP1_PREFIX + "3.bias"].float()})
-        feats = want[:, 1:].reshape(2, 32, 32, -1)
-        feats = M.InternVLModel.pixel_shuffle(None, feats, scale_factor=0.5)
-        want_proj = proj(feats.reshape(2, -1, feats.shape[-1]))
-        got_proj = O.extract_feature(sd, spec, px)
-        assert got_proj.shape == want_proj.shape == (2, spec.tokens_per_tile, spec.llm_hidden)
-        assert (got_proj - want_proj).abs().max().item() <= 2e-4 * want_proj.abs().max().item()
+    sd = {k: v.clone().requires_grad_(trainable(k) and ("vision_model" in k or "mlp1" in k)) for k, v in sd0.items()}
+    want_last, want_proj = features(px)
+    got_last = O.vit_forward(sd, spec, px)
+    got_proj = O.extract_feature(sd, spec, px)
+    assert got_last.shape == want_last.shape == (2, 1025, spec.vit_hidden)
+    assert got_proj.shape == want_proj.shape == (2, spec.tokens_per_tile, spec.llm_hidden)
+    assert (got_last - want_last).abs().max().item() <= 2e-4 * want_last.abs().max().item()
+    assert (got_proj - want_proj).abs().max().item() <= 2e-4 * want_proj.abs().max().item()
+    r = torch.randn(want_proj.shape, generator=torch.Generator().manual_seed(9))
+    (want_proj * r).sum().backward()
+    (got_proj * r).sum().backward()
+    checked, scales = 0, []
+    for key, p in back.items():
+        g, w = sd[key].grad, p.grad
+        assert g is not None and w is not None, key
+        assert (g - w.view_as(g)).abs().max().item() <= 1e-3 * w.abs().max().item() + 1e-6, key
+        scales.append(w.abs().max().item())
+        checked += 1
+    H = spec.vit_hidden
+    for k, (p, key, j) in qkv.items():
+        g = sd[key].grad[j * H:(j + 1) * H]
+        # the key bias has a mathematically zero gradient (softmax is shift invariant): both sides hold ~1e-8 of round-off
+        assert (g - p.grad).abs().max().item() <= 1e-3 * p.grad.abs().max().item() + 1e-6, k
+        checked += 1
+    assert checked == 4 + spec.vit_layers * (12 + 6) + 6 and min(scales) > 1e-4      # the 1e-6 floor is far below every real gradient
