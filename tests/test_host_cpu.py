@@ -285,3 +285,24 @@ print("OK", len(names), bad)
     build.build()
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.startswith("OK") and r.stdout.strip().endswith("[]"), (r.returncode, r.stdout[-300:], r.stderr[-300:])
+
+
+def test_flop_model_reproduces_survey_figures():
+    """``roofline.achieved`` and the model-TFLOP/s figures of bench.py are computed from simlingo_b200.spec's FLOP model;
+    it has to reproduce the ALGORITHMIC figures the scope table states: ViT 1.447 TF per frame (attention
+    0.207), projector 0.0046, LLM pass 0.422 / 0.446 / 0.459 TF at L = 545 / 575 / 591, LM head 0.272 GF per row,
+    frame 1.898 TF, offline config 121.5 TF, training step 42.4 TF per GPU"""
+    from simlingo_b200 import spec as S
+    sp = S.INTERNVL2_1B
+    tf = lambda x: x / 1e12
+    assert tf(S.flops_vit(sp, 2)) == pytest.approx(1.447, abs=2e-3)
+    assert tf(2 * sp.vit_layers * sp.vit_heads * 4 * sp.vit_tokens ** 2 * 64) == pytest.approx(0.207, abs=1e-3)
+    assert tf(S.flops_proj(sp, 2)) == pytest.approx(0.0046, abs=2e-4)
+    for L, want in ((545, 0.422), (575, 0.446), (591, 0.459)):
+        assert tf(S.flops_llm(sp, L)) == pytest.approx(want, abs=1.5e-3), L
+    assert 2 * sp.llm_hidden * sp.vocab / 1e9 == pytest.approx(0.272, abs=1e-3)
+    assert tf(S.flops_frame(sp, 575)) == pytest.approx(1.898, abs=3e-3)
+    assert tf(64 * S.flops_frame(sp, 575)) == pytest.approx(121.5, abs=0.2)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert tf(bench.train_flops(sp, 8, 591)) == pytest.approx(42.4, abs=0.3)
