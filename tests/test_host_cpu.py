@@ -306,3 +306,27 @@ def test_flop_model_reproduces_survey_figures():
     sys.path.insert(0, ROOT)
     import bench
     assert tf(bench.train_flops(sp, 8, 591)) == pytest.approx(42.4, abs=0.3)
+
+
+def test_bench_contract_on_a_cpu_only_host():
+    """bench.py without a GPU: the product arm must refuse (no CPU fallback), the reference arm must print exactly ONE
+    JSON line carrying the contract's keys, with the oracle as a bounded sample on the host cores"""
+    import json
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    bench = os.path.join(ROOT, "bench.py")
+    r = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and r.stdout.strip() == "" and "no CPU fallback" in (r.stdout + r.stderr)
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "vla_forward_frames_per_s" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"] and d["value"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
