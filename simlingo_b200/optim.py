@@ -41,6 +41,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_count = 0
         self.launches = 0
+        self._epoch = store.weights_epoch
 
     def check_attached(self) -> None:
         """The parameters must still live in the flat buffers this optimizer updates.  ``model.load_state_dict`` / ``.to()``
@@ -55,6 +56,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def resync_master(self) -> None:
         """After ``load_state_dict`` on the model: take the bf16 parameters as the new fp32 master copy."""
         self.master.copy_(self.store.flat_param)
+        self._epoch = self.store.weights_epoch
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.store.zero_grad()
@@ -67,6 +69,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         st = self.store
         self.check_attached()
+        if st.weights_epoch != self._epoch:   # the model was re-loaded in place since the last step: its values are the truth
+            self.resync_master()
         st.wait_exchange()
         g = self.param_groups[0]
         self.step_count += 1
@@ -133,5 +137,6 @@ class FusedAdamW(torch.optim.Optimizer):
                 self.master[o:o + n].view(shape).copy_(e["master"])
         if have_master:
             self.store.flat_param.copy_(self.master)
+            self._epoch = self.store.weights_epoch
         else:
             self.resync_master()

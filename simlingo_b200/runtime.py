@@ -44,10 +44,20 @@ def engine_for(module: nn.Module, prefix: str, spec: ModelSpec) -> Engine:
     return eng
 
 
-def invalidate(module: nn.Module) -> None:
+def invalidate(module: nn.Module, in_place: bool = False) -> None:
+    """Drops the cached engines after the parameters changed behind them.  ``in_place`` (``load_state_dict``: values
+    overwritten, storage untouched) keeps the training engine — its flat store still backs the parameters, so optimizers
+    and captured graphs built on it stay valid — and only refreshes what it derived from the weights."""
     for m in module.modules():
         m.__dict__.pop(_KEY, None)
-        m.__dict__.pop("_slb_train_engine", None)
+        tr = m.__dict__.get("_slb_train_engine")
+        if tr is None:
+            continue
+        if in_place and tr.still_attached():
+            if m is tr.root:
+                tr.weights_changed()
+        else:
+            m.__dict__.pop("_slb_train_engine", None)
 
 
 def grad_mode(*tensors: Tensor) -> bool:

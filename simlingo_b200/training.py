@@ -140,6 +140,7 @@ class ParamStore:
         self.managed_keys = {k for g in groups if g.managed for k in g.keys}
         self.accumulate = False          # True once a backward has deposited gradients that must be added to
         self.generation = 0              # bumped by the optimizer: derived inference weights are stale
+        self.weights_epoch = 0           # bumped when the parameters were overwritten from outside (load_state_dict): fp32 masters are stale
         # ---- data-parallel exchange -----------------------------------------------------------------
         self.pg = None
         self.world = 1
@@ -286,6 +287,24 @@ class TrainEngine:
                             torch.cat([self.w(p + f"{n}_proj.base_layer.bias") for n in "qkv"], 0).contiguous()))
             self._frozen = out
         return self._frozen
+
+    def still_attached(self) -> bool:
+        """every trainable parameter is still a view into the flat buffer (False after ``.to()`` / ``.float()``)"""
+        flat = self.store.flat_param
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+        return all(lo <= p.data_ptr() < hi and p.dtype == flat.dtype for p in self.store.params.values())
+
+    def weights_changed(self) -> None:
+        """The parameters were overwritten in place (``load_state_dict``): the flat store and the captured graphs stay valid
+        (same addresses); copies derived from the frozen weights are refreshed in place, inference engines and fp32 master
+        weights are told to resynchronise."""
+        if self._frozen is not None:
+            for i, (w, b) in enumerate(self._frozen):
+                p = f"{LLM_PREFIX}model.layers.{i}.self_attn."
+                torch.cat([self.w(p + f"{n}_proj.base_layer.weight") for n in "qkv"], 0, out=w)
+                torch.cat([self.w(p + f"{n}_proj.base_layer.bias") for n in "qkv"], 0, out=b)
+        self.store.generation += 1
+        self.store.weights_epoch += 1
 
     def _wgrad(self, dy: Tensor, x: Tensor, key: str, alpha: float = 1.0) -> None:
         """grad[key] (+)= alpha * dy^T x      dy [M, out], x [M, in] -> [out, in]"""

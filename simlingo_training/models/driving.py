@@ -99,7 +99,7 @@ class DrivingModel(_Base):
 
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
-        _rt.invalidate(self)
+        _rt.invalidate(self, in_place=True)
         return out
 
     def _apply(self, fn, *a, **k):

@@ -156,3 +156,45 @@ def test_many_shapes_evict_captured_graphs(setup):
         assert max(ls) - min(ls) < 1e-3 * abs(ls[0]), (ans, ls)
     eng.max_graph_shapes = 4
 
+
+
+def test_optimizer_checkpoint_resume(setup):
+    """save after two steps, restore into a fresh model + an optimizer that already exists (in-place load_state_dict keeps
+    the flat store): state restored bit for bit in torch.optim.AdamW's layout, third step of both runs agrees up to the
+    summation order of the fp32 atomics in the small-parameter gradient reductions"""
+    from simlingo_b200.optim import FusedAdamW
+    spec, case, *_ = setup
+    ex = to_driving_example(case)
+
+    def make(name):
+        m = build_drop_in_model(spec, name).eval()
+        return m, FusedAdamW(list(m.parameters()), m.param_store(), lr=3e-3, weight_decay=0.1, max_grad_norm=0.3)
+
+    def step(m, opt):
+        opt.zero_grad()
+        m.forward_loss(ex)[0].loss.backward()
+        opt.step()
+
+    a, opt_a = make("internvl2-tiny-resume-a")
+    step(a, opt_a); step(a, opt_a)
+    ckpt = {"model": {k: v.clone() for k, v in a.state_dict().items()},
+            "optim": {"param_groups": opt_a.state_dict()["param_groups"],
+                      "state": {i: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in e.items()} for i, e in opt_a.state_dict()["state"].items()}}}
+    b, opt_b = make("internvl2-tiny-resume-b")
+    step(b, opt_b)                                   # b has a live training engine, captured shapes and optimizer state of its own
+    store_b = b.param_store()
+    b.load_state_dict(ckpt["model"], strict=True)
+    assert b.param_store() is store_b                # in-place load keeps the flat store (and the optimizer attached to it)
+    opt_b.load_state_dict(ckpt["optim"])
+    assert opt_b.step_count == 2 and torch.equal(opt_b.master, opt_a.master)
+    assert torch.equal(opt_b.exp_avg, opt_a.exp_avg) and torch.equal(b.param_store().flat_param, a.param_store().flat_param)
+    before = opt_a.master.clone()
+    step(a, opt_a); step(b, opt_b)
+    torch.cuda.synchronize()
+    da, db = opt_a.master - before, opt_b.master - before
+    cos = torch.nn.functional.cosine_similarity(da, db, dim=0).item()
+    assert cos > 0.999, (cos, (da - db).abs().max().item())
+    # model-only reload (no optimizer state): the next step starts from the loaded values, not from a stale fp32 master
+    b.load_state_dict(ckpt["model"], strict=True)
+    step(b, opt_b)
+    assert (opt_b.master - before).abs().max().item() <= 2 * 3e-3
