@@ -228,16 +228,16 @@ class Engine:
         ids_np = ids_cpu.numpy()
         for b in range(B):
             special = sorted(set(ids_np[b][ids_np[b] >= s.first_added_id].tolist()))
-            special = [sid for sid in special if sid in placeholder_values[b]]
+            special = [sid for sid in special if int(np.nonzero(ids_np[b] == sid)[0][0]) != 0]  # reference: first_occurrences.nonzero() drops index 0
             if not special:
                 continue
             if len(special) > 1:
-                raise NotImplementedError("more than one placeholder id with values in a prompt")
+                raise NotImplementedError("more than one placeholder id in a prompt (the released configuration only uses <TARGET_POINT>)")
             sid = special[0]
             pos = int(np.nonzero(ids_np[b] == sid)[0][0])
-            if pos == 0:  # reference: first_occurrences.nonzero() drops index 0
-                continue
-            c = np.asarray(placeholder_values[b][sid], dtype=np.float32).reshape(-1, 2)
+            c = np.asarray(placeholder_values[b][sid], dtype=np.float32).reshape(-1, 2)   # KeyError if absent, as internvl2_model.py:80
+            if pos + c.shape[0] > ids_np.shape[1]:
+                raise RuntimeError(f"placeholder run of token {sid} in row {b} does not fit: {pos} + {c.shape[0]} > {ids_np.shape[1]}")
             if n_per and c.shape[0] != n_per:
                 raise NotImplementedError("placeholder runs of different length in one batch")
             n_per = c.shape[0]

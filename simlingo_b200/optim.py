@@ -82,9 +82,13 @@ class FusedAdamW(torch.optim.Optimizer):
             sq = self.sqnorm
             self.launches += 1
         b1, b2 = g["betas"]
-        lib.adamw_fused(self.master, self.exp_avg, self.exp_avg_sq, st.flat_grad, st.flat_param, float(g["lr"]), float(b1), float(b2),
-                        float(g["eps"]), float(g["weight_decay"]), self.step_count, sqnorm=sq, max_norm=clip, prescale=1.0 / st.world)
-        self.launches += 1
+        # normally one range = the whole buffer; parameters that received no gradient this step (a sub-network that did not
+        # run backward, a head torch left without .grad) are skipped as torch.optim.AdamW skips ``p.grad is None``
+        for a, b in st.update_ranges():
+            lib.adamw_fused(self.master[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], st.flat_grad[a:b], st.flat_param[a:b], float(g["lr"]),
+                            float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]), self.step_count, sqnorm=sq, max_norm=clip,
+                            prescale=1.0 / st.world)
+            self.launches += 1
         st.generation += 1
         return loss
 

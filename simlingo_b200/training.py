@@ -150,6 +150,11 @@ class ParamStore:
         self.bucket_bytes = bucket_bytes
         self._make_buckets()
         self.n_allreduce = 0
+        self.require_sync = True       # False inside no_sync(): gradients accumulate locally, no exchange
+        self._reduced = False          # a bucket of the current accumulation window has already been all-reduced
+        self._touched: set = set()     # groups that received gradients since zero_grad (others are skipped by the optimizer)
+        self._inflight: list = []      # captured forward records whose backward has not run yet (TrainEngine._mark_inflight)
+        self._untouched_keys: set = set()  # torch-managed parameters whose .grad was None at the end of the backward
         self.capture = None            # set while a backward is being captured into CUDA graphs (see TrainEngine)
         self.layout_version = 0        # bumped when captured graphs must be thrown away (e.g. DP switched on)
 
@@ -168,9 +173,30 @@ class ParamStore:
 
     # ---- step protocol ------------------------------------------------------------------------------
     def begin_backward(self) -> None:
+        if self._reduced and self.accumulate and self.world > 1:
+            raise RuntimeError(
+                "simlingo_b200: a second backward without zero_grad() while data parallelism is on would add local gradients to "
+                "already all-reduced sums; run every micro-batch but the last one under `with store.no_sync():` (as with DDP)")
+        self.wait_exchange()   # never drop an exchange that is still in flight
         self.small_acc.zero_()
         self._next_bucket = 0
-        self._works = []
+
+    def no_sync(self):
+        """Context manager for gradient accumulation under data parallelism (torch DDP's ``no_sync``): backward passes
+        inside it only accumulate into the flat gradient buffer; the first backward outside it exchanges the sums."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            prev, self.require_sync = self.require_sync, False
+            try:
+                yield
+            finally:
+                self.require_sync = prev
+        return ctx()
+
+    def syncing(self) -> bool:
+        return self.pg is not None and self.world > 1 and self.require_sync
 
     def skip_to_bucket_after(self, gi: int) -> None:
         """After replaying captured segments that already issued every bucket ending at or before group ``gi``."""
@@ -186,6 +212,7 @@ class ParamStore:
         n = g.small_end - g.small_start
         if n > 0:
             lib.flush_f32(self.small_acc[g.acc_start:g.acc_start + n], self.flat_grad[g.small_start:g.small_end], self.accumulate)
+        self._touched.add(gi)
         self.group_ready(gi)
 
     def enable_data_parallel(self, process_group=None) -> None:
@@ -203,6 +230,7 @@ class ParamStore:
         # async_op: NCCL runs on its own stream after an event on the current (compute) stream
         self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
         self.n_allreduce += 1
+        self._reduced = True
 
     def group_ready(self, gi: int) -> None:
         if self.pg is None or self.world == 1:
@@ -212,20 +240,32 @@ class ParamStore:
             self._next_bucket += 1
             if self.capture is not None:
                 self.capture.split(k)   # close the graph segment here; the all-reduce is issued between two replays
-            else:
+            elif self.require_sync:
                 self.launch_bucket(k)
 
     def finish_backward(self) -> None:
         """End-of-backward hook: adopt gradients autograd produced for the torch-managed parameters, expose
         ``p.grad`` views, launch the remaining all-reduce buckets."""
+        dst, src = [], []
         for k, p in self.params.items():
             v = self.grad_view[k]
-            if k not in self.managed_keys and p.grad is not None and p.grad.data_ptr() != v.data_ptr():
-                if self.accumulate:
-                    v.add_(p.grad)
+            if k not in self.managed_keys:
+                if p.grad is None:
+                    if not self.accumulate:
+                        self._untouched_keys.add(k)   # torch.optim.AdamW skips parameters without a gradient
                 else:
-                    v.copy_(p.grad)
+                    self._untouched_keys.discard(k)
+                    if p.grad.data_ptr() != v.data_ptr():
+                        dst.append(v)
+                        src.append(p.grad.to(v.dtype))
             p.grad = v
+        if dst:   # one multi-tensor launch for the ~25 head / query / waypoint-encoder tensors
+            if self.accumulate:
+                torch._foreach_add_(dst, src)
+            else:
+                torch._foreach_copy_(dst, src)
+        if not self.groups[-1].managed:
+            self._touched.add(len(self.groups) - 1)
         self.group_ready(len(self.groups) - 1)
         self.accumulate = True
 
@@ -235,14 +275,48 @@ class ParamStore:
         self._works = []
 
     def zero_grad(self) -> None:
-        """Engine-managed gradients are overwritten by the next backward; the torch-managed tail is zeroed so that
-        autograd can accumulate into the views in place."""
-        g = self.groups[-1]
-        if not g.managed:
-            self.flat_grad[g.start:g.end].zero_()
-        for k, p in self.params.items():
-            p.grad = self.grad_view[k] if k not in self.managed_keys else None
+        """One memset of the whole flat gradient buffer (0.1 ms for 652 MB): engine-managed ranges are overwritten by the
+        next backward that reaches them, but a sub-network that does not run backward in a step (text-only batch, LLM-only
+        call) must not leave last step's gradients behind for the exchange, the clip norm and the optimizer."""
+        self.wait_exchange()
+        self.flat_grad.zero_()
+        for p in self.params.values():
+            p.grad = None   # autograd allocates the few torch-managed gradients afresh; finish_backward adopts them into the views
         self.accumulate = False
+        self._reduced = False
+        self._touched.clear()
+        self._untouched_keys.clear()
+        for rec in self._inflight:     # a forward whose backward never came (evaluation under grad mode) is abandoned here
+            if rec:
+                rec["inflight"] = False
+        self._inflight.clear()
+
+    def update_ranges(self) -> List[Tuple[int, int]]:
+        """Flat ranges the optimizer must update: groups that received gradients since ``zero_grad`` minus torch-managed
+        parameters whose ``.grad`` stayed None (torch.optim.AdamW, which the reference uses, skips those: no weight decay,
+        no moment decay).  One range covering everything in the common case."""
+        if self.pg is not None and self.world > 1:
+            return [(0, self.numel)]   # as DDP: every rank holds the reduced gradient of every parameter
+        out: List[Tuple[int, int]] = []
+
+        def push(a, b):
+            if b <= a:
+                return
+            if out and out[-1][1] == a:
+                out[-1] = (out[-1][0], b)
+            else:
+                out.append((a, b))
+        for gi, g in enumerate(self.groups):
+            if gi not in self._touched:
+                continue
+            if g.managed or not self._untouched_keys:
+                push(g.start, g.end)
+            else:
+                for k in g.keys:
+                    if k not in self._untouched_keys:
+                        o, n = self.offsets[k]
+                        push(o, o + (n + _ALIGN - 1) // _ALIGN * _ALIGN)
+        return out
 
 
 # ====================================================================================================
@@ -272,6 +346,14 @@ class TrainEngine:
         self.graph_replays = 0
         # every captured shape pins its activations in the graph pool (~2.6 GB per sample at the 1B config): keep few
         self.max_graph_shapes = int(os.environ.get("SLB_TRAIN_GRAPH_SHAPES", "4"))
+        # the reference's ``freeze=True`` encoder option (vlm.py:36-44) leaves only mlp1 trainable: the ViT then runs without
+        # saved activations and the backward stops at the projector input
+        vit_keys = [k for k in self.P if k.startswith(VIT_PREFIX)]
+        n_train = sum(1 for k in vit_keys if k in self.store.params)
+        if vit_keys and 0 < n_train < len(vit_keys):
+            raise RuntimeError("simlingo_b200: the InternViT tower must be trainable as a whole or frozen as a whole "
+                               f"({n_train} of {len(vit_keys)} tensors require grad)")
+        self.vit_trainable = n_train > 0
 
     # ---- weights ---------------------------------------------------------------------------------------
     def w(self, key: str) -> Tensor:
@@ -394,7 +476,7 @@ class TrainEngine:
         st = self.store
         for g, k in segments:
             g.replay()
-            if k is not None:
+            if k is not None and st.require_sync:
                 st.launch_bucket(k)
         self.graph_replays += len(segments)
 
@@ -430,6 +512,10 @@ class TrainEngine:
         if not self._graph_ok(key):
             return self._counted(self.vision_forward, pixels)
         rec = self._recs.get(key)
+        if rec is not None and rec.get("inflight"):
+            # this shape's static buffers still hold the activations of a forward whose backward has not run (micro-batches
+            # forwarded back to back, a grad-enabled evaluation forward): do not overwrite them, launch eagerly
+            return self._counted(self.vision_forward, pixels)
         if rec is None:
             rec = dict(version=self.store.layout_version, px=torch.empty_like(pixels), bwd=None)
             cap = TrainEngine._Capture(self)
@@ -441,11 +527,19 @@ class TrainEngine:
         self.launches += rec["fwd_launches"]
         rec["px"].copy_(pixels)
         self._replay(rec["fwd"])
+        self._mark_inflight(rec)
         return rec["out"].detach(), rec["saved"]  # fresh alias of the static output buffer for autograd
+
+    def _mark_inflight(self, rec: dict) -> None:
+        if torch.is_grad_enabled():
+            rec["inflight"] = True
+            self.store._inflight.append(rec)
 
     def vision_backward_auto(self, dout: Tensor, sv) -> None:
         rec = sv.get("graph")
         st = self.store
+        if rec is not None:
+            rec["inflight"] = False
         if rec is None or st.accumulate or rec["version"] != st.layout_version:
             return self._counted(self.vision_backward, dout, sv)
         if rec["bwd"] is None:
@@ -453,17 +547,20 @@ class TrainEngine:
             cap = TrainEngine._Capture(self)
             st.capture = cap
             nb, l0 = st._next_bucket, lib.LAUNCHES
+            touched, st._touched = st._touched, set()
             try:
                 cap.run(lambda: self.vision_backward(rec["dout"], sv))
             finally:
                 st.capture = None
+                rec["bwd_groups"], st._touched = st._touched, touched
             rec["bwd"], rec["bwd_launches"] = cap.segments, lib.LAUNCHES - l0
             rec["keep"].append(cap)
             st._next_bucket = nb
         self.launches += rec["bwd_launches"]
         rec["dout"].copy_(dout)
         self._replay(rec["bwd"])
-        st.skip_to_bucket_after(st.group_index["vit_emb"])
+        st._touched |= rec["bwd_groups"]
+        st.skip_to_bucket_after(max(rec["bwd_groups"]))
 
     def llm_forward_auto(self, inputs: Tensor, mask: Optional[Tensor], dropout: bool):
         B, Lt, _ = inputs.shape
@@ -471,6 +568,8 @@ class TrainEngine:
         if not self._graph_ok(key):
             return self._counted(self.llm_forward, inputs, mask, dropout)
         rec = self._recs.get(key)
+        if rec is not None and rec.get("inflight"):
+            return self._counted(self.llm_forward, inputs, mask, dropout)   # see vision_forward_auto
         if rec is None:
             rec = dict(version=self.store.layout_version, x=torch.empty_like(inputs), bwd=None,
                        mask=None if mask is None else torch.empty_like(mask, dtype=torch.bool))
@@ -486,11 +585,14 @@ class TrainEngine:
         if mask is not None:
             rec["mask"].copy_(mask)
         self._replay(rec["fwd"])
+        self._mark_inflight(rec)
         return rec["out"].detach(), rec["saved"]
 
     def llm_backward_auto(self, dfeats: Tensor, sv) -> Tensor:
         rec = sv.get("graph")
         st = self.store
+        if rec is not None:
+            rec["inflight"] = False
         if rec is None or st.accumulate or rec["version"] != st.layout_version:
             return self._counted(self.llm_backward, dfeats, sv)
         if rec["bwd"] is None:
@@ -498,17 +600,20 @@ class TrainEngine:
             cap = TrainEngine._Capture(self)
             st.capture = cap
             nb, l0 = st._next_bucket, lib.LAUNCHES
+            touched, st._touched = st._touched, set()
             try:
                 rec["dx"] = cap.run(lambda: self.llm_backward(rec["dfeats"], sv))
             finally:
                 st.capture = None
+                rec["bwd_groups"], st._touched = st._touched, touched
             rec["bwd"], rec["bwd_launches"] = cap.segments, lib.LAUNCHES - l0
             rec["keep"].append(cap)
             st._next_bucket = nb
         self.launches += rec["bwd_launches"]
         rec["dfeats"].copy_(dfeats)
         self._replay(rec["bwd"])
-        st.skip_to_bucket_after(st.group_index["llm0"])
+        st._touched |= rec["bwd_groups"]
+        st.skip_to_bucket_after(max(rec["bwd_groups"]))
         return rec["dx"].detach()
 
     # ==================================================================================================
@@ -543,7 +648,8 @@ class TrainEngine:
             fact = lib.gemm(h2, w(p + "mlp.fc1.weight"), bias=w(p + "mlp.fc1.bias"), act=lib.ACT_GELU, aux=fpre, aux_mode=1)
             p2 = lib.gemm(fact, w(p + "mlp.fc2.weight"), bias=w(p + "mlp.fc2.bias"))
             xo = lib.scale_cols_add(p2, w(p + "ls2"), xm)
-            layers.append(dict(x=x, st1=st1, h1=h1, qkv=qkv, lse=lse, att=att, p1=p1, xm=xm, st2=st2, h2=h2, fpre=fpre, fact=fact, p2=p2))
+            if self.vit_trainable:
+                layers.append(dict(x=x, st1=st1, h1=h1, qkv=qkv, lse=lse, att=att, p1=p1, xm=xm, st2=st2, h2=h2, fpre=fpre, fact=fact, p2=p2))
             x = xo
         # projector: drop CLS + pixel shuffle + LN(4096) -> Linear -> GELU -> Linear
         stp = (f32(T * s.tokens_per_tile), f32(T * s.tokens_per_tile))
@@ -551,7 +657,7 @@ class TrainEngine:
         y1p = torch.empty((T * s.tokens_per_tile, s.llm_hidden), device=dev, dtype=bf)
         y1 = lib.gemm(y0, w(MLP1_PREFIX + "1.weight"), bias=w(MLP1_PREFIX + "1.bias"), act=lib.ACT_GELU, aux=y1p, aux_mode=1)
         y2 = lib.gemm(y1, w(MLP1_PREFIX + "3.weight"), bias=w(MLP1_PREFIX + "3.bias"))
-        saved = dict(T=T, cols=cols, layers=layers, xv=x, stp=stp, y0=y0, y1p=y1p, y1=y1)
+        saved = dict(T=T, cols=cols if self.vit_trainable else None, layers=layers, xv=x, stp=stp, y0=y0, y1p=y1p, y1=y1)
         return y2, saved
 
     def vision_backward(self, dy2: Tensor, sv) -> None:
@@ -569,6 +675,8 @@ class TrainEngine:
                                       self._acc(MLP1_PREFIX + "0.weight"), self._acc(MLP1_PREFIX + "0.bias"), T)
         del dy0, dy1p
         st.flush_group("mlp1")
+        if not self.vit_trainable:
+            return   # frozen tower (freeze=True): nothing below the projector needs a gradient (pixels carry none)
         # ---- encoder layers ----
         for i in reversed(range(s.vit_layers)):
             p = f"{VIT_PREFIX}encoder.layers.{i}."
@@ -613,14 +721,14 @@ class TrainEngine:
     # ==================================================================================================
     # Qwen2 decoder stack with un-merged LoRA
     # ==================================================================================================
-    def _lora_a(self, x: Tensor, pre: str, seed: Optional[int]):
-        """t = A dropout(x)   [first half of PEFT lora.Linear.forward]"""
+    def _lora_a(self, x: Tensor, pre: str, seed: Optional[int], seed_t: Optional[Tensor] = None):
+        """t = A dropout(x)   [first half of PEFT lora.Linear.forward]; ``seed_t``: this forward's copy of the step counter"""
         if seed is not None:
-            xd = lib.dropout(x, self.spec.lora_dropout, seed, seed_dev=self.seed_dev)
+            xd = lib.dropout(x, self.spec.lora_dropout, seed, seed_dev=seed_t)
         else:
             xd = x
         t = lib.gemm(xd, self.w(pre + "lora_A.default.weight"))
-        return xd, t, seed
+        return xd, t, seed, seed_t
 
     def _lora_b(self, rec, pre: str, y: Tensor) -> None:
         """y (holding base(x)) += scale * B t"""
@@ -639,7 +747,7 @@ class TrainEngine:
         if rec[2] is None:
             lib.add_inplace(dx, dxd)
         else:
-            lib.dropout_add(dxd, dx, self.spec.lora_dropout, rec[2], seed_dev=self.seed_dev)
+            lib.dropout_add(dxd, dx, self.spec.lora_dropout, rec[2], seed_dev=rec[3])
 
     def llm_forward(self, inputs: Tensor, mask: Optional[Tensor], dropout: bool, static: bool = False):
         """inputs [B, Lt, D] bf16 -> (features after the final norm [B, Lt, D], saved).  ``static``: no host sync on
@@ -658,7 +766,8 @@ class TrainEngine:
             kv_valid = torch.zeros((B, lmax), device=dev, dtype=torch.uint8)
             kv_valid[:, :Lt] = mask.to(torch.uint8)
         use_drop = dropout and s.lora_dropout > 0
-        self.seed_dev.add_(1)  # on the device: a replayed graph draws fresh masks, backward re-reads the same value
+        self.seed_dev.add_(1)  # on the device: a replayed graph draws fresh masks
+        sd_t = self.seed_dev.clone()  # this forward's own copy: its backward regenerates the same masks even if another forward ran since
 
         def seed(i, j):
             return (self.base_seed << 8) + i * 8 + j if use_drop else None
@@ -672,26 +781,26 @@ class TrainEngine:
             r1 = torch.empty(M, device=dev, dtype=torch.float32)
             h1 = lib.rmsnorm(x, w(p + "input_layernorm.weight"), s.rms_eps, rstd=r1)
             qkv = lib.gemm(h1, frozen[i][0], bias=frozen[i][1])
-            lq, lk, lv = self._par(lambda: self._lora_a(h1, pa + "q_proj.", seed(i, 0)), lambda: self._lora_a(h1, pa + "k_proj.", seed(i, 1)),
-                                   lambda: self._lora_a(h1, pa + "v_proj.", seed(i, 2)))
+            lq, lk, lv = self._par(lambda: self._lora_a(h1, pa + "q_proj.", seed(i, 0), sd_t), lambda: self._lora_a(h1, pa + "k_proj.", seed(i, 1), sd_t),
+                                   lambda: self._lora_a(h1, pa + "v_proj.", seed(i, 2), sd_t))
             self._par(lambda: self._lora_b(lq, pa + "q_proj.", qkv[:, :qd]), lambda: self._lora_b(lk, pa + "k_proj.", qkv[:, qd:qd + kd]),
                       lambda: self._lora_b(lv, pa + "v_proj.", qkv[:, qd + kd:]))
             lib.rope_kv_write(qkv, kc[i], vc[i], B, Lt, 0, Hq, Hkv, s.rope_theta)
             lse = torch.empty((B, Hq, Lt), device=dev, dtype=torch.float32)
             att = lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], B, Lt, 0, Hq, Hkv, key_valid=kv_valid, lse=lse)
             xm = lib.gemm(att, w(pa + "o_proj.base_layer.weight"), residual=x)
-            lo = self._lora_a(att, pa + "o_proj.", seed(i, 3))
+            lo = self._lora_a(att, pa + "o_proj.", seed(i, 3), sd_t)
             self._lora_b(lo, pa + "o_proj.", xm)
             r2 = torch.empty(M, device=dev, dtype=torch.float32)
             h2 = lib.rmsnorm(xm, w(p + "post_attention_layernorm.weight"), s.rms_eps, rstd=r2)
             g = lib.gemm(h2, w(pm + "gate_proj.base_layer.weight"))
             u = lib.gemm(h2, w(pm + "up_proj.base_layer.weight"))
-            lg, lu = self._par(lambda: self._lora_a(h2, pm + "gate_proj.", seed(i, 4)), lambda: self._lora_a(h2, pm + "up_proj.", seed(i, 5)))
+            lg, lu = self._par(lambda: self._lora_a(h2, pm + "gate_proj.", seed(i, 4), sd_t), lambda: self._lora_a(h2, pm + "up_proj.", seed(i, 5), sd_t))
             self._lora_b(lg, pm + "gate_proj.", g)
             self._lora_b(lu, pm + "up_proj.", u)
             act = lib.silu_mul(g, u)
             xo = lib.gemm(act, w(pm + "down_proj.base_layer.weight"), residual=xm)
-            ld = self._lora_a(act, pm + "down_proj.", seed(i, 6))
+            ld = self._lora_a(act, pm + "down_proj.", seed(i, 6), sd_t)
             self._lora_b(ld, pm + "down_proj.", xo)
             layers.append(dict(x=x, r1=r1, h1=h1, qkv=qkv, lse=lse, att=att, xm=xm, r2=r2, h2=h2, g=g, u=u, act=act,
                                lora=(lq, lk, lv, lo, lg, lu, ld)))
@@ -797,13 +906,13 @@ def _anchor(eng: TrainEngine, prefix: str) -> Tensor:
 
 def _queue_finish(store: ParamStore) -> None:
     if not getattr(store, "_finish_queued", False):
+        store.begin_backward()   # may refuse (second reduction of the same sums): nothing is queued in that case
         store._finish_queued = True
 
         def cb():
             store._finish_queued = False
             store.finish_backward()
         torch.autograd.Variable._execution_engine.queue_callback(cb)
-        store.begin_backward()
 
 
 class _VisionFn(torch.autograd.Function):

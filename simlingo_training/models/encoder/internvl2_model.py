@@ -59,11 +59,15 @@ class LingoInternVLModel(nn.Module):
             first_pos = {}
             for b, l in hits:
                 first_pos.setdefault((b, int(ids_host[b, l])), l)
-            jobs = [(b, sid, l) for (b, sid), l in sorted(first_pos.items()) if l != 0 and sid in placeholder_values[b]]
+            # as the reference (:80): a special id present in a row (past position 0) without a value for that row is a KeyError
+            jobs = [(b, sid, l) for (b, sid), l in sorted(first_pos.items()) if l != 0]
             if jobs:
                 enc_dtype = wp_encoder.mlp[0].weight.dtype
                 coords = [torch.as_tensor(placeholder_values[b][sid], dtype=torch.float32).reshape(-1, 2) for b, sid, _ in jobs]
                 lengths = [c.shape[0] for c in coords]
+                for (b, sid, l), n in zip(jobs, lengths):
+                    if l + n > seq_len:   # the reference's slice assignment (:91) raises on the size mismatch
+                        raise RuntimeError(f"placeholder run of token {sid} in row {b} does not fit: {l} + {n} > {seq_len}")
                 flat = torch.cat(coords).to(device=input_ids.device).to(enc_dtype)
                 wp = wp_encoder(flat.unsqueeze(0)).squeeze(0).to(inputs_embeds.dtype)
                 rows = torch.cat([torch.arange(l, l + n) + b * seq_len for (b, _, l), n in zip(jobs, lengths)]).to(input_ids.device)

@@ -25,10 +25,12 @@ class LLM(nn.Module):
             raise ValueError(f"Carefull: Variant {self.variant} not tested.")
         self.spec = spec_for_variant(self.variant)
         lora = bool(getattr(self, "lora", False))
-        if lora and (self.lora_r != self.spec.lora_r or self.lora_alpha != self.spec.lora_alpha):
+        if lora:
             import dataclasses
-            self.spec = dataclasses.replace(self.spec, lora_r=self.lora_r, lora_alpha=self.lora_alpha,
-                                            lora_dropout=getattr(self, "lora_dropout", self.spec.lora_dropout))
+            want = dict(lora_r=int(getattr(self, "lora_r", self.spec.lora_r)), lora_alpha=getattr(self, "lora_alpha", self.spec.lora_alpha),
+                        lora_dropout=float(getattr(self, "lora_dropout", self.spec.lora_dropout)))
+            if any(getattr(self.spec, k) != v for k, v in want.items()):   # every LoRA hyper-parameter of the config is honoured (llm.py:106-118)
+                self.spec = dataclasses.replace(self.spec, **want)
         if not lora:
             raise NotImplementedError("simlingo_b200 implements the released configuration (lora=True, all-linear)")
         self.model = Qwen2ForCausalLM(self.spec, lora=True)

@@ -48,15 +48,15 @@ def to_driving_input(case, device=None, dtype=None):
     return DrivingInput(mv(fr), z, z, z, z, z, label, label)
 
 
-def build_drop_in_model(spec, name, seed=0, device="cuda"):
+def build_drop_in_model(spec, name, seed=0, device="cuda", freeze=False, lora_dropout=0.1):
     """DrivingModel (drop-in mirror) on ``spec`` with the deterministic synthetic weights, bf16 on ``device``."""
     from simlingo_b200.modules import register_variant
     from simlingo_b200.spec import init_state_dict
     from simlingo_training.models.driving import DrivingModel
     register_variant(name, spec)
-    cfg = dict(vision_model=dict(_target_="simlingo_training.models.encoder.vlm.VLMEncoderModel", variant=name, embed_dim=512, freeze=False),
+    cfg = dict(vision_model=dict(_target_="simlingo_training.models.encoder.vlm.VLMEncoderModel", variant=name, embed_dim=512, freeze=freeze),
                language_model=dict(_target_="simlingo_training.models.language_model.llm.LLM", variant=name, lora=True, lora_alpha=64,
-                                   lora_r=32, lora_dropout=0.1),
+                                   lora_r=32, lora_dropout=lora_dropout),
                lr=3e-5, weight_decay=0.1, betas=(0.9, 0.999), pct_start=0.05, speed_wps_mode="2d", predict_route_as_wps=True)
     torch.set_default_dtype(torch.bfloat16)
     try:

@@ -60,6 +60,33 @@ assert rel(got_g, 2 * ref_g) < 2e-2, rel(got_g, 2 * ref_g)                 # sum
 du, dr = got_p - p0.float(), ref_p - p0.float()
 cos = (du * dr).sum() / (du.norm() * dr.norm())
 assert cos > 0.98, cos.item()
+# ... and element-wise where the gradient is well above that noise (>= 5 % of the largest element of its group)
+for g in store.groups:
+    b = ref_g[g.start:g.end]
+    big = b.abs() >= 0.05 * b.abs().max()
+    if big.any():
+        a, c = du[g.start:g.end][big], dr[g.start:g.end][big]
+        assert rel(a, c) < 5e-2, (g.name, rel(a, c))
+# gradient accumulation under data parallelism (ADVICE r1): two micro-batches, the first under no_sync(), reduce once
+store.flat_param.copy_(p0)
+opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], store, lr=1e-3, weight_decay=0.1, max_grad_norm=0.3)
+n0 = store.n_allreduce
+opt.zero_grad()
+with store.no_sync():
+    model.training_step(ex)["loss"].backward()
+assert store.n_allreduce == n0
+model.training_step(ex)["loss"].backward()
+store.wait_exchange()
+torch.cuda.synchronize()
+assert store.n_allreduce == n0 + len(store._buckets)
+acc_g = store.flat_grad.float()
+assert rel(acc_g, 4 * ref_g) < 2e-2, rel(acc_g, 4 * ref_g)          # 2 micro-batches x 2 ranks, every range reduced exactly once
+try:
+    model.training_step(ex)["loss"].backward()
+    raise AssertionError("a third backward on already-reduced gradients was accepted")
+except RuntimeError as e:
+    assert "no_sync" in str(e), e
+store.zero_grad()
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)

@@ -181,6 +181,32 @@ store.wait_exchange()
 assert store.n_allreduce == len(store._buckets)
 assert torch.equal(store.flat_grad.float(), torch.full((store.numel,), float(sum(range(1, world + 1)))))
 assert all(p.grad.data_ptr() == store.grad_view[k].data_ptr() for k, p in store.params.items())
+# gradient accumulation under data parallelism: a second backward on already-reduced sums must be refused ...
+try:
+    store.begin_backward()
+    raise AssertionError("second backward after an exchange was accepted")
+except RuntimeError as e:
+    assert "no_sync" in str(e)
+# ... and under no_sync() the exchange is deferred to the last micro-batch: world * (g1 + g2) is never formed
+store.zero_grad()
+assert float(store.flat_grad.abs().max()) == 0.0
+n0 = store.n_allreduce
+with store.no_sync():
+    store.begin_backward()
+    store.flat_grad.add_(float(rank + 1))
+    for gi in range(len(store.groups) - 1):
+        store.group_ready(gi)
+    store.finish_backward()
+assert store.n_allreduce == n0 and store.accumulate
+store.begin_backward()
+store.flat_grad.add_(float(rank + 1))
+for gi in range(len(store.groups) - 1):
+    store.group_ready(gi)
+store.finish_backward()
+store.wait_exchange()
+assert store.n_allreduce == n0 + len(store._buckets)
+assert torch.equal(store.flat_grad.float(), torch.full((store.numel,), 2.0 * sum(range(1, world + 1))))
+assert store.update_ranges() == [(0, store.numel)]
 dist.destroy_process_group()
 print("ok", rank)
 """
@@ -196,6 +222,38 @@ def test_world_size_2_gloo():
     for p in procs:
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, out
+
+
+def test_store_tracks_which_parameters_received_gradients():
+    """torch.optim.AdamW (the reference's optimizer) skips parameters whose .grad is None; the flat store therefore reports
+    to the fused optimizer only the ranges of groups a backward reached since zero_grad, minus torch-managed parameters
+    autograd left without a gradient.  Host logic on a CPU store."""
+    from simlingo_b200.spec import tiny_spec
+    from simlingo_b200.training import ParamStore
+    from tests.helpers import build_drop_in_model
+    spec = tiny_spec(2, 2, 512)
+    model = build_drop_in_model(spec, "internvl2-tiny-touch", device="cpu")
+    store = ParamStore(model, "", spec, bucket_bytes=8 << 20, allow_cpu=True)
+    store.zero_grad()
+    assert store.update_ranges() == []
+    # an LLM-only backward: the two decoder groups and the torch-managed tail, where only the route head got a gradient
+    store.begin_backward()
+    store._touched.update({store.group_index["llm1"], store.group_index["llm0"]})
+    for k, p in store.params.items():
+        if k.startswith("adaptors.driving.route_head"):
+            p.grad = torch.ones_like(p)
+    store.finish_backward()
+    rng = store.update_ranges()
+    g0, g1 = store.groups[store.group_index["llm1"]], store.groups[store.group_index["llm0"]]
+    assert rng[0] == (g1.start if g1.start < g0.start else g0.start, max(g0.end, g1.end))
+    covered = lambda o: any(a <= o < b for a, b in rng)
+    for k in store.params:
+        o, _ = store.offsets[k]
+        want = k.startswith("language_model.") or k.startswith("adaptors.driving.route_head")
+        assert covered(o) == want, k
+    assert float(store.grad_view["adaptors.driving.route_head.0.bias"].min()) == 1.0
+    store.zero_grad()   # everything is cleared again, stale gradients cannot survive a step
+    assert float(store.flat_grad.abs().max()) == 0.0 and store.update_ranges() == []
 
 
 def test_fused_adamw_state_dict_interoperates_with_torch_adamw():
@@ -317,7 +375,7 @@ def test_bench_contract_on_a_cpu_only_host():
     bench = os.path.join(ROOT, "bench.py")
     r = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and r.stdout.strip() == "" and "no CPU fallback" in (r.stdout + r.stderr)
-    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -330,3 +388,9 @@ def test_bench_contract_on_a_cpu_only_host():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the default run carries the other BASELINE configurations as sub-objects (training step, agent step, language mode)
+    for sub, metric, unit in (("train", "vla_train_samples_per_s", "samples/s"), ("agent", "agent_step_latency_ms_p50", "ms"),
+                              ("language", "language_generated_tokens_per_s", "tokens/s")):
+        assert d[sub]["metric"] == metric and d[sub]["unit"] == unit and d[sub]["value"] > 0 and d[sub]["cpu_baseline"]["kind"] == "port", sub
+        assert "workload" in d[sub]["config"]
+    assert d["agent"]["higher_is_better"] is False

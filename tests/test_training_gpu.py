@@ -85,11 +85,19 @@ def test_fused_adamw_step_matches_oracle(setup):
               "language_model.model.base_model.model.model.layers.0.self_attn.q_proj.lora_A.default.weight",
               "language_model.model.base_model.model.model.layers.1.mlp.down_proj.lora_B.default.weight"]:
         p0 = sd[k].detach()
-        ref, _, _ = O.adamw_step(p0, grads_ref[k] * coef, torch.zeros_like(p0), torch.zeros_like(p0), 1, 3e-3)
         o, n = store.offsets[k]
         got = opt.master[o:o + n].view(p0.shape).cpu()
-        # first Adam step moves every element by ~lr * sign(g): compare the updates
-        assert relerr(got - p0, ref - p0) < 5e-2 or ((got - p0).sign() == (ref - p0).sign()).float().mean() > 0.97, k
+        # The first Adam step moves every element by ~lr * sign(g), so elements whose gradient is rounding noise amplify any
+        # gradient difference to a full step; the optimizer kernel is therefore checked on the gradient it actually consumed
+        # (flat bf16 buffer, compared with the oracle's in test_loss_and_gradients_match_oracle): update within 1e-3 ...
+        g_used = store.grad_view[k].float().cpu()
+        coef_used = min(1.0, 0.3 / (opt.grad_norm() + 1e-6))
+        ref, _, _ = O.adamw_step(p0, g_used * coef_used, torch.zeros_like(p0), torch.zeros_like(p0), 1, 3e-3)
+        assert relerr(got - p0, ref - p0) < 1e-3, k
+        # ... and against the oracle's own gradient wherever that gradient is not noise (|g| >= 5 % of the tensor's largest)
+        ref_o, _, _ = O.adamw_step(p0, grads_ref[k] * coef, torch.zeros_like(p0), torch.zeros_like(p0), 1, 3e-3)
+        big = grads_ref[k].abs() >= 0.05 * grads_ref[k].abs().max()
+        assert big.any() and relerr((got - p0)[big], (ref_o - p0)[big]) < 5e-2, k
         assert relerr(named[k], got) < 1e-2
     # the inference engine must see the updated weights (derived LoRA-folded copies are rebuilt)
     with torch.no_grad():
@@ -198,3 +206,101 @@ def test_optimizer_checkpoint_resume(setup):
     b.load_state_dict(ckpt["model"], strict=True)
     step(b, opt_b)
     assert (opt_b.master - before).abs().max().item() <= 2 * 3e-3
+
+
+def test_text_only_step_leaves_no_stale_vision_gradients(setup):
+    """a batch without images (reference internvl2_model.py:133-135, ``pixel_values.size(0) == 0``) never enters the
+    vision backward.  Last step's ViT / mlp1 gradients must not survive into the exchange, the clip norm or the optimizer, and -
+    as with torch.optim.AdamW, which skips ``p.grad is None`` - the ViT weights, their moments and their decay stay untouched."""
+    from simlingo_b200.optim import FusedAdamW
+    from simlingo_b200.spec import VIT_PREFIX, MLP1_PREFIX
+    from simlingo_training.utils.custom_types import DrivingExample, DrivingInput, DrivingLabel, LanguageLabel
+    spec, case, *_, model = setup
+    store = model.param_store()
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], store, lr=1e-3, weight_decay=0.1, max_grad_norm=0.3)
+    ex = to_driving_example(case)
+    opt.zero_grad()
+    model.forward_loss(ex)[0].loss.backward()
+    opt.step()                                     # a normal step: every vision gradient range is now populated
+    vit_keys = [k for k in store.params if k.startswith(VIT_PREFIX) or k.startswith(MLP1_PREFIX)]
+    assert any(float(store.grad_view[k].abs().max()) > 0 for k in vit_keys)
+    # text-only example: the image span removed from the prompt, an empty camera tensor
+    ids = case["ids"]
+    keep = [i for i in range(ids.shape[1]) if int(ids[0, i]) not in (spec.img_context_id, spec.img_start_id, spec.img_end_id)]
+    idx = torch.tensor(keep)
+    cut = lambda t: t[:, idx].cuda()
+    lab = LanguageLabel(cut(case["ids"]), cut(case["valid"]), cut(case["valid"]), case["placeholders"], [""] * ids.shape[0], cut(case["loss_masking"]))
+    z = torch.zeros(ids.shape[0], 1, device="cuda")
+    di = DrivingInput(torch.zeros((0, 1, 2, 3, 448, 448), device="cuda", dtype=torch.bfloat16), z, z, z, z, z, lab, lab)
+    wps, path = case["labels"]
+    ex_text = DrivingExample(di, DrivingLabel(wps.cuda(), path.cuda(), lab, torch.zeros(1)), ["x"] * ids.shape[0])
+    snap = {k: (opt.master[o:o + n].clone(), opt.exp_avg[o:o + n].clone()) for k in vit_keys for o, n in [store.offsets[k]]}
+    lora_key = next(k for k in store.params if ".lora_B." in k)
+    o, n = store.offsets[lora_key]
+    lora_before = opt.master[o:o + n].clone()
+    opt.zero_grad()
+    out, _ = model.forward_loss(ex_text)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.loss)
+    for k in vit_keys:
+        assert float(store.grad_view[k].abs().max()) == 0.0, k
+    opt.step()
+    torch.cuda.synchronize()
+    for k in vit_keys:
+        o2, n2 = store.offsets[k]
+        assert torch.equal(opt.master[o2:o2 + n2], snap[k][0]) and torch.equal(opt.exp_avg[o2:o2 + n2], snap[k][1]), k
+    assert not torch.equal(opt.master[o:o + n], lora_before)   # the decoder's LoRA weights did train
+
+
+def test_frozen_vision_tower_trains_projector_only():
+    """the reference's ``freeze=True`` encoder option (vlm.py:36-44) freezes the ViT and keeps mlp1 trainable.  The
+    backward must stop at the projector, and the gradients of everything that still trains must equal the oracle's."""
+    from oracle import model as O
+    from simlingo_b200.optim import FusedAdamW
+    from simlingo_b200.spec import VIT_PREFIX
+    spec = tiny_spec(2, 2, 4096)
+    case = make_case_inputs(spec, 2, seed=6, answer_len=16)
+    sd = {k: v.clone().requires_grad_(trainable(k) and not k.startswith(VIT_PREFIX)) for k, v in init_state_dict(spec, seed=0).items()}
+    wps, path = case["labels"]
+    loss_ref, _, _ = O.forward_loss(sd, spec, case["frames"], case["ids"], case["valid"], case["loss_masking"], case["placeholders"], wps, path,
+                                    training=False)
+    loss_ref.backward()
+    model = build_drop_in_model(spec, "internvl2-tiny-frozen", freeze=True).eval()
+    store = model.param_store()
+    assert not any(k.startswith(VIT_PREFIX) for k in store.params) and "mlp1" in store.group_index and "vit0" not in store.group_index
+    opt = FusedAdamW(list(model.parameters()), store, lr=1e-3, weight_decay=0.1, max_grad_norm=0.3)
+    ex = to_driving_example(case)
+    vit_before = {k: v.detach().clone() for k, v in model.state_dict().items() if k.startswith(VIT_PREFIX)}
+    for _ in range(3):      # eager, capture, replay
+        opt.zero_grad()
+        out, _ = model.forward_loss(ex)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        assert relerr(out.loss, loss_ref.detach()) < 2e-2
+        worst = {k: relerr(store.grad_view[k], v.grad) for k, v in sd.items() if v.requires_grad and v.grad is not None and v.grad.abs().max() > 0}
+        bad = {k: e for k, e in worst.items() if e > 5e-2}
+        assert len(worst) > 50 and not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:5]
+    opt.step()
+    after = model.state_dict()
+    assert all(torch.equal(after[k], v) for k, v in vit_before.items())
+
+
+def test_lora_dropout_from_config_is_honoured():
+    """a config that changes only ``lora_dropout`` must reach the kernels (0.0: training mode is deterministic)."""
+    spec = tiny_spec(2, 2, 4096)
+    model = build_drop_in_model(spec, "internvl2-tiny-nodrop", lora_dropout=0.0)
+    assert model.language_model.spec.lora_dropout == 0.0 and model.spec.lora_dropout == 0.0
+    ex = to_driving_example(make_case_inputs(spec, 1, seed=8, answer_len=8))
+    store = model.param_store()
+    model.train()
+    losses = []
+    for _ in range(2):
+        store.zero_grad()
+        out, _ = model.forward_loss(ex)
+        out.loss.backward()
+        losses.append(out.loss.item())
+    model.eval()
+    with torch.no_grad():
+        out_eval, _ = model.forward_loss(ex)
+    assert abs(losses[0] - losses[1]) < 1e-3 * abs(losses[0]) and abs(losses[0] - out_eval.loss.item()) < 2e-2 * abs(losses[0])
