@@ -584,11 +584,13 @@ def run_train(args, ctx):
     ms_e2e = ctx.timed_region(e2e_step, args.steps)
     e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
     h2d = sum(hb[k].numel() * hb[k].element_size() for k in ("frames", "ids", "valid", "loss_masking", "wps", "path"))
+    dp_backend = store.dp_backend if world > 1 else None
     line = None
     if rank == 0:
         peaks = measured_peaks()
         teng.graphs_enabled = False  # the per-launch event timing needs the eager launches (the timed region above replays graphs)
         store.pg, store.world = None, 1  # rank 0 alone from here on: no collectives in the roofline pass
+        store.layout_version += 1
         step(example)
         roof = gemm_roofline(peaks, lambda: step(example))
         teng.graphs_enabled = True
@@ -599,7 +601,7 @@ def run_train(args, ctx):
                 "e2e": {"value": round(e2e_val, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": round(ms_e2e / args.steps, 3)},
                 "gpu_launches": launches, "cuda_graph_replays": teng.graph_replays, "clocks": clocks, "roofline": roof, "loss": round(float(loss_host), 4),
-                "n_allreduce": n_ar, "allreduce_bytes_per_step": store.numel * 2 if world > 1 else 0, "allreduce_exposed_ms": exposed, "dp_check": dp_check,
+                "n_allreduce": n_ar, "allreduce_bytes_per_step": store.numel * 2 if world > 1 else 0, "allreduce_exposed_ms": exposed, "dp_backend": dp_backend, "dp_check": dp_check,
                 "model_tflops_per_gpu": round(flops_step * args.steps / (ms * 1e-3) / 1e12, 1),
                 "model_flops_frac_of_peak": round(flops_step * args.steps / (ms * 1e-3) / 1e12 / peaks["tflops"], 4),
                 "algorithmic_tflop_per_step_per_gpu": round(flops_step / 1e12, 2)}
@@ -614,6 +616,8 @@ def run_train(args, ctx):
             line["parity_vs_oracle"] = {"what": "forward_loss of sample 0 at the initial weights (eval mode: LoRA dropout off) vs the fp32 CPU oracle, tolerance 2e-2",
                                         "loss": round(float(out.loss), 4), "loss_oracle": round(loss_ref, 4),
                                         "loss_relerr": round(abs(float(out.loss) - loss_ref) / abs(loss_ref), 5)}
+    if store.comm is not None:
+        store.comm.destroy()
     release(model, opt, teng, store, example)
     return line
 
@@ -797,7 +801,7 @@ def run_language(args, ctx):
 
 # --------------------------------------------------------------------------------------------------
 SUB_KEYS = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "higher_is_better", "dtype", "config", "e2e", "gpu_launches", "roofline",
-            "cpu_baseline", "parity_vs_oracle", "loss", "n_allreduce", "allreduce_bytes_per_step", "allreduce_exposed_ms", "dp_check",
+            "cpu_baseline", "parity_vs_oracle", "loss", "n_allreduce", "allreduce_bytes_per_step", "allreduce_exposed_ms", "dp_backend", "dp_check",
             "model_tflops_per_gpu", "model_flops_frac_of_peak", "algorithmic_tflop_per_step_per_gpu", "cuda_graph_replays", "latency",
             "realtime_budget_ms", "samples_per_s", "clocks", "impl")
 

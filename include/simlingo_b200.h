@@ -139,7 +139,6 @@ int slb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 /* ---- LM head tail: argmax over fp32 logits (llm.py:157-158) ---- */
 int slb_argmax_f32(const float* logits, int64_t ld, int rows, int cols, int64_t* out_idx, float* out_margin,
                    void* stream);
-/* fused softmax cross-entropy over fp32 logits rows: loss[r] = lse - logit[label]; dlogits optional (bf16) */
 /* ---- driving heads (adaptors.py:113-115,130-132,163-180) and wp encoder (adaptors.py:64-93) ----
  * feats [B,30,896] -> route [B,20,2] (896->512->256->2 SiLU, cumsum), speed [B,10,2] (896->256->2), fp32 out */
 typedef struct {
@@ -151,10 +150,6 @@ int slb_driving_heads(const void* feats, int64_t ld_batch, const slb_heads_weigh
 typedef struct { const void *w0, *b0, *w2, *b2, *w4, *b4; } slb_wp_weights;
 int slb_wp_encoder(const float* coords, const slb_wp_weights* w, void* out, int n_points, void* stream);
 
-/* ---- fused multi-tensor AdamW with global-norm clip (driving.py:718-724; train.py:206) ----------
- * flat fp32 master params / moments, bf16 gradient (flat), bf16 model copy written back. */
-/* ---- data-parallel gradient exchange (Lightning DDP / ZeRO-2 in the reference, train.py:160-168) --
- * NCCL communicator handled as an opaque pointer; unique id is a 128-byte blob exchanged by the host. */
 /* ================================ training-only entry points ===================================
  * The reference trains through torch autograd + flash-attn backward + torch.optim.AdamW under Lightning
  * (driving.py:236-271,718-732; train.py:160-217).  dgrad / wgrad GEMMs use slb_gemm_bf16 with b_t / a_t+b_t. */
@@ -206,11 +201,27 @@ int slb_attn_gqa_bwd(const void* q, int64_t ldq, const void* kcache, const void*
  * dlogits (bf16, row stride ldd >= cols, zero padded) = (softmax - onehot) * grad_scale; label < 0 => ignored */
 int slb_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* labels, float* loss, void* dlogits, int64_t ldd,
                    float grad_scale, int rows, int cols, void* stream);
-/* fused AdamW + global-norm clip over flat buffers (driving.py:718-724; train.py:206) */
+/* fused multi-tensor AdamW + global-norm clip over flat buffers (torch.optim.AdamW at driving.py:718-724, Trainer(gradient_clip_val)
+ * at train.py:206): fp32 master parameters / moments, bf16 gradients in, bf16 model copy written back in the same pass;
+ * the gradient is scaled by grad_prescale (1/world under data parallelism) and by min(1, max_norm / (|g| + 1e-6)) */
 int slb_grad_sqnorm(const void* grad_bf16, int64_t n, float* out_sq, void* stream);
 int slb_adamw_fused(float* master, float* m, float* v, const void* grad_bf16, void* param_bf16, int64_t n, float lr,
                     float beta1, float beta2, float eps, float wd, int step, const float* grad_sqnorm, float max_norm,
                     float grad_prescale, void* stream);
+
+/* ---- data-parallel gradient exchange (Lightning DDP / DeepSpeed ZeRO-2 in the reference: train.py:160-168,
+ * train_simlingo_seed1.sh:27) -------------------------------------------------------------------------------------------
+ * One NCCL communicator per process (= per GPU), created and destroyed explicitly; NCCL is resolved at run time
+ * (libnccl.so.2), so nothing here is needed on a single GPU.  The 128-byte unique id comes from slb_comm_unique_id on one
+ * rank and reaches the others through the host (simlingo_b200/dist.py broadcasts it with torch.distributed).
+ * slb_allreduce_bucket: in-place all-reduce of `n` elements (dtype 0 = bf16, 1 = fp32; average 0 = SUM, 1 = mean) enqueued
+ * on `stream`; the training runtime issues one per finished gradient bucket on its own communication stream while the
+ * backward pass continues on the compute stream.  slb_comm_version: NCCL version code, 0 when NCCL cannot be loaded. */
+int slb_comm_version(void);
+int slb_comm_unique_id(void* out_128_bytes /* host */);
+int slb_comm_init(void** comm_out, const void* unique_id_128_bytes /* host */, int rank, int world);
+int slb_comm_destroy(void* comm);
+int slb_allreduce_bucket(void* comm, void* buf, int64_t n, int dtype, int average, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
 """Builds ``libsimlingo_b200.so`` (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-No torch dependency: the library is plain CUDA runtime + (optionally) NCCL; Python reaches it through
+No torch dependency: the library links against the CUDA runtime only (NCCL for the data-parallel exchange is resolved with
+dlsym at run time, csrc/comm.cu); Python reaches it through
 ``ctypes`` (``simlingo_b200/lib.py``).  ``nvcc`` cross-compiles without a GPU."""
 from __future__ import annotations
 
@@ -13,18 +14,11 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libsimlingo_b200.so"
-SOURCES = ["api.cu", "gemm.cu", "gemv.cu", "attention.cu", "attention_vit.cu", "elementwise.cu", "backward.cu", "attention_bwd.cu", "optim_comm.cu", "preprocess.cu", "postprocess.cu"]
+SOURCES = ["api.cu", "gemm.cu", "gemv.cu", "attention.cu", "attention_vit.cu", "elementwise.cu", "backward.cu", "attention_bwd.cu", "optim.cu", "comm.cu", "preprocess.cu", "postprocess.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC",
 ]
-
-
-def _nccl_paths():
-    """NCCL headers ship with the CUDA toolkit here; the runtime library is the torch-bundled one
-    (resolved at load time by lib.py before dlopen of our .so)."""
-    inc = "/usr/local/cuda/include"
-    return inc if os.path.exists(os.path.join(inc, "nccl.h")) else None
 
 
 def _digest(paths) -> str:
@@ -46,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = HERE / "build"
     objdir.mkdir(exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = list(NVCC_FLAGS)
     procs = []
     objs = []
     for s in srcs:
@@ -62,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed for {s.name}:\n{out}")
         if verbose and out:
             print(out)
-    link = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "shared"]
+    link = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "shared", "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

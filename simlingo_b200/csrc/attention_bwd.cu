@@ -51,7 +51,7 @@ struct Trace {
 
 struct BwdParams {
   long long* trace;
-  int variant;  // SLB_BWD_VARIANT (timing experiments only, results are wrong): 1 no dV MMAs, 2 no dK, 4 no dQ, 8 no softmax math
+  int variant;  // always 0 unless built with -DSLB_ABLATION (SLB_BWD_VARIANT timing experiments: 1 no dV MMAs, 2 no dK, 4 no dQ, 8 no softmax math)
   int lq, lkv, past, causal;
   int hq, group;
   int q_col0, k_col0, v_col0;
@@ -422,9 +422,13 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
   if (rc) return rc;
   p.batch = batch;
   p.trace = slb_debug_trace_ptr();
+#ifdef SLB_ABLATION  // timing experiments only (results are wrong by construction): not compiled into the product library
   static int variant = -1;
   if (variant < 0) { const char* ev = getenv("SLB_BWD_VARIANT"); variant = ev ? atoi(ev) : 0; }
   p.variant = variant;
+#else
+  p.variant = 0;
+#endif
   static bool attr_set = false;
   if (!attr_set) {
     SLB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));

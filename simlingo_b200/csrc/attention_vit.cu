@@ -585,9 +585,6 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   const int n_items = ((n_tokens - 1) / (2 * BQ)) * heads * tiles;
   const int grid = n_items < slb_num_sms() ? n_items : slb_num_sms();
-  // SLB_VIT2_VARIANT (timing experiments only, results are wrong): 1 no exp2, 2 no proxy fence, 4 no P stores, 8 short max; 16 = warpgroup turn-taking around the exp phase (valid results; measured: no gain)
-  static int variant = -1;
-  if (variant < 0) { const char* ev = getenv("SLB_VIT2_VARIANT"); variant = ev ? atoi(ev) : 0; }
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal);
     if (e != cudaSuccess) return e;
@@ -595,6 +592,11 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
     return cudaGetLastError();
   };
   cudaError_t e;
+#ifdef SLB_ABLATION
+  // SLB_VIT2_VARIANT (timing experiments only, results are wrong; not compiled into the product library): 1 no exp2, 2 no proxy
+  // fence, 4 no P stores, 8 short max; 16 = warpgroup turn-taking around the exp phase (valid results; measured: no gain)
+  static int variant = -1;
+  if (variant < 0) { const char* ev = getenv("SLB_VIT2_VARIANT"); variant = ev ? atoi(ev) : 0; }
   switch (variant) {
     case 1: e = launch(attn_vit2_kernel<1>); break;
     case 2: e = launch(attn_vit2_kernel<2>); break;
@@ -606,6 +608,9 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
     case 16: e = launch(attn_vit2_kernel<16>); break;
     default: e = launch(attn_vit2_kernel<0>); break;
   }
+#else
+  e = launch(attn_vit2_kernel<0>);
+#endif
   if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_vit2 launch: %s", cudaGetErrorString(e)); return 1; }
   const size_t smem = ((size_t)kClsHeads * 64 + 2 * kClsWarps * kClsHeads + kClsWarps * 256 + (size_t)kClsHeads * n_tokens) * sizeof(float);
   attn_vit_cls_kernel<<<dim3(heads / kClsHeads, tiles), kClsThreads, smem, stream>>>((const bf16*)qkv, (bf16*)out, lse, n_tokens, heads, 0.125f);

@@ -19,9 +19,13 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 
 static int slb_gemm_res_prefetch() {
+#ifdef SLB_ABLATION  // A/B timing switch, not compiled into the product library
   static int v = -1;
   if (v < 0) { const char* e = getenv("SLB_GEMM_NO_RESPF"); v = (e && atoi(e)) ? 0 : 1; }
   return v;
+#else
+  return 1;
+#endif
 }
 
 struct EpiParams {

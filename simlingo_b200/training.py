@@ -150,6 +150,9 @@ class ParamStore:
         self.bucket_bytes = bucket_bytes
         self._make_buckets()
         self.n_allreduce = 0
+        self.comm = None               # simlingo_b200.dist.NativeComm once data parallelism is on with the native backend
+        self.dp_backend = "torch"
+        self._comm_pending = False
         self.require_sync = True       # False inside no_sync(): gradients accumulate locally, no exchange
         self._reduced = False          # a bucket of the current accumulation window has already been all-reduced
         self._touched: set = set()     # groups that received gradients since zero_grad (others are skipped by the optimizer)
@@ -215,22 +218,53 @@ class ParamStore:
         self._touched.add(gi)
         self.group_ready(gi)
 
-    def enable_data_parallel(self, process_group=None) -> None:
+    def enable_data_parallel(self, process_group=None, backend: Optional[str] = None) -> None:
         """Average gradients over the ranks of ``process_group`` (default: the world group): SUM all-reduce of the flat
         bf16 gradient range, bucketed and issued as the backward pass completes each bucket; the 1/world factor is
-        folded into the fused optimizer kernel."""
+        folded into the fused optimizer kernel.
+
+        ``backend``: "native" (default on CUDA) = the library's own NCCL communicator through the C ABI
+        (``slb_comm_init`` / ``slb_allreduce_bucket``, csrc/comm.cu) on a dedicated high-priority stream, bootstrapped over
+        ``process_group``; "torch" = ``torch.distributed.all_reduce`` (what the gloo host-logic tests on CPU use);
+        "native-graph" = native, with the bucket all-reduces captured INSIDE the backward CUDA graphs on a forked stream
+        instead of being issued between graph segments.  Env override: SLB_DP_BACKEND."""
+        import os
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("torch.distributed is not initialised")
+        backend = backend or os.environ.get("SLB_DP_BACKEND") or ("native" if self.flat_grad.is_cuda else "torch")
+        if backend not in ("native", "native-graph", "torch"):
+            raise ValueError(f"unknown data-parallel backend {backend!r}")
         self.pg = process_group if process_group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.pg)
+        self.dp_backend = backend
+        if backend != "torch" and self.world > 1 and self.comm is None:
+            from .dist import NativeComm
+            self.comm = NativeComm(self.pg, self.flat_grad.device)
         self.layout_version += 1
 
-    def launch_bucket(self, k: int) -> None:
+    def disable_data_parallel(self) -> None:
+        self.wait_exchange()
+        self.pg, self.world = None, 1
+        self.layout_version += 1
+
+    def launch_bucket(self, k: int, stream=None) -> None:
+        """All-reduce of bucket ``k`` behind everything queued so far on the current stream."""
         a, b, _ = self._buckets[k]
-        # async_op: NCCL runs on its own stream after an event on the current (compute) stream
-        self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if self.comm is not None and self.dp_backend != "torch":
+            cs = self.comm.stream
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            cs.wait_event(ev)                      # (while capturing: the communication stream joins the capture here)
+            self.comm.all_reduce(self.flat_grad[a:b], stream=cs)
+            self._comm_pending = True
+        else:
+            # async_op: NCCL runs on its own stream after an event on the current (compute) stream
+            self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
         self.n_allreduce += 1
         self._reduced = True
+
+    def in_graph(self) -> bool:
+        return self.comm is not None and self.dp_backend == "native-graph"
 
     def group_ready(self, gi: int) -> None:
         if self.pg is None or self.world == 1:
@@ -239,7 +273,11 @@ class ParamStore:
             k = self._next_bucket
             self._next_bucket += 1
             if self.capture is not None:
-                self.capture.split(k)   # close the graph segment here; the all-reduce is issued between two replays
+                if self.in_graph():
+                    self.launch_bucket(k)   # captured: a forked branch of the backward graph, joined at the end of the capture
+                    self.capture.n_inline += 1
+                else:
+                    self.capture.split(k)   # close the graph segment here; the all-reduce is issued between two replays
             elif self.require_sync:
                 self.launch_bucket(k)
 
@@ -270,9 +308,13 @@ class ParamStore:
         self.accumulate = True
 
     def wait_exchange(self) -> None:
+        """The current stream waits for every exchange in flight (no host blocking)."""
         for w in self._works:
             w.wait()
         self._works = []
+        if self._comm_pending:
+            torch.cuda.current_stream().wait_stream(self.comm.stream)
+            self._comm_pending = False
 
     def zero_grad(self) -> None:
         """One memset of the whole flat gradient buffer (0.1 ms for 652 MB): engine-managed ranges are overwritten by the
@@ -435,6 +477,7 @@ class TrainEngine:
             self.eng = eng
             self.segments: List[Tuple[torch.cuda.CUDAGraph, Optional[int]]] = []
             self.g: Optional[torch.cuda.CUDAGraph] = None
+            self.n_inline = 0   # all-reduces captured inside the graph ("native-graph" backend)
 
         def _begin(self):
             self.g = torch.cuda.CUDAGraph()
@@ -459,6 +502,9 @@ class TrainEngine:
                 self._begin()
                 try:
                     out = fn()
+                    if self.n_inline:   # the forked communication branch must rejoin before the capture ends
+                        cs.wait_stream(eng.store.comm.stream)
+                        eng.store._comm_pending = False
                 finally:
                     self.g.capture_end()
                 self.segments.append((self.g, None))
@@ -476,7 +522,7 @@ class TrainEngine:
         st = self.store
         for g, k in segments:
             g.replay()
-            if k is not None and st.require_sync:
+            if k is not None and st.syncing():
                 st.launch_bucket(k)
         self.graph_replays += len(segments)
 
@@ -540,7 +586,7 @@ class TrainEngine:
         st = self.store
         if rec is not None:
             rec["inflight"] = False
-        if rec is None or st.accumulate or rec["version"] != st.layout_version:
+        if rec is None or st.accumulate or rec["version"] != st.layout_version or (st.in_graph() and not st.require_sync):
             return self._counted(self.vision_backward, dout, sv)
         if rec["bwd"] is None:
             rec["dout"] = torch.empty_like(rec["out"])
@@ -593,7 +639,7 @@ class TrainEngine:
         st = self.store
         if rec is not None:
             rec["inflight"] = False
-        if rec is None or st.accumulate or rec["version"] != st.layout_version:
+        if rec is None or st.accumulate or rec["version"] != st.layout_version or (st.in_graph() and not st.require_sync):
             return self._counted(self.llm_backward, dfeats, sv)
         if rec["bwd"] is None:
             rec["dfeats"] = torch.empty_like(rec["out"])

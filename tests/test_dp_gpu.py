@@ -33,7 +33,7 @@ p0 = store.flat_param.clone()
 def run(steps, dp):
     store.flat_param.copy_(p0)
     if dp:
-        store.enable_data_parallel()
+        store.enable_data_parallel(backend=dp if isinstance(dp, str) else None)
     else:
         store.pg, store.world = None, 1
         store.layout_version += 1
@@ -87,6 +87,14 @@ try:
 except RuntimeError as e:
     assert "no_sync" in str(e), e
 store.zero_grad()
+assert store.dp_backend == "native" and store.comm is not None and store.comm.calls == store.n_allreduce   # the library's own communicator did the work
+# the same exchange with the all-reduces captured inside the backward graphs
+got2_p, got2_g = run(3, dp="native-graph")
+for g in store.groups:
+    a, b = got2_g[g.start:g.end], ref_g[g.start:g.end]
+    assert rel(a, 2 * b) < 2e-2, ("in-graph", g.name, rel(a, 2 * b))
+assert any(c.n_inline > 0 for rec in eng._recs.values() for c in rec.get("keep", []) if hasattr(c, "n_inline"))
+store.comm.destroy()
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)

@@ -330,7 +330,7 @@ import ctypes, os, re
 root = {root!r}
 header = open(os.path.join(root, "include", "simlingo_b200.h")).read()
 so = ctypes.CDLL(os.path.join(root, "simlingo_b200", "libsimlingo_b200.so"))
-names = sorted(set(re.findall(r"\b(slb_[a-z0-9_]+)\s*\(", header)) - {{"slb_last_error", "slb_version", "slb_num_sms"}})
+names = sorted(set(re.findall(r"\b(slb_[a-z0-9_]+)\s*\(", header)) - {{"slb_last_error", "slb_version", "slb_num_sms", "slb_comm_version"}})
 zeros = [ctypes.c_void_p(0)] * 16
 bad = []
 for n in names:
