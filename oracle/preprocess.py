@@ -108,8 +108,9 @@ def pil_resize_bicubic(img_chw: np.ndarray, out_h: int, out_w: int) -> np.ndarra
     return _resample_axis(_resample_axis(img_chw, out_w, 2), out_h, 1)
 
 
-def preprocess_tiles_u8(img_chw: np.ndarray, max_num_grid: int = 2, image_size: int = 448) -> np.ndarray:
-    """-> uint8 [tiles, 3, 448, 448]: the resized image cut into its grid, row-major (internvl2_utils.py:249-262)."""
+def preprocess_tiles_u8(img_chw: np.ndarray, max_num_grid: int = 2, image_size: int = 448, use_thumbnail: bool = False) -> np.ndarray:
+    """-> uint8 [tiles, 3, 448, 448]: the resized image cut into its grid, row-major (internvl2_utils.py:249-262); with
+    ``use_thumbnail`` and more than one tile, the whole image resized to 448 x 448 is appended (:263-265)."""
     _, h, w = img_chw.shape
     gw, gh = tile_grid(w, h, 1, max_num_grid, image_size)
     big = pil_resize_bicubic(img_chw, gh * image_size, gw * image_size)
@@ -117,6 +118,8 @@ def preprocess_tiles_u8(img_chw: np.ndarray, max_num_grid: int = 2, image_size: 
     for i in range(gw * gh):
         x0, y0 = (i % gw) * image_size, (i // gw) * image_size
         tiles.append(big[:, y0:y0 + image_size, x0:x0 + image_size])
+    if use_thumbnail and len(tiles) != 1:
+        tiles.append(pil_resize_bicubic(img_chw, image_size, image_size))
     return np.stack(tiles)
 
 

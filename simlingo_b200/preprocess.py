@@ -78,7 +78,8 @@ def tile_grid(width: int, height: int, min_num: int = 1, max_num: int = 2, image
 
 @lru_cache(maxsize=16)
 def _plan(height: int, width: int, max_num: int, device_index: int):
-    gw, gh = tile_grid(width, height, 1, max_num, 448)
+    """max_num = 0: the 1 x 1 "thumbnail" grid (whole frame resized to one 448 x 448 tile)"""
+    gw, gh = tile_grid(width, height, 1, max_num, 448) if max_num > 0 else (1, 1)
     dev = torch.device("cuda", device_index)
     tabs = []
     for in_size, out_size in ((width, 448 * gw), (height, 448 * gh)):
@@ -88,17 +89,26 @@ def _plan(height: int, width: int, max_num: int, device_index: int):
     return gw, gh, tabs
 
 
-def preprocess_frames(frames: torch.Tensor, max_num_grid: int = 2) -> torch.Tensor:
-    """frames uint8 [B, 3, H, W] (CUDA) -> bf16 [B, tiles, 3, 448, 448]"""
+def preprocess_frames(frames: torch.Tensor, max_num_grid: int = 2, use_global_img: bool = False) -> torch.Tensor:
+    """frames uint8 [B, 3, H, W] (CUDA) -> bf16 [B, tiles, 3, 448, 448].  ``use_global_img``: the reference's thumbnail
+    (``dynamic_preprocess(use_thumbnail=True)``, internvl2_utils.py:262-265): when the grid has more than one tile, the whole
+    frame resized to 448 x 448 is appended as an extra tile (same resampler, 1 x 1 grid)."""
     if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[1] == 3):
         raise RuntimeError("simlingo_b200.preprocess: frames must be a uint8 CUDA tensor [B, 3, H, W] (no CPU fallback)")
     frames = frames.contiguous()
     B, _, H, W = frames.shape
-    gw, gh, tabs = _plan(H, W, max_num_grid, frames.device.index or 0)
-    tmp = torch.empty((B, 3, H, 448 * gw), device=frames.device, dtype=torch.uint8)
-    out = torch.empty((B, gw * gh, 3, 448, 448), device=frames.device, dtype=torch.bfloat16)
-    lib._check(lib.load().slb_preprocess_frames(lib._p(frames), lib._p(tmp), C.byref(tabs[0][1]), C.byref(tabs[1][1]), lib._p(out), B, H, W, gw, gh,
-                                               lib._stream()), "preprocess_frames", 2)
+
+    def run(max_num):
+        gw, gh, tabs = _plan(H, W, max_num, frames.device.index or 0)
+        tmp = torch.empty((B, 3, H, 448 * gw), device=frames.device, dtype=torch.uint8)
+        out = torch.empty((B, gw * gh, 3, 448, 448), device=frames.device, dtype=torch.bfloat16)
+        lib._check(lib.load().slb_preprocess_frames(lib._p(frames), lib._p(tmp), C.byref(tabs[0][1]), C.byref(tabs[1][1]), lib._p(out), B, H, W, gw, gh,
+                                                   lib._stream()), "preprocess_frames", 2)
+        return out
+
+    out = run(max_num_grid)
+    if use_global_img and out.shape[1] != 1:
+        out = torch.cat([out, run(0)], dim=1)
     return out
 
 
@@ -108,10 +118,8 @@ def preprocess_image_batch(images_batch_list: Union[Sequence[torch.Tensor], torc
     {'pixel_values': [B, tiles, 3, 448, 448] bf16 on the GPU, 'image_sizes': [B, 2] (height, width)}."""
     if input_size != 448:
         raise NotImplementedError("InternVL2-1B tiles are 448 x 448")
-    if use_global_img:
-        raise NotImplementedError("use_global_img=True (thumbnail tile) is not used by the released SimLingo configuration")
     imgs: List[torch.Tensor] = list(images_batch_list) if not torch.is_tensor(images_batch_list) else list(images_batch_list.unbind(0))
     dev = torch.device(device) if device is not None else (imgs[0].device if imgs[0].is_cuda else torch.device("cuda", torch.cuda.current_device()))
     batch = torch.stack([i.to(torch.uint8) for i in imgs]).to(dev, non_blocking=True)
     sizes = torch.tensor([[int(i.shape[1]), int(i.shape[2])] for i in imgs])
-    return {"pixel_values": preprocess_frames(batch, max_num_grid), "image_sizes": sizes}
+    return {"pixel_values": preprocess_frames(batch, max_num_grid, use_global_img), "image_sizes": sizes}

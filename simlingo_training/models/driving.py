@@ -125,7 +125,7 @@ class DrivingModel(_Base):
         adaptor_dict = self.adaptors(example, inference=True)
         adaptor_dict = self.vision_model.image_encoder.replace_placeholder_tokens(
             adaptor_dict=adaptor_dict,
-            pixel_values=driving_input.camera_images,
+            pixel_values=self._pixels(driving_input),
             placeholder_values=driving_input.prompt_inference.placeholder_values,
             wp_encoder=self.wp_encoder,
         )
@@ -136,10 +136,24 @@ class DrivingModel(_Base):
         self.sampled_tokens = tokens
         return self.speed_wps, self.route, self.language
 
+    def _pixels(self, driving_input: DrivingInput) -> Tensor:
+        """``camera_images`` as tiles [B, T, NP, 3, 448, 448].  Raw uint8 frames [B, T, 3, H, W] (what
+        ``simlingo_training.dataloader.datamodule.Collator`` ships) are resized / tiled / normalised here on the device with the
+        Pillow-exact kernel instead of in the dataloader workers (reference internvl2_utils.py:179-267)."""
+        cam = driving_input.camera_images
+        if cam is not None and cam.dtype == torch.uint8 and cam.dim() == 5:
+            from simlingo_b200.preprocess import preprocess_frames
+            B, T, C, H, W = cam.shape
+            dev = next(self.parameters()).device
+            tiles = preprocess_frames(cam.reshape(B * T, C, H, W).to(dev, non_blocking=True), max_num_grid=2,
+                                      use_global_img=bool(self.cfg_data_module.get("use_global_img", False)) if hasattr(self.cfg_data_module, "get") else False)
+            return tiles.view(B, T, tiles.shape[1], 3, 448, 448)
+        return cam
+
     def _substituted(self, driving_input: DrivingInput, adaptor_dict: Dict) -> Dict:
         return self.vision_model.image_encoder.replace_placeholder_tokens(
             adaptor_dict=adaptor_dict,
-            pixel_values=driving_input.camera_images,
+            pixel_values=self._pixels(driving_input),
             placeholder_values=driving_input.prompt.placeholder_values,
             wp_encoder=self.wp_encoder,
         )

@@ -46,4 +46,10 @@ for name, (h, w, seed) in CASES.items():
     out[name + "_norm_row0"] = pv[:, :, 0, :16].numpy()   # a few normalised float32 values (operation order of ToTensor / Normalize)
     out[name + "_image_sizes"] = res["image_sizes"].numpy()
     print(name, tuple(pv.shape), res["image_sizes"].tolist())
+    # use_global_img=True (reference dynamic_preprocess(use_thumbnail=True), :262-265): the thumbnail tile is appended
+    res_t = ref.preprocess_image_batch([img], input_size=448, use_global_img=True, max_num_grid=2)
+    pv_t = res_t["pixel_values"][0]
+    u8_t = torch.round((pv_t * std + mean) * 255.0)
+    assert torch.equal(((u8_t / 255.0) - mean) / std, pv_t) and pv_t.shape[0] == 3 and torch.equal(pv_t[:2], pv)
+    out[name + "_thumb_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(u8_t[2].to(torch.uint8).numpy()).tobytes()).digest(), dtype=np.uint8)
 np.savez_compressed(os.path.join(os.path.dirname(__file__), "preprocess.npz"), **out)

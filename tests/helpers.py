@@ -73,3 +73,60 @@ def to_driving_example(case, device="cuda", dtype=torch.bfloat16):
     wps, path = case["labels"]
     B = case["ids"].shape[0]
     return DrivingExample(di, DrivingLabel(wps.to(device), path.to(device), di.prompt, torch.zeros(1)), ["x"] * B)
+
+
+class StubChatTokenizer:
+    """Deterministic stand-in for the InternVL2 tokenizer's batch interface (no tokenizer files offline): splits on the
+    chat / image special tokens, newlines and whitespace, maps pieces to ids by a stable hash; pads to the longest row on
+    ``padding_side``.  Enough to exercise the token-level wire format (role-marker search, loss mask, padding)."""
+    SPECIALS = {"<|im_start|>": 151644, "<|im_end|>": 151645, "<img>": 151646, "</img>": 151647, "<IMG_CONTEXT>": 151648,
+                "<TARGET_POINT>": 151662, "\n": 198}
+
+    def __init__(self, padding_side="left"):
+        import re
+        self.padding_side = padding_side
+        self.pad_token_id = 151643
+        self.eos_token_id = 151645
+        self._split = re.compile("(" + "|".join(re.escape(k) for k in self.SPECIALS) + r"|\s+)")
+
+    def convert_tokens_to_ids(self, tok):
+        return self.SPECIALS[tok]
+
+    def _encode(self, text):
+        import zlib
+        out = []
+        for piece in self._split.split(text):
+            if not piece or (piece.isspace() and piece != "\n"):
+                continue
+            out.append(self.SPECIALS[piece] if piece in self.SPECIALS else zlib.crc32(piece.encode()) % 150000)
+        return out
+
+    def __call__(self, text, padding=False, return_tensors=None, add_special_tokens=True):
+        if isinstance(text, str):
+            return {"input_ids": self._encode(text)}
+        rows = [self._encode(t) for t in text]
+        width = max(len(r) for r in rows)
+        pad = lambda r: ([self.pad_token_id] * (width - len(r)) + r) if self.padding_side == "left" else (r + [self.pad_token_id] * (width - len(r)))
+        ids = torch.tensor([pad(r) for r in rows], dtype=torch.long)
+        return {"input_ids": ids, "attention_mask": (ids != self.pad_token_id).long()}
+
+
+def make_dataset_outputs(n, seed, h=359, w=1024):
+    """``DatasetOutput`` samples shaped like the reference's driving dataset items (dataset_base.py / dataset_driving.py):
+    one user + one assistant turn, a <TARGET_POINT> placeholder pair, 11 waypoints, 20 route points."""
+    import numpy as np
+    from simlingo_b200.spec import synth_camera
+    from simlingo_training.utils.custom_types import DatasetOutput
+    rs = np.random.RandomState(seed)
+    out = []
+    for i in range(n):
+        q = "Current speed: %.1f m/s. Target waypoint: <TARGET_POINT><TARGET_POINT>. " % rs.uniform(0, 10) + " ".join(["Predict"] + ["the"] * int(rs.randint(0, 4)) + ["waypoints."])
+        a = "Waypoints: " + " ".join("w%d" % int(rs.randint(0, 50)) for _ in range(int(rs.randint(2, 7))))
+        conv = [{"role": "user", "content": [{"type": "text", "text": q}]}, {"role": "assistant", "content": [{"type": "text", "text": a}]}]
+        out.append(DatasetOutput(
+            conversation=conv, answer=[conv[1]], image_ff=synth_camera(h, w, seed * 100 + i)[None], image_ff_org_size=np.array([512, 1024]),
+            waypoints=rs.rand(11, 2).astype(np.float32).cumsum(0), waypoints_1d=rs.rand(11, 2).astype(np.float32), path=rs.rand(20, 2).astype(np.float32).cumsum(0),
+            target_points=rs.randn(2).astype(np.float32) * 10, speed=float(rs.uniform(0, 10)),
+            placeholder_values={"<TARGET_POINT>": rs.randn(2, 2).astype(np.float32) * 10}, measurement_path=f"route_{seed}/measurements/{i:04d}.json.gz",
+            dataset="driving", qa_templates=("q?", "a."), eval_infos={"k": i}))
+    return out

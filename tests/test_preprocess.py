@@ -33,6 +33,11 @@ def test_oracle_matches_reference_run(golden, name):
     assert np.array_equal(digest, golden[name + "_sha256"]), "oracle tiles differ from the reference's Pillow output"
     assert np.array_equal(P.normalize(tiles)[:, :, 0, :16], golden[name + "_norm_row0"])
     assert golden[name + "_image_sizes"].tolist() == [[h, w]]
+    # use_global_img=True: the reference appends the whole frame resized to one 448 x 448 tile
+    with_thumb = P.preprocess_tiles_u8(P.synth_camera(h, w, seed), use_thumbnail=True)
+    assert with_thumb.shape == (3, 3, 448, 448) and np.array_equal(with_thumb[:2], tiles)
+    digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(with_thumb[2]).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(digest, golden[name + "_thumb_sha256"]), "oracle thumbnail tile differs from the reference's Pillow output"
 
 
 def test_tile_grid_and_tables_of_the_product_match_oracle():
@@ -59,6 +64,17 @@ def test_gpu_preprocess_is_bit_exact(name):
     for k, img in enumerate(imgs):
         ref = torch.from_numpy(P.normalize(P.preprocess_tiles_u8(img))).to(torch.bfloat16)
         assert torch.equal(pv[k].cpu(), ref), f"{name}[{k}]: {(pv[k].cpu().float() - ref.float()).abs().max().item()}"
+
+
+@pytest.mark.gpu
+def test_gpu_thumbnail_tile_is_bit_exact():
+    """use_global_img=True (reference internvl2_utils.py:262-265): [2 grid tiles | whole frame as a third tile]"""
+    from simlingo_training.utils.internvl2_utils import preprocess_image_batch
+    h, w, seed = P.CASES["agent_359x1024"]
+    img = P.synth_camera(h, w, seed)
+    pv = preprocess_image_batch([torch.from_numpy(img)], input_size=448, use_global_img=True, max_num_grid=2)["pixel_values"]
+    ref = torch.from_numpy(P.normalize(P.preprocess_tiles_u8(img, use_thumbnail=True))).to(torch.bfloat16)
+    assert pv.shape == (1, 3, 3, 448, 448) and torch.equal(pv[0].cpu(), ref)
 
 
 @pytest.mark.gpu
