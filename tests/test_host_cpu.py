@@ -394,3 +394,43 @@ def test_bench_contract_on_a_cpu_only_host():
         assert d[sub]["metric"] == metric and d[sub]["unit"] == unit and d[sub]["value"] > 0 and d[sub]["cpu_baseline"]["kind"] == "port", sub
         assert "workload" in d[sub]["config"]
     assert d["agent"]["higher_is_better"] is False
+
+
+def test_zero_checkpoint_directory_round_trip(tmp_path):
+    """train.py:104-111: a DeepSpeed ZeRO-2 checkpoint DIRECTORY (flat fp32 partitions per rank, padded to 2 * world; frozen
+    parameters as fragments; tied tensors through shared_params; Lightning's ``_forward_module.`` prefix) or a single file is
+    turned into the state_dict ``DrivingModel.load_state_dict`` takes.  Layout per deepspeed/utils/zero_to_fp32.py (0.16.2)."""
+    from simlingo_b200.checkpoint import load_checkpoint, load_zero_checkpoint, write_zero2_checkpoint
+    from simlingo_b200.spec import tiny_spec
+    from tests.helpers import build_drop_in_model
+    spec = tiny_spec(1, 1, 512)
+    model = build_drop_in_model(spec, "internvl2-tiny-ckpt", device="cpu")
+    want = model.state_dict()
+    for world in (1, 3, 8):
+        d = str(tmp_path / f"zero_w{world}")
+        write_zero2_checkpoint(model, d, world)
+        files = sorted(os.listdir(os.path.join(d, "checkpoint")))
+        assert len([f for f in files if f.endswith("_optim_states.pt")]) == world and open(os.path.join(d, "latest")).read() == "checkpoint"
+        part = torch.load(os.path.join(d, "checkpoint", "zero_pp_rank_0_mp_rank_00_optim_states.pt"), weights_only=False)
+        n = part["optimizer_state_dict"]["single_partition_of_fp32_groups"][0].numel()
+        assert (n * world) % (2 * world) == 0 and n * world >= sum(p.numel() for p in model.parameters() if p.requires_grad)
+        got = load_zero_checkpoint(d)
+        assert set(got) == set(want), set(got) ^ set(want)
+        for k, v in want.items():
+            assert got[k].dtype == torch.float32 and torch.equal(got[k], v.float()), k
+        # the aliases the reference's module tree produces stay tied (llm.py:91, adaptors.py:227-229)
+        assert got["adaptors.language.lm_head.weight"].data_ptr() == got["language_model.model.base_model.model.lm_head.weight"].data_ptr()
+        fresh = build_drop_in_model(spec, "internvl2-tiny-ckpt", seed=7, device="cpu")
+        fresh.load_state_dict(load_checkpoint(d), strict=True)
+        assert all(torch.equal(a, b) for a, b in zip(fresh.state_dict().values(), want.values()))
+    one = str(tmp_path / "single.pt")
+    torch.save({"state_dict": {"_forward_module." + k: v for k, v in want.items()}, "epoch": 3}, one)
+    got = load_checkpoint(one)
+    assert set(got) == set(want) and all(torch.equal(got[k], want[k]) for k in want)
+    # damaged directories fail loudly
+    os.remove(os.path.join(str(tmp_path / "zero_w3"), "checkpoint", "zero_pp_rank_2_mp_rank_00_optim_states.pt"))
+    with pytest.raises(ValueError, match="Expected 3"):
+        load_zero_checkpoint(str(tmp_path / "zero_w3"))
+    os.remove(os.path.join(str(tmp_path / "zero_w1"), "latest"))
+    with pytest.raises(ValueError, match="latest"):
+        load_zero_checkpoint(str(tmp_path / "zero_w1"))
