@@ -13,6 +13,10 @@ __device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
   float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
   uint4 u;
   u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
@@ -22,15 +26,15 @@ __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm / RMSNorm forward: one warp per row, row kept in registers (MAXV 8-wide vectors per lane)
 // ------------------------------------------------------------------------------------------------
-template <int MAXV, bool RMS>
+template <int MAXV, bool RMS, typename XT = bf16>  // XT = float: the fp32 residual stream of the Qwen2 inference path
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-norm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b, bf16* __restrict__ y,
+norm_fwd_kernel(const XT* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b, bf16* __restrict__ y,
                 int rows, int cols, float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nvec = cols >> 3;
-  const bf16* xr = x + (size_t)row * cols;
+  const XT* xr = x + (size_t)row * cols;
   float v[MAXV][8];
   float s = 0.f;
 #pragma unroll
@@ -491,6 +495,15 @@ extern "C" int slb_layernorm_fwd(const void* x, const void* w, const void* b, vo
     norm_fwd_kernel<4, false><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd);
   else
     norm_fwd_kernel<16, false><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_rmsnorm_fwd_f32(const float* x, const void* w, void* y, int rows, int cols, float eps, float* rstd, void* stream) {
+  SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm_f32: bad shape %d x %d", rows, cols);
+  SLB_CHECK_ARG(x && w && y && (((uintptr_t)x) & 15) == 0, "rmsnorm_f32: null / unaligned operand");
+  const int grid = ceil_div(rows, kWarpsPerBlock);
+  norm_fwd_kernel<4, true, float><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>(x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

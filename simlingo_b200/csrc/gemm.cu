@@ -685,6 +685,7 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
     if (slb_skinny_try(a, stream, &rc)) return rc;  // 5..32 rows (batched decode): mma.sync weight streaming
   }
   SLB_CHECK_ARG(a->rms_weight == nullptr, "gemm: the fused RMSNorm prologue exists only on the M <= 4 weight-streaming path");
+  SLB_CHECK_ARG(!a->a_fp32, "gemm: fp32 activation rows (a_fp32) are only taken by the fused RMSNorm prologue of the M <= 4 path");
   int bn = a->block_n;
   if (a->swiglu && bn != 2256 && bn != 256) bn = (a->M >= 4096) ? 2256 : 256;
   if (bn == 0) {

@@ -20,6 +20,7 @@ struct GemvParams {
   float alpha;
   int act, swiglu, out_fp32;
   const bf16* rms_w; float rms_eps;
+  int a_fp32;  // A holds fp32 rows (the fp32 residual stream entering the fused RMSNorm prologue)
 };
 
 constexpr int kRows = 4;      // weight rows per warp step
@@ -73,12 +74,33 @@ gemv_bf16_kernel(GemvParams p) {
     group_rows(g, rows);
     load_w(rows, 0, wv);
   }
+  if (p.a_fp32) {
+    // fp32 activation rows (residual stream): RMSNorm in fp32 straight from global memory (M * K * 4 bytes, L2-resident), one
+    // rounding to bf16 when the normalised row is staged
+    const float* af = reinterpret_cast<const float*>(p.A);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float s = 0.f;
+      for (int k = threadIdx.x; k < K; k += blockDim.x) { const float v = af[(size_t)m * p.lda + k]; s += v * v; }
+      s = warp_sum(s);
+      if (lane == 0) red[warp] = s;
+      __syncthreads();
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGemvWarps; ++w) t += red[w];
+      const float rstd = rsqrtf(t / K + p.rms_eps);
+      for (int k = threadIdx.x; k < K; k += blockDim.x)
+        xs[(size_t)m * K + k] = __float2bfloat16(af[(size_t)m * p.lda + k] * rstd * __bfloat162float(p.rms_w[k]));
+      __syncthreads();
+    }
+  } else {
   for (int i = threadIdx.x; i < M * kvec; i += blockDim.x) {
     const int m = i / kvec, v = i % kvec;
     reinterpret_cast<uint4*>(xs)[i] = *reinterpret_cast<const uint4*>(p.A + (size_t)m * p.lda + v * 8);
   }
   __syncthreads();
-  if (p.rms_w) {
+  }
+  if (p.rms_w && !p.a_fp32) {
     // fused Qwen2RMSNorm of the activation rows (same arithmetic as norm_fwd_kernel: x * rstd * w in fp32, one rounding)
 #pragma unroll
     for (int m = 0; m < M; ++m) {
@@ -191,7 +213,9 @@ int slb_gemv_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
   if (a->M > 4 || a->a_t || a->b_t || (a->K % 8) != 0 || (size_t)a->M * a->K * 2 > 200 * 1024) return 0;
   if (a->swiglu && (a->N % 256) != 0) return 0;
   if ((((uintptr_t)a->A) & 15) || (((uintptr_t)a->B) & 15) || (a->lda % 8) || (a->ldb % 8)) return 0;
+  if (a->a_fp32 && !a->rms_weight) return 0;
   GemvParams p;
+  p.a_fp32 = a->a_fp32;
   p.A = (const bf16*)a->A; p.lda = a->lda;
   p.W = (const bf16*)a->B; p.ldw = a->ldb;
   p.out = a->out; p.ldo = a->ldo;
@@ -323,7 +347,7 @@ skinny_gemm_kernel(GemvParams p, int M) {
 
 // called by slb_gemm_bf16 for 4 < M <= 32 with K-major operands; returns 1 if it took the problem
 int slb_skinny_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
-  if (a->M <= 4 || a->M > 32 || a->a_t || a->b_t || (a->K % 32) != 0 || a->rms_weight || a->aux) return 0;
+  if (a->M <= 4 || a->M > 32 || a->a_t || a->b_t || (a->K % 32) != 0 || a->rms_weight || a->aux || a->a_fp32) return 0;
   if (a->swiglu && (a->N % 256) != 0) return 0;
   if ((((uintptr_t)a->A) & 15) || (((uintptr_t)a->B) & 15) || (a->lda % 8) || (a->ldb % 8)) return 0;
   GemvParams p;
@@ -333,7 +357,7 @@ int slb_skinny_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
   p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
   p.res = a->residual; p.ldr = a->ldr;
   p.N = a->N; p.K = a->K; p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
-  p.rms_w = nullptr; p.rms_eps = 0.f;
+  p.rms_w = nullptr; p.rms_eps = 0.f; p.a_fp32 = 0;
   // 32 weight rows per CTA (the activations are re-read from L2 by every CTA: wider tiles halve that traffic); 16 for the
   // small projections so that they still spread over > 50 CTAs
   const bool wide = a->N >= 4096;

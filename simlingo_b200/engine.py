@@ -293,11 +293,15 @@ class Engine:
     def llm_chunk(self, x: Tensor, batch: int, lq: int, past: int, cache: Tuple[Tensor, Tensor],
                   key_valid: Optional[Tensor] = None, collect: Optional[list] = None, past_dev: Optional[Tensor] = None) -> Tensor:
         """One pass of ``lq`` new positions per sequence through all decoder layers.
-        x [B*lq, 896] (consumed in place) -> residual stream before the final norm."""
+        x [B*lq, 896] -> residual stream before the final norm, fp32.  The residual stream is kept in fp32 (branch outputs
+        are added to it in the o_proj / down_proj epilogues without an intermediate rounding): rounding it to bf16 after each
+        of the 48 sub-layers is by far the largest term of the bf16-vs-fp32 feature error (2.0 % of 2.5 % at 24 layers,
+        profiles/r02_diag_rounding.log), for +4 bytes per element and sub-layer of HBM traffic."""
         s = self.spec
         kc, vc = cache
         M = batch * lq
-        h = torch.empty_like(x)
+        x = x.float() if x.dtype != torch.float32 else x
+        h = torch.empty((M, s.llm_hidden), device=self.dev, dtype=torch.bfloat16)
         qkv = torch.empty((M, s.qkv_dim), device=self.dev, dtype=torch.bfloat16)
         att = torch.empty((M, s.llm_heads * s.head_dim), device=self.dev, dtype=torch.bfloat16)
         act = torch.empty((M, s.llm_mlp), device=self.dev, dtype=torch.bfloat16)
@@ -311,13 +315,13 @@ class Engine:
             lib.rope_kv_write(qkv, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, s.rope_theta, past_dev=past_dev)
             lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, key_valid=key_valid, out=att,
                          past_dev=past_dev)
-            lib.gemm(att, ly["o"], out=x, residual=x)
+            lib.gemm(att, ly["o"], out=x, residual=x, out_fp32=True)
             if fuse_norm:
                 lib.gemm(x, ly["gu"], out=act, swiglu=True, rms_weight=ly["ln2"], rms_eps=s.rms_eps)
             else:
                 lib.rmsnorm(x, ly["ln2"], s.rms_eps, out=h)
                 lib.gemm(h, ly["gu"], out=act, swiglu=True)
-            lib.gemm(act, ly["d"], out=x, residual=x)
+            lib.gemm(act, ly["d"], out=x, residual=x, out_fp32=True)
             if collect is not None:
                 collect.append(x.clone())
         self.launches += 8 * s.llm_layers

@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float), ("act", C.c_int32), ("swiglu", C.c_int32), ("out_fp32", C.c_int32),
         ("a_t", C.c_int32), ("b_t", C.c_int32), ("block_n", C.c_int32),
         ("rms_weight", C.c_void_p), ("rms_eps", C.c_float),
-        ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("aux_mode", C.c_int32),
+        ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("aux_mode", C.c_int32), ("a_fp32", C.c_int32),
     ]
 
 
@@ -96,8 +96,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
          a_t: bool = False, b_t: bool = False, block_n: int = 0, rms_weight=None, rms_eps: float = 0.0, aux=None,
          aux_mode: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * A @ B^T).  A: [M,K] (or [K,M] if a_t), B: [N,K] (or [K,N] if b_t);
-    2-D, unit inner stride, arbitrary (multiple-of-8) row stride."""
-    _bf16(a, b, bias, scale_n)
+    2-D, unit inner stride, arbitrary (multiple-of-8) row stride.  A may be fp32 when ``rms_weight`` is given (M <= 4)."""
+    a_fp32 = a.dtype == torch.float32
+    if a_fp32:
+        assert rms_weight is not None and a.is_cuda and a.shape[0] <= 4, "fp32 A rows are only taken by the fused RMSNorm prologue (M <= 4)"
+    _bf16(None if a_fp32 else a, b, bias, scale_n)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
@@ -114,7 +117,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
                  None if residual is None else residual.data_ptr(), 0 if residual is None else residual.stride(0),
                  alpha, act, int(swiglu), int(out_fp32), int(a_t), int(b_t), block_n,
                  None if rms_weight is None else rms_weight.data_ptr(), rms_eps,
-                 None if aux is None else aux.data_ptr(), 0 if aux is None else aux.stride(0), aux_mode)
+                 None if aux is None else aux.data_ptr(), 0 if aux is None else aux.stride(0), aux_mode, int(a_fp32))
     if aux is not None:
         assert aux.dtype == torch.bfloat16 and aux.shape == (M, n_out) and aux.stride(1) == 1
     _check(load().slb_gemm_bf16(C.byref(g), _stream()), "gemm_bf16")
@@ -132,7 +135,14 @@ def layernorm(x, w, b, eps, out=None, stats=None):
 
 
 def rmsnorm(x, w, eps, out=None, rstd=None):
-    _bf16(x, w)
+    """x bf16 or fp32 [rows, cols] (fp32: the residual stream of the Qwen2 inference path) -> bf16"""
+    _bf16(w)
+    if x.dtype == torch.float32:
+        assert x.is_cuda and x.is_contiguous()
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out is None else out
+        _check(load().slb_rmsnorm_fwd_f32(_p(x), _p(w), _p(out), x.shape[0], x.shape[1], C.c_float(eps), _p(rstd), _stream()), "rmsnorm_fwd_f32")
+        return out
+    _bf16(x)
     out = torch.empty_like(x) if out is None else out
     _check(load().slb_rmsnorm_fwd(_p(x), _p(w), _p(out), x.shape[0], x.shape[1], C.c_float(eps), _p(rstd), _stream()),
            "rmsnorm_fwd")
