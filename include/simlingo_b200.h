@@ -89,7 +89,10 @@ int slb_attn_vit_fwd(const void* qkv, void* out, float* lse, int tiles, int n_to
  * only bounds the host-side checks), so that one captured CUDA graph serves every decode step; chunks of <= 32 queries. */
 int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
                      int key_valid_ld, void* out, float* lse, int batch, int lq, int past, const int32_t* past_dev, int lmax,
-                     int hq, int hkv, void* stream);
+                     int hq, int hkv, void* workspace, size_t workspace_bytes, void* stream);
+/* device scratch (bytes) the prefill kernel needs when key_valid is given (128-bit validity words per key block); without it
+ * masked prefill falls back to the first-generation kernel */
+size_t slb_attn_gqa_fwd_workspace(int batch, int lq);
 
 /* ---- RoPE + KV-cache write (modeling_qwen2.py:102-146 rotate_half convention, theta 1e6) --------
  * qkv [B*Lq, (Hq+2Hkv)*64] from the fused QKV GEMM; rotates q in place, writes rotated k and v

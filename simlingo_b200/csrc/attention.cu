@@ -538,9 +538,16 @@ extern "C" int slb_attn_vit_fwd(const void* qkv, void* out, float* lse, int tile
   return launch_attn(tm, tm, tm, p, tiles, (cudaStream_t)stream);
 }
 
+size_t slb_attn_gqa2_workspace(int batch, int lq);  // attention_gqa.cu
+int slb_attn_gqa2_try(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid, int key_valid_ld,
+                      void* out, float* lse, int batch, int lq, int past, int lmax, int hq, int hkv, uint32_t* kmask_ws, cudaStream_t stream,
+                      int* rc_out);
+
+extern "C" size_t slb_attn_gqa_fwd_workspace(int batch, int lq) { return slb_attn_gqa2_workspace(batch, lq); }
+
 extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
                                 int key_valid_ld, void* out, float* lse, int batch, int lq, int past, const int32_t* past_dev, int lmax,
-                                int hq, int hkv, void* stream) {
+                                int hq, int hkv, void* workspace, size_t workspace_bytes, void* stream) {
   SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax && hq % hkv == 0, "attn_gqa: bad shape");
   SLB_CHECK_ARG((ldq % 8) == 0, "attn_gqa: ldq must be a multiple of 8");
   SLB_CHECK_ARG(past + lq <= kMaxKvBlocks * BKV, "attn_gqa: at most %d keys", kMaxKvBlocks * BKV);
@@ -570,6 +577,12 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
     return SLB_OK;
   }
   SLB_CHECK_ARG(past_dev == nullptr, "attn_gqa: a device-side position is only supported for chunks of <= 32 queries without lse");
+  {  // prefill / teacher-forced pass: the persistent head-pair kernel (attention_gqa.cu)
+    int rc2 = SLB_OK;
+    uint32_t* ws = (workspace && workspace_bytes >= slb_attn_gqa2_workspace(batch, lq)) ? (uint32_t*)workspace : nullptr;
+    if (slb_attn_gqa2_try(q, ldq, kcache, vcache, key_valid, key_valid_ld, out, lse, batch, lq, past, lmax, hq, hkv, ws, (cudaStream_t)stream, &rc2))
+      return rc2;
+  }
   CUtensorMap tq, tk, tv;
   int rc = slb_make_tmap_3d(&tq, q, (uint64_t)ldq, (uint64_t)lq, (uint64_t)batch, (uint64_t)ldq * 2, (uint64_t)lq * ldq * 2, HD, BQ, 1);
   if (rc) return rc;

@@ -14,6 +14,7 @@
 //   (one 64-long dot product per row, added to O in the epilogue); as a *query* it is handled by a tiny
 //   CUDA-core kernel (one block per (tile, head)).  That keeps every MMA tile full: 1025 = 1 + 8*128.
 #include "common.cuh"
+#include "attn_common.cuh"
 #include "../../include/simlingo_b200.h"
 
 #include <cstdlib>
@@ -58,40 +59,6 @@ struct Vit2Params {
   int n_tokens, heads, nkv, tiles;
   float scale_log2;
 };
-
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-__device__ __forceinline__ float max32(const uint32_t (&s)[32], float m) {
-  float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four independent FMNMX3 chains
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    m0 = fmax3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-    m1 = fmax3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-    m2 = fmax3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-    m3 = fmax3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-  }
-  return fmaxf(fmax3(m0, m1, m2), m3);
-}
-// (a, b) * (sc, sc) + (-m, -m) on the packed fp32x2 pipe
-__device__ __forceinline__ void ffma2(float& a, float& b, uint64_t sc2, uint64_t nm2) {
-  uint64_t v, d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(v), "l"(sc2), "l"(nm2));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d));
-}
-__device__ __forceinline__ uint64_t pack2f(float a, float b) {
-  uint64_t v;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
-  return v;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 
 // p = exp2(s * scale - mref) for 32 scores; accumulates the (packed) row sum; writes 64 bytes (4 x 16 B chunks) of P.
 template <int VAR>

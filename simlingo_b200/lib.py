@@ -190,11 +190,18 @@ def attn_gqa(q, ldq, kcache, vcache, batch, lq, past, hq=14, hkv=2, key_valid=No
     assert kcache.shape == (batch, hkv, lmax, 64) and kcache.is_contiguous() and vcache.is_contiguous()
     out = torch.empty((batch * lq, hq * 64), device=q.device, dtype=torch.bfloat16) if out is None else out
     kv_ld = 0
+    ws, ws_bytes = None, 0
     if key_valid is not None:
         assert key_valid.dtype == torch.uint8 and key_valid.dim() == 2 and key_valid.stride(1) == 1
         kv_ld = key_valid.stride(0)
+        if lq >= 128 and past == 0 and past_dev is None:   # masked prefill: validity words per key block
+            fn = load().slb_attn_gqa_fwd_workspace
+            fn.restype = C.c_size_t
+            ws_bytes = int(fn(batch, lq))
+            ws = _workspace(ws_bytes, q.device)
     _check(load().slb_attn_gqa_fwd(_p(q), C.c_int64(ldq), _p(kcache), _p(vcache), _p(key_valid), kv_ld, _p(out), _p(lse),
-                                   batch, lq, past, _p(past_dev), lmax, hq, hkv, _stream()), "attn_gqa_fwd")
+                                   batch, lq, past, _p(past_dev), lmax, hq, hkv, _p(ws), C.c_size_t(ws_bytes), _stream()), "attn_gqa_fwd",
+           2 if ws is not None else 1)
     return out
 
 

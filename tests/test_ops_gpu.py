@@ -297,6 +297,50 @@ def test_attn_gqa_and_rope(lib, B, lq, past, use_valid):
     assert relerr(out, ref) < 2e-2
 
 
+@pytest.mark.parametrize("B,L,lmax,pad", [(1, 128, 128, None), (3, 575, 640, None), (5, 591, 640, "right"), (4, 545, 768, "left"), (40, 575, 640, None)])
+def test_attn_gqa_prefill_kernel(lib, B, L, lmax, pad):
+    """The persistent head-pair prefill kernel (attention_gqa.cu; Lq >= 128, past = 0): causal block skipping + diagonal mask,
+    7 heads per kv head in pairs (one single-head item per group), left / right key padding through validity words, a cache
+    longer than the sequence, enough items for several per CTA (B = 40: 1600 items), output and log-sum-exp."""
+    Hq, Hkv = 14, 2
+    q = rnd(B * L, (Hq + 2 * Hkv) * 64, seed=11)
+    kc = torch.zeros(B, Hkv, lmax, 64, device="cuda", dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    kc[:, :, :L] = rnd(B, Hkv, L, 64, seed=12)
+    vc[:, :, :L] = rnd(B, Hkv, L, 64, seed=13)
+    if lmax > L:   # stale rows beyond the sequence (a reused cache): must never be attended
+        kc[:, :, L:] = 7.0
+        vc[:, :, L:] = -9.0
+    valid = None
+    if pad is not None:
+        valid = torch.ones(B, lmax, device="cuda", dtype=torch.uint8)
+        if pad == "left":
+            valid[1, :9] = 0
+            valid[2, :200] = 0      # more than one whole key block masked
+        else:
+            valid[1, L - 40:] = 0
+            valid[3, L - 300:] = 0
+    lse = torch.empty(B, Hq, L, device="cuda")
+    out = lib.attn_gqa(q, q.stride(0), kc, vc, B, L, 0, key_valid=valid, lse=lse)
+    qq = q.float().view(B, L, Hq + 2 * Hkv, 64)[:, :, :Hq].transpose(1, 2)
+    kk, vv = kc.float()[:, :, :L].repeat_interleave(Hq // Hkv, 1), vc.float()[:, :, :L].repeat_interleave(Hq // Hkv, 1)
+    s = (qq @ kk.transpose(-1, -2)) * 0.125
+    m = torch.ones(L, L, device="cuda", dtype=torch.bool).tril()[None, None]
+    if valid is not None:
+        m = m & valid[:, None, None, :L].bool()
+    s = s.masked_fill(~m, float("-inf"))
+    ref = (torch.softmax(s, -1).nan_to_num(0.0) @ vv).transpose(1, 2).reshape(B * L, Hq * 64)
+    lse_ref = torch.logsumexp(s, -1)
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out, ref) < 2e-2
+    live = torch.isfinite(lse_ref)
+    assert torch.equal(torch.isfinite(lse), live)                     # fully masked (padding) rows: out = 0, lse = -inf
+    assert (lse[live] - lse_ref[live]).abs().max().item() < 2e-2
+    dead_rows = (~live).transpose(1, 2).reshape(B * L, Hq)
+    if dead_rows.any():
+        assert out.view(B * L, Hq, 64)[dead_rows].abs().max().item() == 0.0
+
+
 def test_embed_assemble_gather_argmax(lib):
     B, L, H, V, n_img = 2, 545, 896, 4096, 512
     img_id = V - 7
