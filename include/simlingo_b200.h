@@ -54,6 +54,9 @@ typedef struct {
   void* aux; int64_t ld_aux;      /* bf16 [M,N] or NULL.  aux_mode 1: the pre-activation alpha*acc + bias is also stored there (training
                                    *   forward of fc1: GELU input kept for backward); 2: v *= gelu'(aux[m,n]) (fc2 dgrad -> d pre-GELU) */
   int32_t aux_mode;
+  const void* A2; int64_t lda2;   /* optional second A source, bf16 [M,K2]: logically appended to A along k, B then holds K + K2 columns per row.
+                                   *   y = [x | t] [W | s B_lora]^T: the un-merged LoRA branch (t = A_lora x) rides in the base GEMM's k loop */
+  int32_t K2;
   int32_t a_fp32;                 /* 1: A holds fp32 rows [M,K] (ld in fp32 elements): the fp32 residual stream of the Qwen2 inference path
                                    *   entering the fused RMSNorm prologue (requires rms_weight, M <= 4) */
 } slb_gemm_args;
@@ -68,6 +71,11 @@ int slb_rmsnorm_fwd(const void* x, const void* w, void* y, int rows, int cols, f
 /* same with fp32 input rows (the Qwen2 inference path keeps its residual stream in fp32: rounding the stream to bf16 after each
  * of the 48 sub-layers is the dominant term of the bf16-vs-fp32 error of the features, profiles/r02_diag_rounding.log) */
 int slb_rmsnorm_fwd_f32(const float* x, const void* w, void* y, int rows, int cols, float eps, float* rstd, void* stream);
+/* the InternViT inference path does the same (profiles/r02_diag_rounding_e2e.log): fp32 residual stream out of the embedding
+ * assembly, through LayerNorm (fp32 in, bf16 out) and the proj / fc2 epilogues (fp32 residual + out), into the projector front */
+int slb_layernorm_fwd_f32(const float* x, const void* w, const void* b, void* y, int rows, int cols, float eps, void* stream);
+int slb_vit_assemble_f32(const void* patch_out, const void* cls, const void* pos, float* x, int tiles, void* stream);
+int slb_pixel_shuffle_ln_f32(const float* x, const void* w, const void* b, void* y, int tiles, float eps, void* stream);
 /* ---- ViT embeddings (UPSTREAM InternVisionEmbeddings, intern_vit.py:103-115) ---------------------
  * im2col: pixels [T,3,448,448] -> patches [T*1024, kpad] (k = c*196 + py*14 + px, zero padded);
  * assemble: x[t,0] = cls + pos[0]; x[t,1+p] = patch_out[t*1024+p] + pos[1+p] */

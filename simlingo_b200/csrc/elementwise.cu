@@ -23,6 +23,11 @@ __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm / RMSNorm forward: one warp per row, row kept in registers (MAXV 8-wide vectors per lane)
 // ------------------------------------------------------------------------------------------------
@@ -91,8 +96,9 @@ norm_fwd_kernel(const XT* __restrict__ x, const bf16* __restrict__ w, const bf16
 
 // drop CLS + pixel_shuffle(0.5,'v2') + LayerNorm(4096): out row (t, i, j) gathers the 2x2 block of
 // patch tokens [(2i,2j),(2i,2j+1),(2i+1,2j),(2i+1,2j+1)] channel-concatenated.
+template <typename XT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-pixel_shuffle_ln_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+pixel_shuffle_ln_kernel(const XT* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
                         bf16* __restrict__ y, int tiles, float eps, float* __restrict__ mean_out,
                         float* __restrict__ rstd_out) {
   constexpr int C = 1024, G = 32, G2 = 16, NT = 1025, COLS = 4096, MAXV = 16;
@@ -161,8 +167,9 @@ __global__ void im2col_patch_kernel(const bf16* __restrict__ px, bf16* __restric
   }
 }
 
+template <typename OT>
 __global__ void vit_assemble_kernel(const bf16* __restrict__ patch_out, const bf16* __restrict__ cls,
-                                    const bf16* __restrict__ pos, bf16* __restrict__ x, int tiles) {
+                                    const bf16* __restrict__ pos, OT* __restrict__ x, int tiles) {
   constexpr int C = 1024, NT = 1025, VPR = C / 8;
   const size_t total = (size_t)tiles * NT * VPR;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -499,6 +506,15 @@ extern "C" int slb_layernorm_fwd(const void* x, const void* w, const void* b, vo
   return SLB_OK;
 }
 
+extern "C" int slb_layernorm_fwd_f32(const float* x, const void* w, const void* b, void* y, int rows, int cols, float eps, void* stream) {
+  SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "layernorm_f32: bad shape %d x %d", rows, cols);
+  SLB_CHECK_ARG(x && w && b && y && (((uintptr_t)x) & 15) == 0, "layernorm_f32: null / unaligned operand");
+  const int grid = ceil_div(rows, kWarpsPerBlock);
+  norm_fwd_kernel<4, false, float><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>(x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, nullptr, nullptr);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
 extern "C" int slb_rmsnorm_fwd_f32(const float* x, const void* w, void* y, int rows, int cols, float eps, float* rstd, void* stream) {
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm_f32: bad shape %d x %d", rows, cols);
   SLB_CHECK_ARG(x && w && y && (((uintptr_t)x) & 15) == 0, "rmsnorm_f32: null / unaligned operand");
@@ -520,8 +536,18 @@ extern "C" int slb_pixel_shuffle_ln(const void* x, const void* w, const void* b,
                                     float* rstd, void* stream) {
   SLB_CHECK_ARG(tiles > 0, "pixel_shuffle_ln: tiles=%d", tiles);
   const int rows = tiles * 256;
-  pixel_shuffle_ln_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ST(stream)>>>(
+  pixel_shuffle_ln_kernel<bf16><<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ST(stream)>>>(
       (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, tiles, eps, mean, rstd);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+// fp32 residual stream of the InternViT inference path (see slb_layernorm_fwd_f32)
+extern "C" int slb_pixel_shuffle_ln_f32(const float* x, const void* w, const void* b, void* y, int tiles, float eps, void* stream) {
+  SLB_CHECK_ARG(tiles > 0 && x && w && b && y, "pixel_shuffle_ln_f32: bad args");
+  const int rows = tiles * 256;
+  pixel_shuffle_ln_kernel<float><<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ST(stream)>>>(
+      x, (const bf16*)w, (const bf16*)b, (bf16*)y, tiles, eps, nullptr, nullptr);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -537,7 +563,15 @@ extern "C" int slb_im2col_patch(const void* pixels, void* patches, int tiles, in
 extern "C" int slb_vit_assemble(const void* patch_out, const void* cls, const void* pos, void* x, int tiles, void* stream) {
   SLB_CHECK_ARG(tiles > 0, "vit_assemble: tiles=%d", tiles);
   const size_t total = (size_t)tiles * 1025 * 128;
-  vit_assemble_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)patch_out, (const bf16*)cls, (const bf16*)pos, (bf16*)x, tiles);
+  vit_assemble_kernel<bf16><<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)patch_out, (const bf16*)cls, (const bf16*)pos, (bf16*)x, tiles);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_vit_assemble_f32(const void* patch_out, const void* cls, const void* pos, float* x, int tiles, void* stream) {
+  SLB_CHECK_ARG(tiles > 0 && patch_out && cls && pos && x, "vit_assemble_f32: bad args");
+  const size_t total = (size_t)tiles * 1025 * 128;
+  vit_assemble_kernel<float><<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)patch_out, (const bf16*)cls, (const bf16*)pos, x, tiles);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

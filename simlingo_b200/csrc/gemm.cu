@@ -31,6 +31,7 @@ static int slb_gemm_res_prefetch() {
 struct EpiParams {
   long long* dbg;  // optional [16] int64: wait-cycle counters of cluster 0 (slb_debug_set_trace), else null
   int M, N, K;
+  int K2;          // columns of the second A source (A2), logically appended to A along k; B spans K + K2 columns
   void* out;
   long long ldo;
   const bf16* bias;
@@ -293,7 +294,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
 
 template <int BN, int TA, int TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_a2, EpiParams p) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -307,7 +309,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m * p.num_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb1 = (p.K + BK - 1) / BK;
+  const int num_kb = num_kb1 + (p.K2 + BK - 1) / BK;   // k-blocks of A, then of A2 (K is a multiple of BK when K2 > 0)
   constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512: power of two
 
   if (warp == 0 && lane == 0) {
@@ -348,7 +351,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (elect_one_sync()) {
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           if (TA == 0) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+            if (kb < num_kb1) tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+            else tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - num_kb1) * BK, m0);
           } else {
 #pragma unroll
             for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * (64 * BK * 2), &tmap_a, &full_bar[stage], m0 + g * 64, k0);
@@ -436,17 +440,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <int BN, int TA, int TB>
 int launch_gemm(const slb_gemm_args* a, cudaStream_t stream) {
   using L = SmemLayout<BN>;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta2;
   int rc;
+  const int K2 = (a->A2 && a->K2 > 0) ? a->K2 : 0;
   if (!TA) rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM);
   else     rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, BK);
   if (rc) return rc;
-  if (!TB) rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN);
+  if (!TB) rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)(a->K + K2), (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN);
   else     rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, BK);
   if (rc) return rc;
+  ta2 = ta;
+  if (K2) {
+    rc = slb_make_tmap_2d(&ta2, a->A2, (uint64_t)K2, (uint64_t)a->M, (uint64_t)a->lda2 * 2, BK, BM);
+    if (rc) return rc;
+  }
   EpiParams p;
   p.dbg = nullptr;
-  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.K2 = K2;
   p.out = a->out; p.ldo = a->ldo;
   p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
   p.res = a->residual; p.ldr = a->ldr;
@@ -464,7 +474,7 @@ int launch_gemm(const slb_gemm_args* a, cudaStream_t stream) {
   int grid = p.num_m * p.num_n;
   int sms = slb_num_sms();
   if (grid > sms) grid = sms;
-  kern<<<grid, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, ta2, p);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -488,7 +498,8 @@ struct Smem2 {
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_a2, EpiParams p) {
   using L = Smem2<BN>;
   constexpr int kStages = L::kStages;
   constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator stage (BN <= 256)
@@ -505,7 +516,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int num_tiles = p.num_m * p.num_n;  // cluster tiles (256 x BN)
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb1 = (p.K + BK - 1) / BK;
+  const int num_kb = num_kb1 + (p.K2 + BK - 1) / BK;   // k-blocks of A, then of A2
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
@@ -546,7 +558,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint8_t* sb = sa + L::kABytes;
           if (elect_one_sync()) {
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            if (kb < num_kb1) tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            else tma_load_2d_2sm(sa, &tmap_a2, &full_bar[stage], (kb - num_kb1) * BK, m0);
             tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
           }
           __syncwarp();
@@ -630,14 +643,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 template <int BN>
 int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
   using L = Smem2<BN>;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta2;
+  const int K2 = (a->A2 && a->K2 > 0) ? a->K2 : 0;
   int rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM);
   if (rc) return rc;
-  rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN / 2);
+  rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)(a->K + K2), (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN / 2);
   if (rc) return rc;
+  ta2 = ta;
+  if (K2) {
+    rc = slb_make_tmap_2d(&ta2, a->A2, (uint64_t)K2, (uint64_t)a->M, (uint64_t)a->lda2 * 2, BK, BM);
+    if (rc) return rc;
+  }
   EpiParams p;
   p.dbg = slb_debug_trace_ptr();
-  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.K2 = K2;
   p.out = a->out; p.ldo = a->ldo;
   p.bias = (const bf16*)a->bias; p.scale_n = (const bf16*)a->scale_n;
   p.res = a->residual; p.ldr = a->ldr;
@@ -655,7 +674,7 @@ int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
   int clusters = p.num_m * p.num_n;
   const int max_clusters = slb_num_sms() / 2;
   if (clusters > max_clusters) clusters = max_clusters;
-  kern<<<clusters * 2, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, p);
+  kern<<<clusters * 2, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, ta2, p);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -679,6 +698,11 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
     SLB_CHECK_ARG(!a->bias && !a->scale_n && !a->residual && !a->act, "gemm: swiglu excludes other epilogue terms");
   }
   SLB_CHECK_ARG(!a->aux || (!a->swiglu && (a->aux_mode == 1 || a->aux_mode == 2)), "gemm: aux_mode must be 1 or 2 (no swiglu)");
+  if (a->A2 && a->K2 > 0) {
+    SLB_CHECK_ARG(!a->a_t && !a->b_t, "gemm: a second A source (A2) needs K-major operands");
+    SLB_CHECK_ARG((a->K % 64) == 0 && (a->K2 % 8) == 0 && (a->lda2 % 8) == 0 && ((uintptr_t)a->A2 & 15) == 0,
+                  "gemm: A2 needs K %% 64 == 0, K2 %% 8 == 0 and 16-byte aligned rows (K=%d K2=%d lda2=%lld)", a->K, a->K2, (long long)a->lda2);
+  }
   if (a->block_n == 0 && !a->aux) {  // 1..4 activation rows: weight-streaming GEMV on the CUDA cores (HBM-bound)
     int rc = SLB_OK;
     if (slb_gemv_try(a, stream, &rc)) return rc;

@@ -21,6 +21,7 @@ struct GemvParams {
   int act, swiglu, out_fp32;
   const bf16* rms_w; float rms_eps;
   int a_fp32;  // A holds fp32 rows (the fp32 residual stream entering the fused RMSNorm prologue)
+  const bf16* A2; long long lda2; int K2;  // second activation source appended along k (weights hold K + K2 columns per row)
 };
 
 constexpr int kRows = 4;      // weight rows per warp step
@@ -38,8 +39,8 @@ __global__ void __launch_bounds__(kGemvWarps * 32)
 gemv_bf16_kernel(GemvParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ float red[kGemvWarps];
-  bf16* xs = reinterpret_cast<bf16*>(smem_raw);  // [M][K]
-  const int K = p.K, kvec = K >> 3;
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);  // [M][K + K2]
+  const int K = p.K, KT = p.K + p.K2, kvec = KT >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_groups = p.swiglu ? p.N / 4 : (p.N + kRows - 1) / kRows;  // groups of 4 weight rows
 
@@ -90,22 +91,31 @@ gemv_bf16_kernel(GemvParams p) {
       for (int w = 0; w < kGemvWarps; ++w) t += red[w];
       const float rstd = rsqrtf(t / K + p.rms_eps);
       for (int k = threadIdx.x; k < K; k += blockDim.x)
-        xs[(size_t)m * K + k] = __float2bfloat16(af[(size_t)m * p.lda + k] * rstd * __bfloat162float(p.rms_w[k]));
+        xs[(size_t)m * KT + k] = __float2bfloat16(af[(size_t)m * p.lda + k] * rstd * __bfloat162float(p.rms_w[k]));
       __syncthreads();
     }
   } else {
-  for (int i = threadIdx.x; i < M * kvec; i += blockDim.x) {
-    const int m = i / kvec, v = i % kvec;
-    reinterpret_cast<uint4*>(xs)[i] = *reinterpret_cast<const uint4*>(p.A + (size_t)m * p.lda + v * 8);
+  const int kvec1 = K >> 3;
+  for (int i = threadIdx.x; i < M * kvec1; i += blockDim.x) {
+    const int m = i / kvec1, v = i % kvec1;
+    reinterpret_cast<uint4*>(xs + (size_t)m * KT)[v] = *reinterpret_cast<const uint4*>(p.A + (size_t)m * p.lda + v * 8);
   }
   __syncthreads();
+  }
+  if (p.K2 > 0) {   // the appended activations (LoRA down-projection outputs) are never normalised
+    const int kvec2 = p.K2 >> 3;
+    for (int i = threadIdx.x; i < M * kvec2; i += blockDim.x) {
+      const int m = i / kvec2, v = i % kvec2;
+      reinterpret_cast<uint4*>(xs + (size_t)m * KT + K)[v] = *reinterpret_cast<const uint4*>(p.A2 + (size_t)m * p.lda2 + v * 8);
+    }
+    __syncthreads();
   }
   if (p.rms_w && !p.a_fp32) {
     // fused Qwen2RMSNorm of the activation rows (same arithmetic as norm_fwd_kernel: x * rstd * w in fp32, one rounding)
 #pragma unroll
     for (int m = 0; m < M; ++m) {
       float s = 0.f;
-      for (int k = threadIdx.x; k < K; k += blockDim.x) { const float v = __bfloat162float(xs[(size_t)m * K + k]); s += v * v; }
+      for (int k = threadIdx.x; k < K; k += blockDim.x) { const float v = __bfloat162float(xs[(size_t)m * KT + k]); s += v * v; }
       s = warp_sum(s);
       if (lane == 0) red[warp] = s;
       __syncthreads();
@@ -114,7 +124,7 @@ gemv_bf16_kernel(GemvParams p) {
       for (int w = 0; w < kGemvWarps; ++w) t += red[w];
       const float rstd = rsqrtf(t / K + p.rms_eps);
       for (int k = threadIdx.x; k < K; k += blockDim.x)
-        xs[(size_t)m * K + k] = __float2bfloat16(__bfloat162float(xs[(size_t)m * K + k]) * rstd * __bfloat162float(p.rms_w[k]));
+        xs[(size_t)m * KT + k] = __float2bfloat16(__bfloat162float(xs[(size_t)m * KT + k]) * rstd * __bfloat162float(p.rms_w[k]));
       __syncthreads();
     }
   }
@@ -133,7 +143,7 @@ gemv_bf16_kernel(GemvParams p) {
         float xf[M][8];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-          const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * K)[v];
+          const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * KT)[v];
           const float2 a = unpack_bf16(xv.x), b = unpack_bf16(xv.y), c = unpack_bf16(xv.z), d = unpack_bf16(xv.w);
           xf[m][0] = a.x; xf[m][1] = a.y; xf[m][2] = b.x; xf[m][3] = b.y; xf[m][4] = c.x; xf[m][5] = c.y; xf[m][6] = d.x; xf[m][7] = d.y;
         }
@@ -194,7 +204,7 @@ gemv_bf16_kernel(GemvParams p) {
 
 template <int M>
 int launch_gemv(const GemvParams& p, cudaStream_t stream) {
-  const size_t smem = (size_t)M * p.K * 2;
+  const size_t smem = (size_t)M * (p.K + p.K2) * 2;
   auto kern = gemv_bf16_kernel<M>;
   if (smem > 48 * 1024) SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_groups = p.swiglu ? p.N / 4 : ceil_div(p.N, kRows);
@@ -210,12 +220,17 @@ int launch_gemv(const GemvParams& p, cudaStream_t stream) {
 
 // called by slb_gemm_bf16 for M <= 4 with K-major operands; returns 1 if it took the problem (rc in *rc_out)
 int slb_gemv_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
-  if (a->M > 4 || a->a_t || a->b_t || (a->K % 8) != 0 || (size_t)a->M * a->K * 2 > 200 * 1024) return 0;
+  if (a->M > 4 || a->a_t || a->b_t || (a->K % 8) != 0 || (size_t)a->M * (a->K + (a->A2 ? a->K2 : 0)) * 2 > 200 * 1024) return 0;
   if (a->swiglu && (a->N % 256) != 0) return 0;
   if ((((uintptr_t)a->A) & 15) || (((uintptr_t)a->B) & 15) || (a->lda % 8) || (a->ldb % 8)) return 0;
   if (a->a_fp32 && !a->rms_weight) return 0;
   GemvParams p;
   p.a_fp32 = a->a_fp32;
+  p.A2 = nullptr; p.lda2 = 0; p.K2 = 0;
+  if (a->A2 && a->K2 > 0) {
+    if ((a->K2 % 8) || (a->lda2 % 8) || (((uintptr_t)a->A2) & 15)) return 0;
+    p.A2 = (const bf16*)a->A2; p.lda2 = a->lda2; p.K2 = a->K2;
+  }
   p.A = (const bf16*)a->A; p.lda = a->lda;
   p.W = (const bf16*)a->B; p.ldw = a->ldb;
   p.out = a->out; p.ldo = a->ldo;
@@ -271,10 +286,13 @@ skinny_gemm_kernel(GemvParams p, int M) {
     wrow[nt] = reinterpret_cast<const uint4*>(p.W + (size_t)row * p.ldw) + q;
   }
   const uint4* arow[MT][2];
+  const uint4* arow2[MT][2];   // second activation source (chunks beyond K)
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     arow[mt][0] = reinterpret_cast<const uint4*>(p.A + (size_t)min(mt * 16 + g, M - 1) * p.lda) + q;
     arow[mt][1] = reinterpret_cast<const uint4*>(p.A + (size_t)min(mt * 16 + 8 + g, M - 1) * p.lda) + q;
+    arow2[mt][0] = p.K2 ? reinterpret_cast<const uint4*>(p.A2 + (size_t)min(mt * 16 + g, M - 1) * p.lda2) + q : arow[mt][0];
+    arow2[mt][1] = p.K2 ? reinterpret_cast<const uint4*>(p.A2 + (size_t)min(mt * 16 + 8 + g, M - 1) * p.lda2) + q : arow[mt][1];
   }
   float acc[MT][NT][4];
 #pragma unroll
@@ -283,15 +301,17 @@ skinny_gemm_kernel(GemvParams p, int M) {
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-  const int nchunks = p.K >> 5;
+  const int nchunks1 = p.K >> 5, nchunks = (p.K + p.K2) >> 5;
 #pragma unroll(NT <= 2 ? 4 : 2)
   for (int c = warp; c < nchunks; c += 8) {
     uint4 bw[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) bw[nt] = __ldg(wrow[nt] + c * 4);
+    const bool tail = c >= nchunks1;
+    const int ca = tail ? c - nchunks1 : c;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const uint4 lo = __ldg(arow[mt][0] + c * 4), hi = __ldg(arow[mt][1] + c * 4);
+      const uint4 lo = __ldg((tail ? arow2[mt][0] : arow[mt][0]) + ca * 4), hi = __ldg((tail ? arow2[mt][1] : arow[mt][1]) + ca * 4);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         mma_bf16_16816(acc[mt][nt], lo.x, hi.x, lo.y, hi.y, bw[nt].x, bw[nt].y);
@@ -348,6 +368,8 @@ skinny_gemm_kernel(GemvParams p, int M) {
 // called by slb_gemm_bf16 for 4 < M <= 32 with K-major operands; returns 1 if it took the problem
 int slb_skinny_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
   if (a->M <= 4 || a->M > 32 || a->a_t || a->b_t || (a->K % 32) != 0 || a->rms_weight || a->aux || a->a_fp32) return 0;
+  const bool has2 = a->A2 && a->K2 > 0;
+  if (has2 && ((a->K2 % 32) || (a->lda2 % 8) || (((uintptr_t)a->A2) & 15))) return 0;
   if (a->swiglu && (a->N % 256) != 0) return 0;
   if ((((uintptr_t)a->A) & 15) || (((uintptr_t)a->B) & 15) || (a->lda % 8) || (a->ldb % 8)) return 0;
   GemvParams p;
@@ -358,6 +380,7 @@ int slb_skinny_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
   p.res = a->residual; p.ldr = a->ldr;
   p.N = a->N; p.K = a->K; p.alpha = a->alpha; p.act = a->act; p.swiglu = a->swiglu; p.out_fp32 = a->out_fp32;
   p.rms_w = nullptr; p.rms_eps = 0.f; p.a_fp32 = 0;
+  p.A2 = has2 ? (const bf16*)a->A2 : nullptr; p.lda2 = has2 ? a->lda2 : 0; p.K2 = has2 ? a->K2 : 0;
   // 32 weight rows per CTA (the activations are re-read from L2 by every CTA: wider tiles halve that traffic); 16 for the
   // small projections so that they still spread over > 50 CTAs
   const bool wide = a->N >= 4096;

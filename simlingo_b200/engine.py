@@ -95,15 +95,48 @@ class Engine:
 
         self.llm_layers = []
         self.has_llm = (LLM_PREFIX + "model.norm.weight") in self.sd
+        self.has_lora = self.has_llm and (f"{LLM_PREFIX}model.layers.0.self_attn.q_proj.lora_A.default.weight") in self.sd
+        bf = torch.bfloat16
+
+        def lora(prefix: str):
+            """(A [r, in], sc * B [out, r]) in bf16 (sc = alpha / r = 2: exact)"""
+            a, b = self.sd[prefix + "lora_A.default.weight"].detach(), self.sd[prefix + "lora_B.default.weight"].detach()
+            return a.to(bf), (sc * b.float()).to(bf)
+
         for i in range(s.llm_layers if self.has_llm else 0):
             p = f"{LLM_PREFIX}model.layers.{i}."
-            qkv = torch.cat([merged(p + f"self_attn.{n}_proj.") for n in "qkv"], 0).to(torch.bfloat16).contiguous()
+            # (1) LoRA folded into the weights, rounded once: the decode steps (one new position per sequence, weight-streaming
+            #     kernels, launch-bound) - token ids and the K/V of generated positions
+            qkv = torch.cat([merged(p + f"self_attn.{n}_proj.") for n in "qkv"], 0).to(bf).contiguous()
             bqkv = torch.cat([w(p + f"self_attn.{n}_proj.base_layer.bias") for n in "qkv"], 0).contiguous()
-            o = merged(p + "self_attn.o_proj.").to(torch.bfloat16).contiguous()
-            gu = _interleave_gate_up(merged(p + "mlp.gate_proj.").to(torch.bfloat16), merged(p + "mlp.up_proj.").to(torch.bfloat16))
-            d = merged(p + "mlp.down_proj.").to(torch.bfloat16).contiguous()
-            self.llm_layers.append(dict(qkv=qkv, bqkv=bqkv, o=o, gu=gu, d=d, ln1=w(p + "input_layernorm.weight"),
-                                        ln2=w(p + "post_attention_layernorm.weight")))
+            o = merged(p + "self_attn.o_proj.").to(bf).contiguous()
+            gu = _interleave_gate_up(merged(p + "mlp.gate_proj.").to(bf), merged(p + "mlp.up_proj.").to(bf))
+            d = merged(p + "mlp.down_proj.").to(bf).contiguous()
+            ly = dict(qkv=qkv, bqkv=bqkv, o=o, gu=gu, d=d, ln1=w(p + "input_layernorm.weight"), ln2=w(p + "post_attention_layernorm.weight"))
+            if self.has_lora:
+                # (2) un-merged, exact: y = [x | t] [W | sc B]^T with t = A x riding in the base GEMM's k loop (slb_gemm_bf16 A2).
+                #     Folding rounds W + sc B A to bf16, which alone costs ~2 % of route / waypoint accuracy at 24 layers
+                #     (profiles/r02_diag_rounding_e2e.log); prefill, the teacher-forced pass and the query pass use this set.
+                r = s.lora_r
+                aq, bq = lora(p + "self_attn.q_proj.")
+                ak, bk = lora(p + "self_attn.k_proj.")
+                av, bv = lora(p + "self_attn.v_proj.")
+                qd, kd = bq.shape[0], bk.shape[0]
+                b2 = torch.zeros((qd + 2 * kd, 3 * r), device=self.dev, dtype=bf)
+                b2[:qd, :r], b2[qd:qd + kd, r:2 * r], b2[qd + kd:, 2 * r:] = bq, bk, bv
+                ly["qkv_x"] = torch.cat([torch.cat([w(p + f"self_attn.{n}_proj.base_layer.weight") for n in "qkv"], 0), b2], 1).contiguous()
+                ly["a_qkv"] = torch.cat([aq, ak, av], 0).contiguous()
+                ao, bo = lora(p + "self_attn.o_proj.")
+                ly["o_x"], ly["a_o"] = torch.cat([w(p + "self_attn.o_proj.base_layer.weight"), bo], 1).contiguous(), ao.contiguous()
+                ag, bg = lora(p + "mlp.gate_proj.")
+                au, bu = lora(p + "mlp.up_proj.")
+                z = torch.zeros_like(bg)
+                ly["gu_x"] = _interleave_gate_up(torch.cat([w(p + "mlp.gate_proj.base_layer.weight"), bg, z], 1),
+                                                 torch.cat([w(p + "mlp.up_proj.base_layer.weight"), z, bu], 1))
+                ly["a_gu"] = torch.cat([ag, au], 0).contiguous()
+                ad, bd = lora(p + "mlp.down_proj.")
+                ly["d_x"], ly["a_d"] = torch.cat([w(p + "mlp.down_proj.base_layer.weight"), bd], 1).contiguous(), ad.contiguous()
+            self.llm_layers.append(ly)
         a = "adaptors.driving."
         if (a + "route_head.0.weight") in self.sd:
             self.heads_w = lib.HeadsWeights(*[w(a + k).data_ptr() for k in (
@@ -174,28 +207,29 @@ class Engine:
     # InternViT + projector
     # ------------------------------------------------------------------------------------------
     def vit(self, pixels: Tensor, collect: Optional[list] = None) -> Tensor:
-        """pixels [T,3,448,448] bf16 -> hidden [T*1025, 1024] (after the last encoder layer)."""
+        """pixels [T,3,448,448] bf16 -> hidden [T*1025, 1024] (after the last encoder layer), fp32: as in the decoder the
+        residual stream stays in fp32 (LayerNorm reads it, the proj / fc2 epilogues add the layer-scaled branch to it)."""
         s, w = self.spec, self._w
         T = pixels.shape[0]
         e = VIT_PREFIX + "embeddings."
         cols = lib.im2col_patch(pixels.contiguous(), PATCH_KPAD)
         po = lib.gemm(cols, self.patch_w, bias=w(e + "patch_embedding.bias"))
-        x = lib.vit_assemble(po, w(e + "class_embedding"), w(e + "position_embedding"), T)
+        x = lib.vit_assemble(po, w(e + "class_embedding"), w(e + "position_embedding"), T, fp32=True)
         del cols, po
         N = s.vit_tokens
-        h = torch.empty_like(x)
+        h = torch.empty((T * N, s.vit_hidden), device=self.dev, dtype=torch.bfloat16)
         qkv = torch.empty((T * N, 3 * s.vit_hidden), device=self.dev, dtype=torch.bfloat16)
-        att = torch.empty_like(x)
+        att = torch.empty_like(h)
         f = torch.empty((T * N, s.vit_mlp), device=self.dev, dtype=torch.bfloat16)
         for i in range(s.vit_layers):
             p = f"{VIT_PREFIX}encoder.layers.{i}."
             lib.layernorm(x, w(p + "norm1.weight"), w(p + "norm1.bias"), s.vit_eps, out=h)
             lib.gemm(h, w(p + "attn.qkv.weight"), out=qkv, bias=w(p + "attn.qkv.bias"))
             lib.attn_vit(qkv, T, N, s.vit_heads, out=att)
-            lib.gemm(att, w(p + "attn.proj.weight"), out=x, bias=w(p + "attn.proj.bias"), scale_n=w(p + "ls1"), residual=x)
+            lib.gemm(att, w(p + "attn.proj.weight"), out=x, bias=w(p + "attn.proj.bias"), scale_n=w(p + "ls1"), residual=x, out_fp32=True)
             lib.layernorm(x, w(p + "norm2.weight"), w(p + "norm2.bias"), s.vit_eps, out=h)
             lib.gemm(h, w(p + "mlp.fc1.weight"), out=f, bias=w(p + "mlp.fc1.bias"), act=lib.ACT_GELU)
-            lib.gemm(f, w(p + "mlp.fc2.weight"), out=x, bias=w(p + "mlp.fc2.bias"), scale_n=w(p + "ls2"), residual=x)
+            lib.gemm(f, w(p + "mlp.fc2.weight"), out=x, bias=w(p + "mlp.fc2.bias"), scale_n=w(p + "ls2"), residual=x, out_fp32=True)
             if collect is not None:
                 collect.append(x.clone())
         self.launches += 3 + 7 * s.vit_layers
@@ -305,9 +339,14 @@ class Engine:
         qkv = torch.empty((M, s.qkv_dim), device=self.dev, dtype=torch.bfloat16)
         att = torch.empty((M, s.llm_heads * s.head_dim), device=self.dev, dtype=torch.bfloat16)
         act = torch.empty((M, s.llm_mlp), device=self.dev, dtype=torch.bfloat16)
-        fuse_norm = M <= 4  # decode: RMSNorm folded into the weight-streaming GEMVs (two launches fewer per layer)
+        exact = self.has_lora and lq > 1   # prefill / teacher-forced / query pass: un-merged LoRA (see refresh)
+        fuse_norm = M <= 4 and not exact  # decode: RMSNorm folded into the weight-streaming GEMVs (two launches fewer per layer)
         for i, ly in enumerate(self.llm_layers):
-            if fuse_norm:
+            if exact:
+                lib.rmsnorm(x, ly["ln1"], s.rms_eps, out=h)
+                t = lib.gemm(h, ly["a_qkv"])
+                lib.gemm(h, ly["qkv_x"], out=qkv, bias=ly["bqkv"], a2=t)
+            elif fuse_norm:
                 lib.gemm(x, ly["qkv"], out=qkv, bias=ly["bqkv"], rms_weight=ly["ln1"], rms_eps=s.rms_eps)
             else:
                 lib.rmsnorm(x, ly["ln1"], s.rms_eps, out=h)
@@ -315,16 +354,25 @@ class Engine:
             lib.rope_kv_write(qkv, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, s.rope_theta, past_dev=past_dev)
             lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, key_valid=key_valid, out=att,
                          past_dev=past_dev)
-            lib.gemm(att, ly["o"], out=x, residual=x, out_fp32=True)
-            if fuse_norm:
-                lib.gemm(x, ly["gu"], out=act, swiglu=True, rms_weight=ly["ln2"], rms_eps=s.rms_eps)
-            else:
+            if exact:
+                t = lib.gemm(att, ly["a_o"])
+                lib.gemm(att, ly["o_x"], out=x, residual=x, out_fp32=True, a2=t)
                 lib.rmsnorm(x, ly["ln2"], s.rms_eps, out=h)
-                lib.gemm(h, ly["gu"], out=act, swiglu=True)
-            lib.gemm(act, ly["d"], out=x, residual=x, out_fp32=True)
+                t = lib.gemm(h, ly["a_gu"])
+                lib.gemm(h, ly["gu_x"], out=act, swiglu=True, a2=t)
+                t = lib.gemm(act, ly["a_d"])
+                lib.gemm(act, ly["d_x"], out=x, residual=x, out_fp32=True, a2=t)
+            else:
+                lib.gemm(att, ly["o"], out=x, residual=x, out_fp32=True)
+                if fuse_norm:
+                    lib.gemm(x, ly["gu"], out=act, swiglu=True, rms_weight=ly["ln2"], rms_eps=s.rms_eps)
+                else:
+                    lib.rmsnorm(x, ly["ln2"], s.rms_eps, out=h)
+                    lib.gemm(h, ly["gu"], out=act, swiglu=True)
+                lib.gemm(act, ly["d"], out=x, residual=x, out_fp32=True)
             if collect is not None:
                 collect.append(x.clone())
-        self.launches += 8 * s.llm_layers
+        self.launches += (12 if exact else 8) * s.llm_layers - (0 if not fuse_norm else 2 * s.llm_layers)
         return x
 
     def final_norm(self, x: Tensor) -> Tensor:

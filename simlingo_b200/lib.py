@@ -30,7 +30,8 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float), ("act", C.c_int32), ("swiglu", C.c_int32), ("out_fp32", C.c_int32),
         ("a_t", C.c_int32), ("b_t", C.c_int32), ("block_n", C.c_int32),
         ("rms_weight", C.c_void_p), ("rms_eps", C.c_float),
-        ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("aux_mode", C.c_int32), ("a_fp32", C.c_int32),
+        ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("aux_mode", C.c_int32),
+        ("A2", C.c_void_p), ("lda2", C.c_int64), ("K2", C.c_int32), ("a_fp32", C.c_int32),
     ]
 
 
@@ -94,7 +95,7 @@ def _bf16(*ts):
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, scale_n=None,
          residual=None, alpha: float = 1.0, act: int = ACT_NONE, swiglu: bool = False, out_fp32: bool = False,
          a_t: bool = False, b_t: bool = False, block_n: int = 0, rms_weight=None, rms_eps: float = 0.0, aux=None,
-         aux_mode: int = 0) -> torch.Tensor:
+         aux_mode: int = 0, a2=None) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * A @ B^T).  A: [M,K] (or [K,M] if a_t), B: [N,K] (or [K,N] if b_t);
     2-D, unit inner stride, arbitrary (multiple-of-8) row stride.  A may be fp32 when ``rms_weight`` is given (M <= 4)."""
     a_fp32 = a.dtype == torch.float32
@@ -104,7 +105,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
-    assert K == Kb, (a.shape, b.shape, a_t, b_t)
+    K2 = 0
+    if a2 is not None:   # second A source appended along k: b holds K + K2 columns
+        _bf16(a2)
+        assert not a_t and not b_t and a2.dim() == 2 and a2.shape[0] == M and a2.stride(1) == 1
+        K2 = a2.shape[1]
+    assert K + K2 == Kb, (a.shape, b.shape, a_t, b_t, K2)
     n_out = N // 2 if swiglu else N
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
@@ -117,7 +123,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
                  None if residual is None else residual.data_ptr(), 0 if residual is None else residual.stride(0),
                  alpha, act, int(swiglu), int(out_fp32), int(a_t), int(b_t), block_n,
                  None if rms_weight is None else rms_weight.data_ptr(), rms_eps,
-                 None if aux is None else aux.data_ptr(), 0 if aux is None else aux.stride(0), aux_mode, int(a_fp32))
+                 None if aux is None else aux.data_ptr(), 0 if aux is None else aux.stride(0), aux_mode,
+                 None if a2 is None else a2.data_ptr(), 0 if a2 is None else a2.stride(0), K2, int(a_fp32))
     if aux is not None:
         assert aux.dtype == torch.bfloat16 and aux.shape == (M, n_out) and aux.stride(1) == 1
     _check(load().slb_gemm_bf16(C.byref(g), _stream()), "gemm_bf16")
@@ -125,8 +132,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
 
 
 def layernorm(x, w, b, eps, out=None, stats=None):
-    _bf16(x, w, b)
     rows, cols = x.shape[0], x.shape[1]
+    if x.dtype == torch.float32:   # fp32 residual stream (InternViT inference path)
+        _bf16(w, b)
+        assert x.is_cuda and x.is_contiguous() and stats is None
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out is None else out
+        _check(load().slb_layernorm_fwd_f32(_p(x), _p(w), _p(b), _p(out), rows, cols, C.c_float(eps), _stream()), "layernorm_fwd_f32")
+        return out
+    _bf16(x, w, b)
     out = torch.empty_like(x) if out is None else out
     mean, rstd = (stats if stats is not None else (None, None))
     _check(load().slb_layernorm_fwd(_p(x), _p(w), _p(b), _p(out), rows, cols, C.c_float(eps), _p(mean), _p(rstd), _stream()),
@@ -158,16 +171,25 @@ def im2col_patch(pixels, kpad=640, out=None):
     return out
 
 
-def vit_assemble(patch_out, cls, pos, tiles, out=None):
+def vit_assemble(patch_out, cls, pos, tiles, out=None, fp32=False):
     _bf16(patch_out, cls, pos)
+    if fp32:
+        out = torch.empty((tiles * 1025, 1024), device=patch_out.device, dtype=torch.float32) if out is None else out
+        _check(load().slb_vit_assemble_f32(_p(patch_out), _p(cls), _p(pos), _p(out), tiles, _stream()), "vit_assemble_f32")
+        return out
     out = torch.empty((tiles * 1025, 1024), device=patch_out.device, dtype=torch.bfloat16) if out is None else out
     _check(load().slb_vit_assemble(_p(patch_out), _p(cls), _p(pos), _p(out), tiles, _stream()), "vit_assemble")
     return out
 
 
 def pixel_shuffle_ln(x, w, b, tiles, eps, out=None, stats=None):
-    _bf16(x, w, b)
     out = torch.empty((tiles * 256, 4096), device=x.device, dtype=torch.bfloat16) if out is None else out
+    if x.dtype == torch.float32:
+        _bf16(w, b)
+        assert x.is_cuda and x.is_contiguous() and stats is None
+        _check(load().slb_pixel_shuffle_ln_f32(_p(x), _p(w), _p(b), _p(out), tiles, C.c_float(eps), _stream()), "pixel_shuffle_ln_f32")
+        return out
+    _bf16(x, w, b)
     mean, rstd = (stats if stats is not None else (None, None))
     _check(load().slb_pixel_shuffle_ln(_p(x), _p(w), _p(b), _p(out), tiles, C.c_float(eps), _p(mean), _p(rstd), _stream()),
            "pixel_shuffle_ln")
