@@ -197,18 +197,24 @@ __device__ __forceinline__ void aux_gelu_grad32(const EpiParams& p, int row, int
 // its DRAM latency (one ~1 us stall per chunk otherwise: the layer-scale residual GEMMs sat at 51 % tensor-pipe
 // utilisation) overlaps with TMEM loads, math and stores.
 struct ResPrefetch {
-  uint4 v[4];
+  uint4 v[8];   // 32 bf16 (4 vectors) or 32 fp32 (8 vectors: the fp32 residual streams of the inference path)
   bool valid;
 };
 __device__ __forceinline__ bool res_vec_ok(const EpiParams& p) {
-  return p.res_prefetch && p.res && !p.out_fp32 && !p.swiglu && ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+  return p.res_prefetch && p.res && !p.swiglu && ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
 }
 __device__ __forceinline__ void res_prefetch(const EpiParams& p, int row, int col0, ResPrefetch& r) {
   r.valid = row < p.M && col0 + 32 <= p.N;
   if (r.valid) {
-    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (long long)row * p.ldr + col0);
+    if (p.out_fp32) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res) + (long long)row * p.ldr + col0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r.v[i] = src[i];
+      for (int i = 0; i < 8; ++i) r.v[i] = src[i];
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (long long)row * p.ldr + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r.v[i] = src[i];
+    }
   }
 }
 template <int BN>
@@ -262,7 +268,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
         for (int i = 0; i < 32; ++i) v[i] *= sc[i];
       }
       if (row_ok) {
-        if (use_pre && cur.valid) {
+        if (use_pre && cur.valid && p.out_fp32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[4 * i + 0] += __uint_as_float(cur.v[i].x); v[4 * i + 1] += __uint_as_float(cur.v[i].y);
+            v[4 * i + 2] += __uint_as_float(cur.v[i].z); v[4 * i + 3] += __uint_as_float(cur.v[i].w);
+          }
+        } else if (use_pre && cur.valid) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float2 a = unpack_bf16(cur.v[i].x), b = unpack_bf16(cur.v[i].y), c2 = unpack_bf16(cur.v[i].z), d = unpack_bf16(cur.v[i].w);
