@@ -51,7 +51,8 @@ struct EpiParams {
 
 template <int BN>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  // narrow tiles (tall-skinny products such as the LoRA down-projections, N <= 64) are bound by the A stream: deeper rings
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -223,6 +224,44 @@ __device__ __forceinline__ int epi_first_chunk(int half) {
   return half ? kFirst * 32 : 0;
 }
 
+// One 32-column chunk through every epilogue option, no assumptions on alignment (see epilogue_tile for the fast path).
+__device__ __noinline__ void epilogue_chunk_generic(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int col0) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  if (p.bias) {
+    float b[32];
+    load32_bf16(p.bias, col0, p.N, b);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += b[i];
+  }
+  if (p.aux_mode == 1 && row_ok) aux_store32(p, row, col0, v, p.N);
+  if (p.aux_mode == 2 && row_ok) aux_gelu_grad32(p, row, col0, v, p.N);
+  if (p.act == SLB_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+  } else if (p.act == SLB_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+  } else if (p.act == SLB_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (p.scale_n) {
+    float sc[32];
+    load32_bf16(p.scale_n, col0, p.N, sc);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= sc[i];
+  }
+  if (row_ok) {
+    if (p.res) add_residual32(p, row, col0, v, p.N);
+    store_row32(p, row, col0, v, p.N);
+  }
+}
+
 // Epilogue of one accumulator tile for one thread (= one output row), 32-column chunks [c_begin, c_end):
 // TMEM -> registers -> fused epilogue -> global.  Two warps share a TMEM lane quadrant and split the chunks.
 template <int BN>
@@ -231,61 +270,93 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
   if (!p.swiglu) {
     constexpr int kChunks = BN / 32, kFirst = (kChunks + 1) / 2;
     const int c_begin = half ? kFirst * 32 : 0, c_end = half ? BN : kFirst * 32;
+    // fast path: whole 32-column chunks, 16-byte aligned bf16 bias / scale vectors, bf16 or fp32 output with aligned rows, no
+    // aux operand.  The per-column vectors and the next chunk's residual are requested BEFORE the TMEM load is awaited, the
+    // arithmetic runs on packed fp32x2 pairs (half the issue slots), erf-GELU on the FMA pipe.
+    const bool vec_io = p.out_fp32 ? (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0))
+                                   : (((p.ldo & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0));
+    const bool fast = vec_io && p.aux_mode == 0 && (p.act == SLB_ACT_NONE || p.act == SLB_ACT_GELU) &&
+                      (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (!p.scale_n || (reinterpret_cast<uintptr_t>(p.scale_n) & 15) == 0) &&
+                      (!p.res || use_pre);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
       if (n0 + c >= p.N) break;  // warp-uniform
-      ResPrefetch cur = pre;
-      if (use_pre && c + 32 < c_end) res_prefetch(p, row, n0 + c + 32, pre);
-      uint32_t r[32];
-      tmem_ld_32x32(taddr + c, r);
-      tmem_ld_wait();
-      float v[32];
+      if (fast && n0 + c + 32 <= p.N) {
+        const int col0 = n0 + c;
+        ResPrefetch cur = pre;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        uint4 bq[4], sq[4];
+        if (p.bias) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-      const int col0 = n0 + c;
-      if (p.bias) {
-        float b[32];
-        load32_bf16(p.bias, col0, p.N, b);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += b[i];
-      }
-      if (p.aux_mode == 1 && row_ok) aux_store32(p, row, col0, v, p.N);
-      if (p.aux_mode == 2 && row_ok) aux_gelu_grad32(p, row, col0, v, p.N);
-      if (p.act == SLB_ACT_GELU) {  // activation switch hoisted out of the per-element loop
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
-      } else if (p.act == SLB_ACT_SILU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
-      } else if (p.act == SLB_ACT_RELU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (p.scale_n) {
-        float sc[32];
-        load32_bf16(p.scale_n, col0, p.N, sc);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= sc[i];
-      }
-      if (row_ok) {
-        if (use_pre && cur.valid && p.out_fp32) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[4 * i + 0] += __uint_as_float(cur.v[i].x); v[4 * i + 1] += __uint_as_float(cur.v[i].y);
-            v[4 * i + 2] += __uint_as_float(cur.v[i].z); v[4 * i + 3] += __uint_as_float(cur.v[i].w);
-          }
-        } else if (use_pre && cur.valid) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 a = unpack_bf16(cur.v[i].x), b = unpack_bf16(cur.v[i].y), c2 = unpack_bf16(cur.v[i].z), d = unpack_bf16(cur.v[i].w);
-            v[8 * i + 0] += a.x; v[8 * i + 1] += a.y; v[8 * i + 2] += b.x; v[8 * i + 3] += b.y;
-            v[8 * i + 4] += c2.x; v[8 * i + 5] += c2.y; v[8 * i + 6] += d.x; v[8 * i + 7] += d.y;
-          }
-        } else if (p.res) {
-          add_residual32(p, row, col0, v, p.N);
+          for (int i = 0; i < 4; ++i) bq[i] = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + i);
         }
-        store_row32(p, row, col0, v, p.N);
+        if (p.scale_n) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sq[i] = __ldg(reinterpret_cast<const uint4*>(p.scale_n + col0) + i);
+        }
+        if (use_pre && c + 32 < c_end) res_prefetch(p, row, col0 + 32, pre);
+        tmem_ld_wait();
+        const uint64_t alpha2 = f2splat(p.alpha);
+        uint64_t v2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          uint64_t a = f2pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          if (p.bias) {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(bq)[i];
+            a = f2fma(a, alpha2, bf2_to_f2(w));
+          } else if (p.alpha != 1.0f) {
+            a = f2mul(a, alpha2);
+          }
+          v2[i] = a;
+        }
+        if (p.act == SLB_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v2[i] = gelu_erf_poly2(v2[i]);
+        }
+        if (p.scale_n) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v2[i] = f2mul(v2[i], bf2_to_f2(reinterpret_cast<const uint32_t*>(sq)[i]));
+        }
+        if (row_ok) {
+          if (p.res && cur.valid) {
+            if (p.out_fp32) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(cur.v);
+                v2[i] = f2add(v2[i], f2pack(__uint_as_float(rw[2 * i]), __uint_as_float(rw[2 * i + 1])));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v2[i] = f2add(v2[i], bf2_to_f2(reinterpret_cast<const uint32_t*>(cur.v)[i]));
+            }
+          }
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(&v2[4 * i]);
+              st_global_v8(o + 8 * i, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+            }
+          } else {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col0;
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a, b;
+              f2unpack(v2[i], a, b);
+              pk[i] = pack_bf16(a, b);
+            }
+            st_global_v8(o, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+            st_global_v8(o + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+          }
+        }
+        continue;
       }
+      // generic path (edge chunks, unaligned operands, aux operands of the training epilogues, SiLU / ReLU): out of line, so
+      // that its 100+ live registers do not weigh on the fast path
+      if (use_pre && c + 32 < c_end) res_prefetch(p, row, n0 + c + 32, pre);
+      epilogue_chunk_generic(p, taddr + c, row, row_ok, n0 + c);
     }
   } else {
     // gate columns [0,BN/2), up columns [BN/2,BN) of this tile; output column base n0/2
@@ -731,6 +802,8 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
       bn = 2256;  // cluster of two CTAs per 256 x 256 tile: 6-stage pipeline, half the L2->smem operand traffic
     } else if (!a->a_t && !a->b_t && a->M >= 4096 && (a->N % 224) == 0) {
       bn = 2224;
+    } else if (!a->a_t && !a->b_t && a->N <= 64 && a->M >= 1024) {
+      bn = a->N <= 32 ? 32 : 64;  // tall-skinny (LoRA down-projection): the A stream is the whole cost
     } else {
       // 1-CTA kernel: pick the tile width with the fewer (weighted) waves; 256-wide tiles halve A re-reads and are
       // ~10 % more efficient per flop, but quantise worse on small problems
@@ -746,7 +819,8 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
     if (bn == 2224) return launch_gemm2<224>(a, stream);
     return launch_gemm2<192>(a, stream);
   }
-  SLB_CHECK_ARG(bn == 128 || bn == 256, "gemm: block_n must be 0, 128, 256 (1-CTA) or 2256 / 2224 / 2192 (2-CTA)");
+  if (!a->a_t && !a->b_t && (bn == 32 || bn == 64)) return bn == 32 ? launch_gemm<32, 0, 0>(a, stream) : launch_gemm<64, 0, 0>(a, stream);
+  SLB_CHECK_ARG(bn == 128 || bn == 256, "gemm: block_n must be 0, 32 / 64 (K-major), 128, 256 (1-CTA) or 2256 / 2224 / 2192 (2-CTA)");
   if (!a->a_t && !a->b_t) return bn == 256 ? launch_gemm<256, 0, 0>(a, stream) : launch_gemm<128, 0, 0>(a, stream);
   if (!a->a_t && a->b_t) return bn == 256 ? launch_gemm<256, 0, 1>(a, stream) : launch_gemm<128, 0, 1>(a, stream);
   return bn == 256 ? launch_gemm<256, 1, 1>(a, stream) : launch_gemm<128, 1, 1>(a, stream);

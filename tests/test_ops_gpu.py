@@ -32,6 +32,7 @@ GEMM_CASES = [
     (128, 128, 64, 128), (256, 256, 128, 256), (300, 200, 72, 0), (2050, 3072, 1024, 0), (2050, 1024, 4096, 128),
     (2050, 1024, 1024, 256), (545, 1152, 896, 0), (545, 896, 4864, 0), (2048, 1024, 640, 0), (545, 32, 896, 128),
     (545, 896, 32, 0), (7, 896, 896, 0), (1, 1152, 896, 0),
+    (4728, 32, 896, 0), (4728, 64, 896, 0), (2050, 32, 4864, 32), (1500, 48, 896, 64),   # narrow tiles (LoRA down-projections)
 ]
 
 
@@ -102,6 +103,38 @@ def test_gemm_aux_epilogues(lib, M, N, K):
     pr = pre.float().requires_grad_()
     F.gelu(pr).backward(dy.float() @ w2.float())
     assert relerr(got, pr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K,K2,kw", [
+    (36800 // 8, 1152, 896, 96, dict(bias=True)),                 # 1-CTA tile, 2 tail k-blocks (second one half out of bounds)
+    (4728, 896, 896, 32, dict(residual=True, out_fp32=True)),     # 2-CTA <224>, fp32 residual stream
+    (4728, 9728, 896, 64, dict(swiglu=True)),                     # 2-CTA <256> SwiGLU
+    (4600, 896, 4864, 32, dict(residual=True, out_fp32=True)),
+    (31, 1152, 896, 96, dict(bias=True)),                         # mma.sync weight streaming (query pass)
+    (20, 9728, 896, 64, dict(swiglu=True)),
+    (3, 896, 4864, 32, dict(residual=True, out_fp32=True)),       # GEMV
+    (1, 1152, 896, 96, dict(bias=True)),
+])
+def test_gemm_second_a_source(lib, M, N, K, K2, kw):
+    """y = [x | t] [W | B]^T: the un-merged LoRA branch rides in the base GEMM's k loop (slb_gemm_args.A2) - every kernel family"""
+    x, t, w = rnd(M, K, seed=1), rnd(M, K2, seed=2), rnd(N, K + K2, scale=0.05, seed=3)
+    ref = torch.cat([x, t], 1).float() @ w.float().t()
+    args = {}
+    if kw.get("bias"):
+        args["bias"] = rnd(N, seed=4)
+        ref = ref + args["bias"].float()
+    if kw.get("swiglu"):
+        g = ref.view(M, N // 256, 2, 128)
+        ref = (F.silu(g[:, :, 0]) * g[:, :, 1]).reshape(M, N // 2)
+        args["swiglu"] = True
+    if kw.get("residual"):
+        res = torch.randn(M, N, device="cuda")
+        ref = ref + res
+        out = res.clone()
+        got = lib.gemm(x, w, out=out, residual=out, out_fp32=True, a2=t)
+    else:
+        got = lib.gemm(x, w, a2=t, **args)
+    assert relerr(got, ref) < (1e-2 if kw.get("swiglu") else 5e-3)
 
 
 def test_gemm_strided_views(lib):
