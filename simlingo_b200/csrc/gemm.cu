@@ -225,7 +225,7 @@ __device__ __forceinline__ int epi_first_chunk(int half) {
 }
 
 // One 32-column chunk through every epilogue option, no assumptions on alignment (see epilogue_tile for the fast path).
-__device__ __noinline__ void epilogue_chunk_generic(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int col0) {
+__device__ __forceinline__ void epilogue_chunk_generic(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int col0) {
   uint32_t r[32];
   tmem_ld_32x32(taddr, r);
   tmem_ld_wait();
@@ -353,8 +353,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t taddr
         }
         continue;
       }
-      // generic path (edge chunks, unaligned operands, aux operands of the training epilogues, SiLU / ReLU): out of line, so
-      // that its 100+ live registers do not weigh on the fast path
+      // generic path (edge chunks, unaligned operands, aux operands of the training epilogues, SiLU / ReLU).  Kept inline: as an
+      // out-of-line subroutine it returned wrong SiLU columns on the B200 (r02_ops_tests5.log)
       if (use_pre && c + 32 < c_end) res_prefetch(p, row, n0 + c + 32, pre);
       epilogue_chunk_generic(p, taddr + c, row, row_ok, n0 + c);
     }
