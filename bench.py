@@ -89,6 +89,8 @@ class ClockSampler:
         self.idx, self.proc = gpu_index, None
 
     def start(self):
+        if os.environ.get("SLB_BENCH_NO_SAMPLER") == "1":   # diagnostic switch: is the nvidia-smi poll itself perturbing the run?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -193,8 +195,14 @@ class Ctx:
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        trace = os.environ.get("SLB_BENCH_TRACE") == "1"   # diagnostic: host-side wall time of every step (adds a sync per step)
         for _ in range(steps):
+            t0 = time.perf_counter()
             fn()
+            if trace:
+                t1 = time.perf_counter()
+                torch.cuda.synchronize()
+                print(f"[rank {self.rank}] step: issue {1e3 * (t1 - t0):.1f} ms, done {1e3 * (time.perf_counter() - t0):.1f} ms", file=sys.stderr, flush=True)
         e1.record()
         self.barrier()
         return self.max_ms(e0.elapsed_time(e1))

@@ -184,6 +184,23 @@ int slb_silu_mul_bwd(const void* gate, const void* up, const void* dout, void* d
 int slb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* y += dropout(x) with the same (seed, index) mask as slb_dropout */
 int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, void* stream);
+/* ---- un-merged LoRA training path (PEFT lora.Linear under llm.py:106-118): the rank-r products ride in the base GEMMs
+ * (forward y = [x | t] [W | s B]^T through slb_gemm_args.A2; backward [dx | dt] = dy [W | s B], one dgrad over the concatenated
+ * weight); these are the HBM-bound passes around them.
+ * slb_dropout_multi: n_out (<= 4) independently masked copies of x in one read; copy j equals slb_dropout(x, seeds[j]).
+ * slb_lora_pack: table_dev = int64 [n_entries][4] on the device {src bf16 [rows, rank] contiguous, dst bf16, rows, dst row
+ *   stride in elements}; dst[row, 0:rank] = scale * src[row, :] for every entry, one launch.
+ * slb_lora_dx: out[M, K] = in[:, 0:K] + sum_j mask_j o (in[:, K + rank*j : K + rank*(j+1)] @ A[j]) / (1 - p), A[j] bf16 [rank, K]
+ *   contiguous; mask_j = the keep mask of slb_dropout(seed = seeds[j]) over the contiguous [M, K] index space (seeds == NULL or
+ *   p == 0: no mask); fp32 accumulation, one rounding.  A / seeds are HOST arrays of n_adapters (<= 4) entries.
+ * slb_silu_mul_cat(_bwd): SwiGLU on gate_up bf16 [rows, 2*inter] = [gate | up]: out = silu(gate) * up; dgate_up = [dgate | dup]. */
+int slb_dropout_multi(const void* x, void* const* ys, const uint64_t* seeds, int n_out, int64_t n, float p,
+                      const uint64_t* seed_dev, void* stream);
+int slb_lora_pack(const int64_t* table_dev, int n_entries, int rank, float scale, void* stream);
+int slb_lora_dx(const void* in, int64_t ld_in, void* out, int64_t ld_out, const void* const* A, const uint64_t* seeds,
+                int n_adapters, int M, int K, int rank, float p, const uint64_t* seed_dev, void* stream);
+int slb_silu_mul_cat(const void* gate_up, void* out, int rows, int inter, void* stream);
+int slb_silu_mul_cat_bwd(const void* gate_up, const void* dout, void* dgate_up, int rows, int inter, void* stream);
 /* y (bf16) = (accumulate ? y : 0) + x (fp32): flush of fp32 small-parameter gradient accumulators */
 int slb_flush_f32_to_bf16(const float* x, void* y, int64_t n, int accumulate, void* stream);
 int slb_add_inplace_bf16(void* a, const void* b, int64_t n, void* stream);

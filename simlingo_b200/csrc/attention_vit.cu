@@ -32,6 +32,8 @@ constexpr int kPBuf = BQ * BKV * 2;
 constexpr int kSmBar = kSmP + 2 * kPBuf;
 constexpr int kSmTotal = kSmBar + 256;
 constexpr float kLazyThreshold = 8.0f;        // log2 units
+constexpr int kDefaultPTmem = 0;              // 1: P operand of the PV product in tensor memory (tcgen05.st + TS-mode MMA)
+constexpr int kDefaultEmuPairs = 0;           // pairs per 16 whose exp2 runs on the FMA / ALU pipes (ex2_emu2)
 #ifndef VIT2_NO_SPEC
 #define VIT2_NO_SPEC 1  /* speculative exp pass disabled: no measurable gain, see DESIGN.md */
 #endif
@@ -61,19 +63,20 @@ struct Vit2Params {
 };
 
 // p = exp2(s * scale - mref) for 32 scores; accumulates the (packed) row sum; writes 64 bytes (4 x 16 B chunks) of P.
-template <int VAR>
+// EMU: which of the 16 pairs take the software exp2 (FMA / ALU pipes) instead of MUFU, see ex2_emu2.
+// PT: P goes to tensor memory (16 columns of packed bf16 pairs at tp) instead of the swizzled smem tile.
+template <int VAR, uint32_t EMU, int PT>
 __device__ __forceinline__ void exp_store32(const uint32_t (&s)[32], uint64_t sc2, uint64_t nm2, uint64_t& sum2, uint8_t* half_row,
-                                            int chunk0, int rsw) {
+                                            int chunk0, int rsw, uint32_t tp) {
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float a = __uint_as_float(s[2 * i]), b = __uint_as_float(s[2 * i + 1]);
-    ffma2(a, b, sc2, nm2);
-    if (!(VAR & 1)) {
-      a = ex2_approx(a);
-      b = ex2_approx(b);
-    }
-    sum2 = fadd2(sum2, pack2f(a, b));
+    const uint64_t x2 = f2fma(f2pack(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+    uint64_t e2 = x2;
+    if (!(VAR & 1)) e2 = ex2_pair<EMU>(x2, i);
+    sum2 = fadd2(sum2, e2);
+    float a, b;
+    f2unpack(e2, a, b);
     pk[i] = pack_bf16(a, b);
   }
   if (VAR & 4) {
@@ -81,6 +84,10 @@ __device__ __forceinline__ void exp_store32(const uint32_t (&s)[32], uint64_t sc
 #pragma unroll
     for (int i = 0; i < 16; ++i) x ^= pk[i];
     if (x == 0x12345678u) *reinterpret_cast<uint32_t*>(half_row) = x;
+    return;
+  }
+  if (PT) {
+    tmem_st_32x16(tp, pk);
     return;
   }
 #pragma unroll
@@ -112,7 +119,7 @@ __device__ __forceinline__ void exp_store32_max(const uint32_t (&s)[32], uint64_
 // query block fastest so that concurrently running CTAs share K/V in L2).  Every mbarrier keeps counting across
 // items (global block counter `blk`), so the TMA / MMA pipelines stay warm over item boundaries: the next item's
 // Q, K_0 and S_0 are in flight while the softmax warps finish the current item's epilogue.
-template <int VAR>
+template <int VAR, uint32_t EMU, int PT>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -225,7 +232,7 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
         constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);
         const uint32_t sk = smem_u32(smem + kSmK), sv = smem_u32(smem + kSmV), sp = smem_u32(smem + kSmP) + g * kPBuf;
         const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(smem + kSmQ) + g * kTile);
-        const uint32_t tm_s = tmem_base + g * BKV, tm_o = tmem_base + 256 + g * HD;
+        const uint32_t tm_s = tmem_base + g * BKV, tm_o = tmem_base + 256 + g * HD, tm_p = tmem_base + 384 + g * (BKV / 2);
         Trace tr{(blockIdx.x == 0 && g == 0 && lane == 0) ? p.trace : nullptr, 0, 0};
         auto issue_s = [&](int blk) {
           const int st = blk % NSTAGE, j = blk % nkv;
@@ -261,8 +268,10 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
           const uint64_t dp0 = umma_desc_kmajor_sw128(sp), dp1 = umma_desc_kmajor_sw128(sp + BQ * 128);
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < BKV / 16; ++k)
-              tc_mma_bf16(tm_o, (k < 4 ? dp0 : dp1) + 2 * (k & 3), dv + (uint64_t)k * (16 * 128 >> 4), idesc_o, (j | k) != 0);
+            for (int k = 0; k < BKV / 16; ++k) {
+              if (PT) tc_mma_bf16_ts(tm_o, tm_p + 8 * k, dv + (uint64_t)k * (16 * 128 >> 4), idesc_o, (j | k) != 0);
+              else tc_mma_bf16(tm_o, (k < 4 ? dp0 : dp1) + 2 * (k & 3), dv + (uint64_t)k * (16 * 128 >> 4), idesc_o, (j | k) != 0);
+            }
             tc_commit(&o_done[2 * g + (blk & 1)]);
             tc_commit(&v_empty[st]);
           }
@@ -280,6 +289,7 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const uint32_t tmem_s = tmem_base + g * BKV + lane_off;
     const uint32_t tmem_o = tmem_base + 256 + g * HD + lane_off;
+    const uint32_t tmem_p = tmem_base + 384 + g * (BKV / 2) + lane_off;   // PT: P_g as packed bf16 pairs, 64 columns
     uint8_t* prow = smem + kSmP + g * kPBuf + r * 128;
     const int rsw = r & 7;
     const float scale = p.scale_log2;
@@ -378,10 +388,10 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
             if (g == 0) { if (blk > 0) asm volatile("bar.sync 1, 256;" ::: "memory"); }
             else        { asm volatile("bar.sync 2, 256;" ::: "memory"); }
           }
-          exp_store32<VAR>(s0, sc2, nm2, sum2, prow, 0, rsw);
-          exp_store32<VAR>(s1, sc2, nm2, sum2, prow, 4, rsw);
-          exp_store32<VAR>(s2, sc2, nm2, sum2, prow + BQ * 128, 0, rsw);
-          exp_store32<VAR>(s3, sc2, nm2, sum2, prow + BQ * 128, 4, rsw);
+          exp_store32<VAR, EMU, PT>(s0, sc2, nm2, sum2, prow, 0, rsw, tmem_p);
+          exp_store32<VAR, EMU, PT>(s1, sc2, nm2, sum2, prow, 4, rsw, tmem_p + 16);
+          exp_store32<VAR, EMU, PT>(s2, sc2, nm2, sum2, prow + BQ * 128, 0, rsw, tmem_p + 32);
+          exp_store32<VAR, EMU, PT>(s3, sc2, nm2, sum2, prow + BQ * 128, 4, rsw, tmem_p + 48);
           if (VAR & 16) {
             if (g == 0) { asm volatile("bar.arrive 2, 256;" ::: "memory"); }
             else if (blk + 1 < total_blk) { asm volatile("bar.arrive 1, 256;" ::: "memory"); }
@@ -393,7 +403,8 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
           l_run += lo + hi;
         }
         tr.rec(700 + blk);  // P written
-        if (!(VAR & 2)) fence_proxy_async_smem();
+        if (PT) tmem_st_wait();
+        else if (!(VAR & 2)) fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
@@ -559,24 +570,41 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
     return cudaGetLastError();
   };
   cudaError_t e;
+  // software-exp2 share (pairs out of 16 per 32-score chunk): SLB_VIT2_EMU selects 0 / 4 / 5 / 6 / 8 for tuning runs; valid
+  // results in every setting
+  static int emu = -1;
+  if (emu < 0) { const char* ev = getenv("SLB_VIT2_EMU"); emu = ev ? atoi(ev) : kDefaultEmuPairs; }
 #ifdef SLB_ABLATION
   // SLB_VIT2_VARIANT (timing experiments only, results are wrong; not compiled into the product library): 1 no exp2, 2 no proxy
   // fence, 4 no P stores, 8 short max; 16 = warpgroup turn-taking around the exp phase (valid results; measured: no gain)
   static int variant = -1;
   if (variant < 0) { const char* ev = getenv("SLB_VIT2_VARIANT"); variant = ev ? atoi(ev) : 0; }
   switch (variant) {
-    case 1: e = launch(attn_vit2_kernel<1>); break;
-    case 2: e = launch(attn_vit2_kernel<2>); break;
-    case 4: e = launch(attn_vit2_kernel<4>); break;
-    case 6: e = launch(attn_vit2_kernel<6>); break;
-    case 7: e = launch(attn_vit2_kernel<7>); break;
-    case 8: e = launch(attn_vit2_kernel<8>); break;
-    case 15: e = launch(attn_vit2_kernel<15>); break;
-    case 16: e = launch(attn_vit2_kernel<16>); break;
-    default: e = launch(attn_vit2_kernel<0>); break;
+    case 1: e = launch(attn_vit2_kernel<1, 0, 0>); break;
+    case 2: e = launch(attn_vit2_kernel<2, 0, 0>); break;
+    case 4: e = launch(attn_vit2_kernel<4, 0, 0>); break;
+    case 6: e = launch(attn_vit2_kernel<6, 0, 0>); break;
+    case 7: e = launch(attn_vit2_kernel<7, 0, 0>); break;
+    case 8: e = launch(attn_vit2_kernel<8, 0, 0>); break;
+    case 15: e = launch(attn_vit2_kernel<15, 0, 0>); break;
+    case 16: e = launch(attn_vit2_kernel<16, 0, 0>); break;
+    default: e = launch(attn_vit2_kernel<0, 0, 0>); break;
   }
 #else
-  e = launch(attn_vit2_kernel<0>);
+  static int pt = -1;   // SLB_VIT2_PT=1: P through tensor memory (TS-mode PV product), tuning switch
+  if (pt < 0) { const char* ev = getenv("SLB_VIT2_PT"); pt = ev ? atoi(ev) : kDefaultPTmem; }
+  switch (emu + 100 * pt) {
+    case 0: e = launch(attn_vit2_kernel<0, 0x0000u, 0>); break;
+    case 4: e = launch(attn_vit2_kernel<0, 0x2222u, 0>); break;
+    case 5: e = launch(attn_vit2_kernel<0, 0x2492u, 0>); break;
+    case 8: e = launch(attn_vit2_kernel<0, 0xAAAAu, 0>); break;
+    case 100: e = launch(attn_vit2_kernel<0, 0x0000u, 1>); break;
+    case 104: e = launch(attn_vit2_kernel<0, 0x2222u, 1>); break;
+    case 105: e = launch(attn_vit2_kernel<0, 0x2492u, 1>); break;
+    case 108: e = launch(attn_vit2_kernel<0, 0xAAAAu, 1>); break;
+    case 106: e = launch(attn_vit2_kernel<0, 0xA492u, 1>); break;
+    default: e = launch(attn_vit2_kernel<0, 0xA492u, 0>); break;   // 6 of 16
+  }
 #endif
   if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_vit2 launch: %s", cudaGetErrorString(e)); return 1; }
   const size_t smem = ((size_t)kClsHeads * 64 + 2 * kClsWarps * kClsHeads + kClsWarps * 256 + (size_t)kClsHeads * n_tokens) * sizeof(float);

@@ -37,6 +37,42 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// 2^x for two values WITHOUT the MUFU pipe (FA4-style software exp2): Cody-Waite split x = floor(x) + f through the 1.5 * 2^23
+// magic constant under round-toward-minus-infinity, 2^f on [0, 1) by a degree-3 polynomial (max relative error 8.8e-5, 1/40 of
+// the bf16 rounding P receives next), floor(x) added into the exponent field (LEA).  x is clamped at -127 (-> ~6e-39).  With
+// head_dim 64 the exp2 stream needs 2 x the tensor time on the 16-lane MUFU pipe: moving ~1/3 of the elements onto the FMA /
+// ALU pipes (10 issue slots per pair) balances MUFU time against issue slots.
+__device__ __forceinline__ uint64_t ex2_emu2(uint64_t x2) {
+  float a, b;
+  f2unpack(x2, a, b);
+  a = fmaxf(a, -127.f);
+  b = fmaxf(b, -127.f);
+  const uint64_t xc = f2pack(a, b);
+  uint64_t xr;   // floor(x) + 1.5 * 2^23: the integer sits in the low mantissa bits
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(xr) : "l"(xc), "l"(f2splat(12582912.f)));
+  const uint64_t xb = f2add(xr, f2splat(-12582912.f));        // floor(x), exact
+  const uint64_t f = f2fma(xb, f2splat(-1.0f), xc);            // x - floor(x) in [0, 1)
+  uint64_t p = f2fma(f, f2splat(0.077119089663028717f), f2splat(0.227564394474029541f));
+  p = f2fma(p, f, f2splat(0.695146143436431885f));
+  p = f2fma(p, f, f2splat(1.0f));                              // 2^f in [1, 2)
+  uint32_t r0, r1, p0, p1;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(r0), "=r"(r1) : "l"(xr));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(p));
+  r0 = (r0 << 23) + p0;
+  r1 = (r1 << 23) + p1;
+  uint64_t out;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(out) : "r"(r0), "r"(r1));
+  return out;
+}
+// exp2 of a packed pair: software path for the pairs selected by the compile-time mask, MUFU otherwise
+template <uint32_t EMU_MASK>
+__device__ __forceinline__ uint64_t ex2_pair(uint64_t x2, int i) {
+  if ((EMU_MASK >> i) & 1u) return ex2_emu2(x2);
+  float a, b;
+  f2unpack(x2, a, b);
+  return f2pack(ex2_approx(a), ex2_approx(b));
+}
+
 // p = exp2(s * scale - mref) for 32 scores; accumulates the (packed) row sum; writes 64 bytes (4 x 16 B chunks) of P into the
 // K-major 128B-swizzled UMMA layout (row r = 128 bytes per 64-key half, chunk index XOR (r & 7)).
 __device__ __forceinline__ void exp_store32_plain(const uint32_t (&s)[32], uint64_t sc2, uint64_t nm2, uint64_t& sum2, uint8_t* half_row,

@@ -1,0 +1,272 @@
+// Side kernels of the un-merged LoRA training path (PEFT lora.Linear: y = W x + b + (alpha/r) B A dropout(x), every adapter with
+// its own dropout mask; reference llm.py:106-118 wraps all seven Qwen2 linears of a layer).
+//
+// The tensor-core work rides in the base GEMMs: forward  y = [x | t] [W | s B]^T  (slb_gemm_bf16 A2, t = A dropout(x)),
+// backward  [dx | dt] = dy [W | s B]  (one dgrad over the concatenated weight).  What is left are HBM-bound passes:
+//   dropout_multi   x -> n independently masked copies in one read of x (q/k/v and gate/up share their input)
+//   lora_pack       scale * B of every adapter -> its column block of the concatenated weights (one launch per step)
+//   lora_dx         dx_out = dx_base + sum_j mask_j o (dt_j A_j) / (1 - p): the rank-r products on the CUDA cores (0.8 GFLOP
+//                   per call), fp32 accumulation over the adapters, one rounding - instead of one [M, K] GEMM + one
+//                   read-modify-write pass per adapter
+//   silu_mul_cat    SwiGLU forward / backward on the [gate | up] output of the fused gate-up GEMM
+#include "common.cuh"
+#include "../../include/simlingo_b200.h"
+
+namespace {
+
+constexpr uint64_t kGold = 0x9E3779B97F4A7C15ULL;
+constexpr int kMaxAdapters = 4;
+
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {   // same generator as dropout_kernel (backward.cu)
+  z ^= z >> 33; z *= 0xff51afd7ed558ccdULL; z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33;
+  return (uint32_t)z;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+inline int grid_for(size_t work, int block) {
+  size_t g = (work + block - 1) / block;
+  size_t cap = (size_t)slb_num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+struct MultiArgs {
+  bf16* y[kMaxAdapters];
+  uint64_t seed[kMaxAdapters];
+  int n;
+};
+__global__ void dropout_multi_kernel(const bf16* __restrict__ x, MultiArgs a, size_t nvec, uint32_t thresh, float scale,
+                                     const uint64_t* __restrict__ seed_dev) {
+  const uint64_t add = seed_dev ? (*seed_dev << 16) : 0;
+  uint64_t sm[kMaxAdapters];
+#pragma unroll
+  for (int j = 0; j < kMaxAdapters; ++j) sm[j] = (a.seed[j] + add) * kGold;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < kMaxAdapters; ++j) {
+      if (j < a.n) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (mix32(sm[j] + i * 8 + e) >= thresh) ? v[e] * scale : 0.f;
+        store8(a.y[j] + i * 8, o);
+      }
+    }
+  }
+}
+
+struct PackEntry { long long src, dst, rows, ld_dst; };   // src: bf16 [rows, r] contiguous; dst: bf16, row stride ld_dst
+__global__ void lora_pack_kernel(const PackEntry* __restrict__ tab, int r8, float scale) {
+  const PackEntry e = tab[blockIdx.x];
+  const bf16* src = reinterpret_cast<const bf16*>(e.src);
+  bf16* dst = reinterpret_cast<bf16*>(e.dst);
+  const long long chunks = e.rows * r8;
+  for (long long q = blockIdx.y * (long long)blockDim.x + threadIdx.x; q < chunks; q += (long long)gridDim.y * blockDim.x) {
+    const long long row = q / r8;
+    const int c = (int)(q % r8);
+    float v[8];
+    load8(src + q * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= scale;
+    store8(dst + row * e.ld_dst + c * 8, v);
+  }
+}
+
+// ---- lora_dx ------------------------------------------------------------------------------------------------------------
+constexpr int DX_ROWS = 64, DX_COLS = 128, DX_THREADS = 256, DX_RMAX = 64;
+struct LoraDxArgs {
+  const bf16* in; long long ld_in;   // [M, >= K + r*n]: base dgrad in columns [0, K), dt_j in columns [K + r*j, K + r*(j+1))
+  bf16* out; long long ld_out;       // [M, K]
+  const bf16* A[kMaxAdapters];       // [r, K] each, contiguous
+  uint64_t seed[kMaxAdapters];
+  int n, M, K, r;
+  uint32_t thresh;
+  float scale;
+  int use_mask;
+};
+__global__ void __launch_bounds__(DX_THREADS)
+lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
+  __shared__ __align__(16) bf16 sA[DX_RMAX * DX_COLS];   // [r][128]
+  __shared__ __align__(16) bf16 sD[DX_ROWS * DX_RMAX];   // [64][r]
+  const int tid = threadIdx.x;
+  const int cg = tid & 15, rg = tid >> 4;
+  const int col_tile = blockIdx.x * DX_COLS, row_tile = blockIdx.y * DX_ROWS;
+  const int c0 = col_tile + cg * 8;
+  const bool col_ok = c0 < a.K;
+  const uint64_t add = seed_dev ? (*seed_dev << 16) : 0;
+  float tot[4][8];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int row = row_tile + rg * 4 + rr;
+    if (row < a.M && col_ok) {
+      load8(a.in + (long long)row * a.ld_in + c0, tot[rr]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tot[rr][e] = 0.f;
+    }
+  }
+  const int r = a.r, r8 = r >> 3;
+  for (int j = 0; j < a.n; ++j) {
+    __syncthreads();
+    for (int q = tid; q < r * (DX_COLS / 8); q += DX_THREADS) {
+      const int k = q >> 4, cc = q & 15;
+      const int c = col_tile + cc * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (c < a.K) v = *reinterpret_cast<const uint4*>(a.A[j] + (long long)k * a.K + c);
+      *reinterpret_cast<uint4*>(sA + k * DX_COLS + cc * 8) = v;
+    }
+    for (int q = tid; q < DX_ROWS * r8; q += DX_THREADS) {
+      const int rw = q / r8, cc = q % r8;
+      const int row = row_tile + rw;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row < a.M) v = *reinterpret_cast<const uint4*>(a.in + (long long)row * a.ld_in + a.K + j * r + cc * 8);
+      *reinterpret_cast<uint4*>(sD + rw * r + cc * 8) = v;
+    }
+    __syncthreads();
+    float acc[4][8];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[rr][e] = 0.f;
+    for (int k = 0; k < r; ++k) {
+      float av[8];
+      load8(sA + k * DX_COLS + cg * 8, av);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float d = __bfloat162float(sD[(rg * 4 + rr) * r + k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[rr][e] = fmaf(d, av[e], acc[rr][e]);
+      }
+    }
+    if (a.use_mask) {
+      const uint64_t sm = (a.seed[j] + add) * kGold;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const uint64_t base = (uint64_t)(row_tile + rg * 4 + rr) * (uint64_t)a.K + (uint64_t)c0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tot[rr][e] += (mix32(sm + base + e) >= a.thresh) ? acc[rr][e] * a.scale : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tot[rr][e] += acc[rr][e];
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int row = row_tile + rg * 4 + rr;
+    if (row < a.M && col_ok) store8(a.out + (long long)row * a.ld_out + c0, tot[rr]);
+  }
+}
+
+// ---- SwiGLU on the concatenated [gate | up] layout ----------------------------------------------------------------------
+__global__ void silu_mul_cat_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, size_t rows, int i8) {
+  const size_t nvec = rows * i8;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < nvec; q += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = q / i8;
+    const int c = (int)(q % i8);
+    const bf16* g = gu + row * (size_t)(2 * i8 * 8) + c * 8;
+    float a[8], b[8], o[8];
+    load8(g, a);
+    load8(g + i8 * 8, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = silu(a[e]) * b[e];
+    store8(out + q * 8, o);
+  }
+}
+__global__ void silu_mul_cat_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dout, bf16* __restrict__ dgu, size_t rows, int i8) {
+  const size_t nvec = rows * i8;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < nvec; q += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = q / i8;
+    const int c = (int)(q % i8);
+    const size_t off = row * (size_t)(2 * i8 * 8) + c * 8;
+    float a[8], b[8], d[8], rgv[8], ruv[8];
+    load8(gu + off, a);
+    load8(gu + off + i8 * 8, b);
+    load8(dout + q * 8, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sg = 1.0f / (1.0f + __expf(-a[e]));
+      ruv[e] = d[e] * a[e] * sg;
+      rgv[e] = d[e] * b[e] * sg * (1.0f + a[e] * (1.0f - sg));
+    }
+    store8(dgu + off, rgv);
+    store8(dgu + off + i8 * 8, ruv);
+  }
+}
+
+}  // namespace
+
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" int slb_dropout_multi(const void* x, void* const* ys, const uint64_t* seeds, int n_out, int64_t n, float p,
+                                 const uint64_t* seed_dev, void* stream) {
+  SLB_CHECK_ARG(x && ys && seeds && n_out >= 1 && n_out <= kMaxAdapters, "dropout_multi: n_out=%d (1..%d)", n_out, kMaxAdapters);
+  SLB_CHECK_ARG(n > 0 && (n % 8) == 0 && p >= 0.f && p < 1.f, "dropout_multi: n=%lld p=%f", (long long)n, p);
+  MultiArgs a;
+  for (int j = 0; j < kMaxAdapters; ++j) {
+    a.y[j] = j < n_out ? (bf16*)ys[j] : nullptr;
+    a.seed[j] = j < n_out ? seeds[j] : 0;
+    SLB_CHECK_ARG(j >= n_out || (ys[j] && ((uintptr_t)ys[j] & 15) == 0), "dropout_multi: output %d null or not 16-byte aligned", j);
+  }
+  a.n = n_out;
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  dropout_multi_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)x, a, n / 8, thresh, 1.0f / (1.0f - p), seed_dev);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_lora_pack(const int64_t* table_dev, int n_entries, int rank, float scale, void* stream) {
+  SLB_CHECK_ARG(table_dev && n_entries > 0 && rank > 0 && (rank % 8) == 0, "lora_pack: n=%d rank=%d", n_entries, rank);
+  lora_pack_kernel<<<dim3(n_entries, 8), 256, 0, ST(stream)>>>(reinterpret_cast<const PackEntry*>(table_dev), rank / 8, scale);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_lora_dx(const void* in, int64_t ld_in, void* out, int64_t ld_out, const void* const* A, const uint64_t* seeds,
+                           int n_adapters, int M, int K, int rank, float p, const uint64_t* seed_dev, void* stream) {
+  SLB_CHECK_ARG(in && out && A && n_adapters >= 1 && n_adapters <= kMaxAdapters, "lora_dx: n_adapters=%d (1..%d)", n_adapters, kMaxAdapters);
+  SLB_CHECK_ARG(M > 0 && K > 0 && (K % 8) == 0 && rank > 0 && (rank % 8) == 0 && rank <= DX_RMAX, "lora_dx: M=%d K=%d rank=%d (rank <= %d)", M, K,
+                rank, DX_RMAX);
+  SLB_CHECK_ARG((ld_in % 8) == 0 && (ld_out % 8) == 0 && ld_in >= K + (int64_t)rank * n_adapters && ld_out >= K &&
+                ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "lora_dx: strides / alignment (ld_in=%lld ld_out=%lld)",
+                (long long)ld_in, (long long)ld_out);
+  SLB_CHECK_ARG(p >= 0.f && p < 1.f, "lora_dx: p=%f", p);
+  LoraDxArgs a;
+  a.in = (const bf16*)in; a.ld_in = ld_in; a.out = (bf16*)out; a.ld_out = ld_out;
+  for (int j = 0; j < kMaxAdapters; ++j) {
+    a.A[j] = j < n_adapters ? (const bf16*)A[j] : nullptr;
+    a.seed[j] = (seeds && j < n_adapters) ? seeds[j] : 0;
+    SLB_CHECK_ARG(j >= n_adapters || (A[j] && ((uintptr_t)A[j] & 15) == 0), "lora_dx: A[%d] null or not 16-byte aligned", j);
+  }
+  a.n = n_adapters; a.M = M; a.K = K; a.r = rank;
+  a.use_mask = (seeds != nullptr && p > 0.f) ? 1 : 0;
+  a.thresh = (uint32_t)((double)p * 4294967296.0);
+  a.scale = 1.0f / (1.0f - p);
+  lora_dx_kernel<<<dim3(ceil_div(K, DX_COLS), ceil_div(M, DX_ROWS)), DX_THREADS, 0, ST(stream)>>>(a, seed_dev);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_silu_mul_cat(const void* gate_up, void* out, int rows, int inter, void* stream) {
+  SLB_CHECK_ARG(gate_up && out && rows > 0 && inter > 0 && (inter % 8) == 0, "silu_mul_cat: %d x %d", rows, inter);
+  silu_mul_cat_kernel<<<grid_for((size_t)rows * (inter / 8), 256), 256, 0, ST(stream)>>>((const bf16*)gate_up, (bf16*)out, (size_t)rows, inter / 8);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+extern "C" int slb_silu_mul_cat_bwd(const void* gate_up, const void* dout, void* dgate_up, int rows, int inter, void* stream) {
+  SLB_CHECK_ARG(gate_up && dout && dgate_up && rows > 0 && inter > 0 && (inter % 8) == 0, "silu_mul_cat_bwd: %d x %d", rows, inter);
+  silu_mul_cat_bwd_kernel<<<grid_for((size_t)rows * (inter / 8), 256), 256, 0, ST(stream)>>>((const bf16*)gate_up, (const bf16*)dout, (bf16*)dgate_up,
+                                                                                             (size_t)rows, inter / 8);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}

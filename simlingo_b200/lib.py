@@ -376,6 +376,60 @@ def dropout_add(x, y, p, seed, seed_dev=None):
     return y
 
 
+def dropout_multi(x, p, seeds, seed_dev=None):
+    """-> list of len(seeds) independently masked copies of x (copy j == dropout(x, p, seeds[j], seed_dev)), one read of x"""
+    _bf16(x)
+    n = len(seeds)
+    assert 1 <= n <= 4 and x.is_contiguous()
+    outs = [torch.empty_like(x) for _ in range(n)]
+    ys = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    sd = (C.c_uint64 * n)(*[int(s) for s in seeds])
+    _check(load().slb_dropout_multi(_p(x), ys, sd, n, C.c_int64(x.numel()), C.c_float(p), _p(seed_dev), _stream()), "dropout_multi")
+    return outs
+
+
+def lora_pack(table, n_entries, rank, scale):
+    """table: int64 CUDA tensor [n_entries, 4] = (src ptr, dst ptr, rows, dst row stride); dst[:, :rank] = scale * src"""
+    assert table.dtype == torch.int64 and table.is_cuda and table.is_contiguous() and table.shape == (n_entries, 4)
+    _check(load().slb_lora_pack(_p(table), n_entries, rank, C.c_float(scale), _stream()), "lora_pack")
+
+
+def lora_dx(cat, K, a_list, p=0.0, seeds=None, seed_dev=None, out=None):
+    """cat bf16 [M, K + r*n] (row stride free) = [base dgrad | dt_0 .. dt_{n-1}] -> out [M, K] = base + sum_j mask_j o (dt_j @ A_j) / (1-p)"""
+    _bf16(cat, *a_list)
+    n = len(a_list)
+    r = a_list[0].shape[0]
+    M = cat.shape[0]
+    assert cat.stride(1) == 1 and cat.shape[1] >= K + r * n and all(a.shape == (r, K) and a.is_contiguous() for a in a_list)
+    out = torch.empty((M, K), device=cat.device, dtype=torch.bfloat16) if out is None else out
+    assert out.stride(1) == 1 and out.shape == (M, K)
+    ap = (C.c_void_p * n)(*[a.data_ptr() for a in a_list])
+    sd = None if seeds is None else (C.c_uint64 * n)(*[int(s) for s in seeds])
+    _check(load().slb_lora_dx(_p(cat), C.c_int64(cat.stride(0)), _p(out), C.c_int64(out.stride(0)), ap, sd, n, M, K, r, C.c_float(p),
+                              _p(seed_dev), _stream()), "lora_dx")
+    return out
+
+
+def silu_mul_cat(gu, out=None):
+    """gu bf16 [rows, 2I] = [gate | up] -> silu(gate) * up  [rows, I]"""
+    _bf16(gu)
+    rows, I2 = gu.shape
+    assert gu.is_contiguous() and I2 % 16 == 0
+    out = torch.empty((rows, I2 // 2), device=gu.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().slb_silu_mul_cat(_p(gu), _p(out), rows, I2 // 2, _stream()), "silu_mul_cat")
+    return out
+
+
+def silu_mul_cat_bwd(gu, dout, out=None):
+    """-> dgu bf16 [rows, 2I] = [dgate | dup]"""
+    _bf16(gu, dout)
+    rows, I2 = gu.shape
+    assert gu.is_contiguous() and dout.is_contiguous() and dout.shape == (rows, I2 // 2)
+    out = torch.empty_like(gu) if out is None else out
+    _check(load().slb_silu_mul_cat_bwd(_p(gu), _p(dout), _p(out), rows, I2 // 2, _stream()), "silu_mul_cat_bwd")
+    return out
+
+
 def flush_f32(x, y, accumulate=False):
     """y (bf16) = [y +] x (fp32)"""
     _f32(x); _bf16(y)

@@ -401,15 +401,37 @@ class TrainEngine:
     def w(self, key: str) -> Tensor:
         return self.P[key].detach()
 
-    def frozen(self):
-        """Concatenated q|k|v base weights / biases of the frozen Qwen2 layers (built once)."""
+    # the four LoRA-wrapped linear groups of a Qwen2 layer: (module prefix inside the layer, adapters sharing the input)
+    _GROUPS = (("qkv", "self_attn.", ("q_proj", "k_proj", "v_proj")), ("o", "self_attn.", ("o_proj",)),
+               ("gu", "mlp.", ("gate_proj", "up_proj")), ("d", "mlp.", ("down_proj",)))
+
+    def packed(self):
+        """Per layer and linear group, the frozen base weights of the adapters that share an input, stacked along the output
+        dimension, with the LoRA up-projections appended along k:  wx = [W | (alpha/r) B_blockdiag]  ([sum out, in + r * n]).
+        Forward:  y = [x | t] wx^T  with t = [A_j dropout_j(x)]_j  (slb_gemm_bf16 A2);  backward:  [dx | dt] = dy wx  (one
+        dgrad).  The W columns are written once (frozen); the B columns are refreshed from the live parameters by ONE
+        ``lora_pack`` launch at the start of every forward (``table``: their addresses inside the flat parameter store)."""
         if self._frozen is None:
-            out = []
-            for i in range(self.spec.llm_layers):
-                p = f"{LLM_PREFIX}model.layers.{i}.self_attn."
-                out.append((torch.cat([self.w(p + f"{n}_proj.base_layer.weight") for n in "qkv"], 0).contiguous(),
-                            torch.cat([self.w(p + f"{n}_proj.base_layer.bias") for n in "qkv"], 0).contiguous()))
-            self._frozen = out
+            s, r = self.spec, self.spec.lora_r
+            layers, table = [], []
+            for i in range(s.llm_layers):
+                p = f"{LLM_PREFIX}model.layers.{i}."
+                ly = {}
+                for name, sub, mods in self._GROUPS:
+                    ws = [self.w(p + sub + m + ".base_layer.weight") for m in mods]
+                    K = ws[0].shape[1]
+                    wx = torch.zeros((sum(w.shape[0] for w in ws), K + r * len(mods)), device=self.dev, dtype=torch.bfloat16)
+                    wx[:, :K] = torch.cat(ws, 0)
+                    row = 0
+                    for j, (m, w) in enumerate(zip(mods, ws)):
+                        b = self.w(p + sub + m + ".lora_B.default.weight")
+                        assert b.shape == (w.shape[0], r) and b.is_contiguous()
+                        table.append((b.data_ptr(), wx[row:, K + r * j:].data_ptr(), w.shape[0], wx.stride(0)))
+                        row += w.shape[0]
+                    ly[name] = wx
+                ly["bqkv"] = torch.cat([self.w(p + f"self_attn.{n}_proj.base_layer.bias") for n in "qkv"], 0).contiguous()
+                layers.append(ly)
+            self._frozen = dict(layers=layers, table=torch.tensor(table, dtype=torch.int64, device=self.dev), n=len(table))
         return self._frozen
 
     def still_attached(self) -> bool:
@@ -423,10 +445,12 @@ class TrainEngine:
         (same addresses); copies derived from the frozen weights are refreshed in place, inference engines and fp32 master
         weights are told to resynchronise."""
         if self._frozen is not None:
-            for i, (w, b) in enumerate(self._frozen):
-                p = f"{LLM_PREFIX}model.layers.{i}.self_attn."
-                torch.cat([self.w(p + f"{n}_proj.base_layer.weight") for n in "qkv"], 0, out=w)
-                torch.cat([self.w(p + f"{n}_proj.base_layer.bias") for n in "qkv"], 0, out=b)
+            for i, ly in enumerate(self._frozen["layers"]):
+                p = f"{LLM_PREFIX}model.layers.{i}."
+                for name, sub, mods in self._GROUPS:
+                    ws = [self.w(p + sub + m + ".base_layer.weight") for m in mods]
+                    ly[name][:, :ws[0].shape[1]] = torch.cat(ws, 0)
+                torch.cat([self.w(p + f"self_attn.{n}_proj.base_layer.bias") for n in "qkv"], 0, out=ly["bqkv"])
         self.store.generation += 1
         self.store.weights_epoch += 1
 
@@ -619,7 +643,7 @@ class TrainEngine:
         if rec is None:
             rec = dict(version=self.store.layout_version, x=torch.empty_like(inputs), bwd=None,
                        mask=None if mask is None else torch.empty_like(mask, dtype=torch.bool))
-            self.frozen()
+            self.packed()
             cap = TrainEngine._Capture(self)
             l0 = lib.LAUNCHES
             rec["out"], rec["saved"] = cap.run(lambda: self.llm_forward(rec["x"], rec["mask"], dropout, static=True))
@@ -767,33 +791,39 @@ class TrainEngine:
     # ==================================================================================================
     # Qwen2 decoder stack with un-merged LoRA
     # ==================================================================================================
-    def _lora_a(self, x: Tensor, pre: str, seed: Optional[int], seed_t: Optional[Tensor] = None):
-        """t = A dropout(x)   [first half of PEFT lora.Linear.forward]; ``seed_t``: this forward's copy of the step counter"""
-        if seed is not None:
-            xd = lib.dropout(x, self.spec.lora_dropout, seed, seed_dev=seed_t)
+    def _lora_down(self, x: Tensor, pre: str, mods, seeds, seed_t: Optional[Tensor]):
+        """t = [A_j dropout_j(x)]_j  ([M, r * n]; first half of PEFT lora.Linear.forward for the n adapters that share the input x).
+        Independent counter-based masks per adapter (PEFT keeps one nn.Dropout per wrapped linear), produced in one read of x;
+        ``seed_t``: this forward's copy of the step counter.  Returns (masked copies, t)."""
+        r, n = self.spec.lora_r, len(mods)
+        if seeds[0] is not None:
+            xds = lib.dropout_multi(x, self.spec.lora_dropout, seeds, seed_dev=seed_t)
         else:
-            xd = x
-        t = lib.gemm(xd, self.w(pre + "lora_A.default.weight"))
-        return xd, t, seed, seed_t
+            xds = [x] * n
+        t = torch.empty((x.shape[0], r * n), device=self.dev, dtype=torch.bfloat16)
+        self._par(*[(lambda j=j: lib.gemm(xds[j], self.w(pre + mods[j] + ".lora_A.default.weight"), out=t[:, r * j:r * (j + 1)])) for j in range(n)])
+        return xds, t
 
-    def _lora_b(self, rec, pre: str, y: Tensor) -> None:
-        """y (holding base(x)) += scale * B t"""
-        lib.gemm(rec[1], self.w(pre + "lora_B.default.weight"), out=y, residual=y, alpha=self.spec.lora_scale)
+    def _lora_bwd(self, dy: Tensor, cat: Tensor, K: int, pre: str, mods, rec, seeds, seed_t, out: Optional[Tensor] = None) -> Tensor:
+        """cat = dy [W | s B] = [dx_base | dt] (the dgrad over the concatenated weight has already produced the gradient of
+        every t_j).  Adds the adapters' parameter gradients  dB_j = s dy_j^T t_j,  dA_j = dt_j^T dropout_j(x)  (tcgen05 wgrad
+        GEMMs, on side streams) and returns  dx = dx_base + sum_j mask_j o (dt_j A_j)  (``lora_dx``)."""
+        r, n, sc = self.spec.lora_r, len(mods), self.spec.lora_scale
+        xds, t = rec
+        a_list = [self.w(pre + m + ".lora_A.default.weight") for m in mods]
+        rows = [a.shape[0] for a in (self.w(pre + m + ".lora_B.default.weight") for m in mods)]
 
-    def _lora_bwd_b(self, dy: Tensor, pre: str, rec) -> None:
-        self._wgrad(dy, rec[1], pre + "lora_B.default.weight", alpha=self.spec.lora_scale)
+        def grads():
+            o = 0
+            for j, m in enumerate(mods):
+                self._wgrad(dy[:, o:o + rows[j]], t[:, r * j:r * (j + 1)], pre + m + ".lora_B.default.weight", alpha=sc)
+                self._wgrad(cat[:, K + r * j:K + r * (j + 1)], xds[j], pre + m + ".lora_A.default.weight")
+                o += rows[j]
 
-    def _lora_bwd_a(self, dy: Tensor, pre: str, rec) -> Tensor:
-        """dA wgrad; returns the gradient w.r.t. the (dropped-out) LoRA input, to be added to the base dgrad"""
-        dt = lib.gemm(dy, self.w(pre + "lora_B.default.weight"), b_t=True, alpha=self.spec.lora_scale)
-        self._wgrad(dt, rec[0], pre + "lora_A.default.weight")
-        return lib.gemm(dt, self.w(pre + "lora_A.default.weight"), b_t=True)
-
-    def _lora_acc(self, dxd: Tensor, dx: Tensor, rec) -> None:
-        if rec[2] is None:
-            lib.add_inplace(dx, dxd)
-        else:
-            lib.dropout_add(dxd, dx, self.spec.lora_dropout, rec[2], seed_dev=rec[3])
+        def dx():
+            use = seeds[0] is not None
+            return lib.lora_dx(cat, K, a_list, p=self.spec.lora_dropout if use else 0.0, seeds=seeds if use else None, seed_dev=seed_t, out=out)
+        return self._par(dx, grads)[0]
 
     def llm_forward(self, inputs: Tensor, mask: Optional[Tensor], dropout: bool, static: bool = False):
         """inputs [B, Lt, D] bf16 -> (features after the final norm [B, Lt, D], saved).  ``static``: no host sync on
@@ -802,8 +832,7 @@ class TrainEngine:
         B, Lt, D = inputs.shape
         M = B * Lt
         dev, bf = self.dev, torch.bfloat16
-        Hq, Hkv, hd, I = s.llm_heads, s.llm_kv_heads, s.head_dim, s.llm_mlp
-        qd, kd = Hq * hd, Hkv * hd
+        Hq, Hkv, hd = s.llm_heads, s.llm_kv_heads, s.head_dim
         lmax = (Lt + 127) // 128 * 128
         kc = torch.zeros((s.llm_layers, B, Hkv, lmax, hd), device=dev, dtype=bf)
         vc = torch.zeros_like(kc)
@@ -815,97 +844,75 @@ class TrainEngine:
         self.seed_dev.add_(1)  # on the device: a replayed graph draws fresh masks
         sd_t = self.seed_dev.clone()  # this forward's own copy: its backward regenerates the same masks even if another forward ran since
 
-        def seed(i, j):
-            return (self.base_seed << 8) + i * 8 + j if use_drop else None
+        def seeds(i, js):
+            return [(self.base_seed << 8) + i * 8 + j if use_drop else None for j in js]
 
         x = inputs.reshape(M, D).contiguous()
-        frozen = self.frozen()
+        pk = self.packed()
+        lib.lora_pack(pk["table"], pk["n"], s.lora_r, s.lora_scale)   # this step's B matrices -> the k-tail of the concatenated weights
         layers = []
         for i in range(s.llm_layers):
             p = f"{LLM_PREFIX}model.layers.{i}."
             pa, pm = p + "self_attn.", p + "mlp."
+            ly = pk["layers"][i]
             r1 = torch.empty(M, device=dev, dtype=torch.float32)
             h1 = lib.rmsnorm(x, w(p + "input_layernorm.weight"), s.rms_eps, rstd=r1)
-            qkv = lib.gemm(h1, frozen[i][0], bias=frozen[i][1])
-            lq, lk, lv = self._par(lambda: self._lora_a(h1, pa + "q_proj.", seed(i, 0), sd_t), lambda: self._lora_a(h1, pa + "k_proj.", seed(i, 1), sd_t),
-                                   lambda: self._lora_a(h1, pa + "v_proj.", seed(i, 2), sd_t))
-            self._par(lambda: self._lora_b(lq, pa + "q_proj.", qkv[:, :qd]), lambda: self._lora_b(lk, pa + "k_proj.", qkv[:, qd:qd + kd]),
-                      lambda: self._lora_b(lv, pa + "v_proj.", qkv[:, qd + kd:]))
+            lqkv = self._lora_down(h1, pa, ("q_proj", "k_proj", "v_proj"), seeds(i, (0, 1, 2)), sd_t)
+            qkv = lib.gemm(h1, ly["qkv"], bias=ly["bqkv"], a2=lqkv[1])
             lib.rope_kv_write(qkv, kc[i], vc[i], B, Lt, 0, Hq, Hkv, s.rope_theta)
             lse = torch.empty((B, Hq, Lt), device=dev, dtype=torch.float32)
             att = lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], B, Lt, 0, Hq, Hkv, key_valid=kv_valid, lse=lse)
-            xm = lib.gemm(att, w(pa + "o_proj.base_layer.weight"), residual=x)
-            lo = self._lora_a(att, pa + "o_proj.", seed(i, 3), sd_t)
-            self._lora_b(lo, pa + "o_proj.", xm)
+            lo = self._lora_down(att, pa, ("o_proj",), seeds(i, (3,)), sd_t)
+            xm = lib.gemm(att, ly["o"], residual=x, a2=lo[1])
             r2 = torch.empty(M, device=dev, dtype=torch.float32)
             h2 = lib.rmsnorm(xm, w(p + "post_attention_layernorm.weight"), s.rms_eps, rstd=r2)
-            g = lib.gemm(h2, w(pm + "gate_proj.base_layer.weight"))
-            u = lib.gemm(h2, w(pm + "up_proj.base_layer.weight"))
-            lg, lu = self._par(lambda: self._lora_a(h2, pm + "gate_proj.", seed(i, 4), sd_t), lambda: self._lora_a(h2, pm + "up_proj.", seed(i, 5), sd_t))
-            self._lora_b(lg, pm + "gate_proj.", g)
-            self._lora_b(lu, pm + "up_proj.", u)
-            act = lib.silu_mul(g, u)
-            xo = lib.gemm(act, w(pm + "down_proj.base_layer.weight"), residual=xm)
-            ld = self._lora_a(act, pm + "down_proj.", seed(i, 6), sd_t)
-            self._lora_b(ld, pm + "down_proj.", xo)
-            layers.append(dict(x=x, r1=r1, h1=h1, qkv=qkv, lse=lse, att=att, xm=xm, r2=r2, h2=h2, g=g, u=u, act=act,
-                               lora=(lq, lk, lv, lo, lg, lu, ld)))
+            lgu = self._lora_down(h2, pm, ("gate_proj", "up_proj"), seeds(i, (4, 5)), sd_t)
+            gu = lib.gemm(h2, ly["gu"], a2=lgu[1])          # [M, 2I] = [gate | up]: one GEMM for both projections
+            act = lib.silu_mul_cat(gu)
+            ld = self._lora_down(act, pm, ("down_proj",), seeds(i, (6,)), sd_t)
+            xo = lib.gemm(act, ly["d"], residual=xm, a2=ld[1])
+            layers.append(dict(x=x, r1=r1, qkv=qkv, lse=lse, att=att, xm=xm, r2=r2, gu=gu, lora=(lqkv, lo, lgu, ld),
+                               seeds=(seeds(i, (0, 1, 2)), seeds(i, (3,)), seeds(i, (4, 5)), seeds(i, (6,)))))
             x = xo
         rf = torch.empty(M, device=dev, dtype=torch.float32)
         feats = lib.rmsnorm(x, w(LLM_PREFIX + "model.norm.weight"), s.rms_eps, rstd=rf)
-        saved = dict(B=B, Lt=Lt, layers=layers, kc=kc, vc=vc, kv_valid=kv_valid, xf=x, rf=rf)
+        saved = dict(B=B, Lt=Lt, layers=layers, kc=kc, vc=vc, kv_valid=kv_valid, xf=x, rf=rf, seed_t=sd_t)
         return feats.view(B, Lt, D), saved
 
     def llm_backward(self, dfeats: Tensor, sv) -> Tensor:
         s, w, st = self.spec, self.w, self.store
         B, Lt = sv["B"], sv["Lt"]
-        D = s.llm_hidden
+        D, I = s.llm_hidden, s.llm_mlp
         M = B * Lt
-        Hq, Hkv, hd = s.llm_heads, s.llm_kv_heads, s.head_dim
-        qd, kd = Hq * hd, Hkv * hd
-        kvv = sv["kv_valid"]
-        frozen = self.frozen()
+        Hq, Hkv = s.llm_heads, s.llm_kv_heads
+        kvv, sd_t = sv["kv_valid"], sv["seed_t"]
+        pk = self.packed()
         dx = lib.rmsnorm_bwd(dfeats.reshape(M, D).contiguous(), sv["xf"], w(LLM_PREFIX + "model.norm.weight"), sv["rf"])
         for i in reversed(range(s.llm_layers)):
             p = f"{LLM_PREFIX}model.layers.{i}."
             pa, pm = p + "self_attn.", p + "mlp."
-            a = sv["layers"][i]
+            a, ly = sv["layers"][i], pk["layers"][i]
             if "graph" not in sv:
                 sv["layers"][i] = None
-            lq, lk, lv, lo, lg, lu, ld = a["lora"]
+            lqkv, lo, lgu, ld = a["lora"]
+            sq, so, sg, sdn = a["seeds"]
             # ---- MLP ----
-            dact = lib.gemm(dx, w(pm + "down_proj.base_layer.weight"), b_t=True)
-            dxd, _ = self._par(lambda: self._lora_bwd_a(dx, pm + "down_proj.", ld), lambda: self._lora_bwd_b(dx, pm + "down_proj.", ld))
-            self._lora_acc(dxd, dact, ld)
-            dg, du = lib.silu_mul_bwd(a["g"], a["u"], dact)
-            dh2 = lib.gemm(dg, w(pm + "gate_proj.base_layer.weight"), b_t=True)
-            lib.gemm(du, w(pm + "up_proj.base_layer.weight"), b_t=True, out=dh2, residual=dh2)
-            dxg, dxu, _, _ = self._par(lambda: self._lora_bwd_a(dg, pm + "gate_proj.", lg), lambda: self._lora_bwd_a(du, pm + "up_proj.", lu),
-                                       lambda: self._lora_bwd_b(dg, pm + "gate_proj.", lg), lambda: self._lora_bwd_b(du, pm + "up_proj.", lu))
-            self._lora_acc(dxg, dh2, lg)
-            self._lora_acc(dxu, dh2, lu)
+            cat = lib.gemm(dx, ly["d"], b_t=True)                       # [dact_base | dt_down]
+            dact = self._lora_bwd(dx, cat, I, pm, ("down_proj",), ld, sdn, sd_t)
+            dgu = lib.silu_mul_cat_bwd(a["gu"], dact)                   # [dgate | dup]
+            cat = lib.gemm(dgu, ly["gu"], b_t=True)                     # [dh2_base | dt_gate dt_up]
+            dh2 = self._lora_bwd(dgu, cat, D, pm, ("gate_proj", "up_proj"), lgu, sg, sd_t)
             dxm = lib.rmsnorm_bwd(dh2, a["xm"], w(p + "post_attention_layernorm.weight"), a["r2"])
             lib.add_inplace(dxm, dx)
             # ---- attention ----
-            datt = lib.gemm(dxm, w(pa + "o_proj.base_layer.weight"), b_t=True)
-            dxo, _ = self._par(lambda: self._lora_bwd_a(dxm, pa + "o_proj.", lo), lambda: self._lora_bwd_b(dxm, pa + "o_proj.", lo))
-            self._lora_acc(dxo, datt, lo)
+            cat = lib.gemm(dxm, ly["o"], b_t=True)                      # [datt_base | dt_o]
+            datt = self._lora_bwd(dxm, cat, Hq * s.head_dim, pa, ("o_proj",), lo, so, sd_t)
             delta = lib.attn_delta(a["att"], datt, B, Lt, Hq)
             dq, dk, dv = lib.attn_gqa_bwd(a["qkv"], s.qkv_dim, sv["kc"][i], sv["vc"][i], datt, a["lse"], delta, B, Lt, Hq, Hkv, key_valid=kvv)
             dqkv = lib.rope_bwd(dq, dk, dv, B, Lt, Hq, Hkv, s.rope_theta)
             del dq, dk, dv
-            dh1 = lib.gemm(dqkv, frozen[i][0], b_t=True)
-            gq, gk, gv = dqkv[:, :qd], dqkv[:, qd:qd + kd], dqkv[:, qd + kd:]
-
-            def all_b():
-                self._lora_bwd_b(gq, pa + "q_proj.", lq)
-                self._lora_bwd_b(gk, pa + "k_proj.", lk)
-                self._lora_bwd_b(gv, pa + "v_proj.", lv)
-            dxq, dxk, dxv, _ = self._par(lambda: self._lora_bwd_a(gq, pa + "q_proj.", lq), lambda: self._lora_bwd_a(gk, pa + "k_proj.", lk),
-                                         lambda: self._lora_bwd_a(gv, pa + "v_proj.", lv), all_b)
-            self._lora_acc(dxq, dh1, lq)
-            self._lora_acc(dxk, dh1, lk)
-            self._lora_acc(dxv, dh1, lv)
+            cat = lib.gemm(dqkv, ly["qkv"], b_t=True)                   # [dh1_base | dt_q dt_k dt_v]
+            dh1 = self._lora_bwd(dqkv, cat, D, pa, ("q_proj", "k_proj", "v_proj"), lqkv, sq, sd_t)
             dxi = lib.rmsnorm_bwd(dh1, a["x"], w(p + "input_layernorm.weight"), a["r1"])
             lib.add_inplace(dxi, dxm)
             dx = dxi

@@ -211,3 +211,59 @@ def test_attn_delta_rowwise_dot(lib, B, L, H):
     want = (o.float() * do.float()).view(B, L, H, 64).sum(-1).permute(0, 2, 1)
     assert got.shape == (B, H, L)
     assert (got - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
+
+
+# ---- un-merged LoRA training path: side kernels of the K-concatenated formulation (csrc/lora.cu) ----
+def test_dropout_multi_matches_dropout(lib):
+    x = rnd(621, 896, seed=1)
+    sd = torch.tensor([5], device="cuda", dtype=torch.int64)
+    seeds = [0x515100, 0x515101, 0x515102]
+    outs = lib.dropout_multi(x, 0.1, seeds, seed_dev=sd)
+    for s, o in zip(seeds, outs):
+        assert torch.equal(o, lib.dropout(x, 0.1, s, seed_dev=sd))
+    assert not torch.equal(outs[0], outs[1])   # independent masks per adapter
+    keep = (outs[0] != 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.01, keep
+
+
+def test_lora_pack(lib):
+    r = 32
+    srcs = [rnd(896, r, seed=1), rnd(128, r, seed=2), rnd(4864, r, seed=3)]
+    K = 896
+    wx = torch.zeros(896 + 128, K + 2 * r, device="cuda", dtype=torch.bfloat16)
+    wd = torch.zeros(4864, 64 + r, device="cuda", dtype=torch.bfloat16)
+    dsts = [wx[:, K:], wx[896:, K + r:], wd[:, 64:]]
+    table = torch.tensor([(s.data_ptr(), d.data_ptr(), s.shape[0], d.stride(0)) for s, d in zip(srcs, dsts)], dtype=torch.int64, device="cuda")
+    lib.lora_pack(table, 3, r, 2.0)
+    assert torch.equal(wx[:896, K:K + r], (2.0 * srcs[0].float()).to(torch.bfloat16))
+    assert torch.equal(wx[896:, K + r:], (2.0 * srcs[1].float()).to(torch.bfloat16))
+    assert torch.equal(wd[:, 64:], (2.0 * srcs[2].float()).to(torch.bfloat16))
+    assert float(wx[:, :K].abs().max()) == 0.0 and float(wx[:896, K + r:].abs().max()) == 0.0 and float(wd[:, :64].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,K,n,p", [(621, 896, 3, 0.1), (300, 4864, 1, 0.1), (130, 896, 2, 0.0), (64, 256, 4, 0.25)])
+def test_lora_dx(lib, M, K, n, p):
+    """out = base + sum_j mask_j o (dt_j A_j) / (1 - p): masks taken from slb_dropout with the same seeds"""
+    r = 32
+    cat = rnd(M, K + r * n + 8, seed=1)[:, :K + r * n]          # row stride != width
+    A = [rnd(r, K, seed=10 + j, scale=0.2) for j in range(n)]
+    seeds = [0xABC00 + j for j in range(n)]
+    sd = torch.tensor([3], device="cuda", dtype=torch.int64)
+    got = lib.lora_dx(cat, K, A, p=p, seeds=seeds if p > 0 else None, seed_dev=sd)
+    ref = cat[:, :K].float()
+    ones = torch.ones(M, K, device="cuda", dtype=torch.bfloat16)
+    for j in range(n):
+        m = lib.dropout(ones, p, seeds[j], seed_dev=sd).float() if p > 0 else ones.float()   # keep / (1 - p)
+        ref = ref + m * (cat[:, K + r * j:K + r * (j + 1)].float() @ A[j].float())
+    assert relerr(got, ref) < 1e-2
+
+
+def test_silu_mul_cat(lib):
+    M, I = 333, 4864
+    gu, dout = rnd(M, 2 * I, seed=1), rnd(M, I, seed=2)
+    g, u = gu[:, :I].float().requires_grad_(), gu[:, I:].float().requires_grad_()
+    ref = F.silu(g) * u
+    ref.backward(dout.float())
+    assert relerr(lib.silu_mul_cat(gu), ref) < 1e-2
+    dgu = lib.silu_mul_cat_bwd(gu, dout)
+    assert relerr(dgu[:, :I], g.grad) < 1e-2 and relerr(dgu[:, I:], u.grad) < 1e-2
