@@ -32,8 +32,8 @@ constexpr int kPBuf = BQ * BKV * 2;
 constexpr int kSmBar = kSmP + 2 * kPBuf;
 constexpr int kSmTotal = kSmBar + 256;
 constexpr float kLazyThreshold = 8.0f;        // log2 units
-constexpr int kDefaultPTmem = 0;              // 1: P operand of the PV product in tensor memory (tcgen05.st + TS-mode MMA)
-constexpr int kDefaultEmuPairs = 0;           // pairs per 16 whose exp2 runs on the FMA / ALU pipes (ex2_emu2)
+constexpr int kDefaultPTmem = 1;              // 1: P operand of the PV product in tensor memory (tcgen05.st + TS-mode MMA)
+constexpr int kDefaultEmuPairs = 4;           // pairs per 16 whose exp2 runs on the FMA / ALU pipes (ex2_emu2)
 #ifndef VIT2_NO_SPEC
 #define VIT2_NO_SPEC 1  /* speculative exp pass disabled: no measurable gain, see DESIGN.md */
 #endif

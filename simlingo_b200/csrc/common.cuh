@@ -392,6 +392,19 @@ __device__ __forceinline__ uint64_t gelu_erf_poly2(uint64_t x2) {
   const uint64_t h = f2mul(x2, f2splat(0.5f));     // un-clamped x / 2: gelu(x) -> x for large x, -> -0 * ... = 0 for large -x
   return f2fma(h, e, h);
 }
+// ---- counter-based dropout mask (LoRA input dropout of the training path) ----
+// One 64-bit hash per aligned group of 4 consecutive elements, 16 bits per element: element i of the flat index space is kept
+// iff bits16(hash(seed', i >> 2), i & 3) >= thresh16, p quantised to 1 / 65536 (0.1 -> 6554 / 65536).  Every kernel that applies
+// or re-generates a mask (dropout, dropout_add, dropout_multi, lora_dx) goes through these three helpers.
+constexpr uint64_t kDropGold = 0x9E3779B97F4A7C15ULL;
+__device__ __forceinline__ uint64_t drop_hash4(uint64_t seed_mul, uint64_t group) {
+  uint64_t z = seed_mul + group;
+  z ^= z >> 33; z *= 0xff51afd7ed558ccdULL; z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33;
+  return z;
+}
+__device__ __forceinline__ bool drop_keep(uint64_t h, int e, uint32_t thresh16) { return ((uint32_t)(h >> (16 * e)) & 0xffffu) >= thresh16; }
+static inline uint32_t drop_thresh16(float p) { return (uint32_t)((double)p * 65536.0 + 0.5); }
+static inline float drop_scale(float p) { return 65536.0f / (65536.0f - (float)drop_thresh16(p)); }   // 1 / P(keep), exactly
 __device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.0f + ex2_approx(-x * 1.4426950408889634f)); }
 
 // host: build a 2-D (or 3-D) bf16 TMA descriptor with 128B swizzle (inner box = 64 elements = 128 bytes)

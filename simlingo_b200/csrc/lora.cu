@@ -14,13 +14,8 @@
 
 namespace {
 
-constexpr uint64_t kGold = 0x9E3779B97F4A7C15ULL;
 constexpr int kMaxAdapters = 4;
 
-__device__ __forceinline__ uint32_t mix32(uint64_t z) {   // same generator as dropout_kernel (backward.cu)
-  z ^= z >> 33; z *= 0xff51afd7ed558ccdULL; z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33;
-  return (uint32_t)z;
-}
 __device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
@@ -47,7 +42,7 @@ __global__ void dropout_multi_kernel(const bf16* __restrict__ x, MultiArgs a, si
   const uint64_t add = seed_dev ? (*seed_dev << 16) : 0;
   uint64_t sm[kMaxAdapters];
 #pragma unroll
-  for (int j = 0; j < kMaxAdapters; ++j) sm[j] = (a.seed[j] + add) * kGold;
+  for (int j = 0; j < kMaxAdapters; ++j) sm[j] = (a.seed[j] + add) * kDropGold;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float v[8];
     load8(x + i * 8, v);
@@ -55,8 +50,9 @@ __global__ void dropout_multi_kernel(const bf16* __restrict__ x, MultiArgs a, si
     for (int j = 0; j < kMaxAdapters; ++j) {
       if (j < a.n) {
         float o[8];
+        const uint64_t h0 = drop_hash4(sm[j], 2 * i), h1 = drop_hash4(sm[j], 2 * i + 1);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (mix32(sm[j] + i * 8 + e) >= thresh) ? v[e] * scale : 0.f;
+        for (int e = 0; e < 8; ++e) o[e] = drop_keep(e < 4 ? h0 : h1, e & 3, thresh) ? v[e] * scale : 0.f;
         store8(a.y[j] + i * 8, o);
       }
     }
@@ -81,7 +77,12 @@ __global__ void lora_pack_kernel(const PackEntry* __restrict__ tab, int r8, floa
 }
 
 // ---- lora_dx ------------------------------------------------------------------------------------------------------------
+// Block = 64 rows x 128 columns, 8 warps; warp w owns rows 16 (w & 3) .., columns 64 (w >> 2) ..  The rank-r products run on
+// mma.sync.m16n8k16 (bf16, fp32 accumulators): dt tile [64, r] and A_j tile [r, 128] staged in padded shared memory (conflict-free
+// 32-bit A-fragment loads / ldmatrix.trans B fragments), one pass per adapter, mask applied on the accumulator fragment, fp32 sum
+// over the adapters on top of the base dgrad, one rounding.  (A first CUDA-core version was LSU / FMA bound at 51 us per call.)
 constexpr int DX_ROWS = 64, DX_COLS = 128, DX_THREADS = 256, DX_RMAX = 64;
+constexpr int DX_LDA = DX_COLS + 8;   // bf16 elements per sA row (272 B: 8 consecutive rows hit 32 distinct banks)
 struct LoraDxArgs {
   const bf16* in; long long ld_in;   // [M, >= K + r*n]: base dgrad in columns [0, K), dt_j in columns [K + r*j, K + r*(j+1))
   bf16* out; long long ld_out;       // [M, K]
@@ -92,28 +93,35 @@ struct LoraDxArgs {
   float scale;
   int use_mask;
 };
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
 __global__ void __launch_bounds__(DX_THREADS)
 lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
-  __shared__ __align__(16) bf16 sA[DX_RMAX * DX_COLS];   // [r][128]
-  __shared__ __align__(16) bf16 sD[DX_ROWS * DX_RMAX];   // [64][r]
-  const int tid = threadIdx.x;
-  const int cg = tid & 15, rg = tid >> 4;
+  __shared__ __align__(16) bf16 sA[DX_RMAX * DX_LDA];            // [r][128 + 8]
+  __shared__ __align__(16) bf16 sD[DX_ROWS * (DX_RMAX + 8)];     // [64][r + 8]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int col_tile = blockIdx.x * DX_COLS, row_tile = blockIdx.y * DX_ROWS;
-  const int c0 = col_tile + cg * 8;
-  const bool col_ok = c0 < a.K;
+  const int wr = (warp & 3) * 16, wc = (warp >> 2) * 64;
+  const int r = a.r, r8 = r >> 3, ldd = r + 8;
   const uint64_t add = seed_dev ? (*seed_dev << 16) : 0;
-  float tot[4][8];
+  const int row0 = row_tile + wr + g, row1 = row0 + 8;
+  float tot[8][4];
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int row = row_tile + rg * 4 + rr;
-    if (row < a.M && col_ok) {
-      load8(a.in + (long long)row * a.ld_in + c0, tot[rr]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) tot[rr][e] = 0.f;
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = col_tile + wc + nt * 8 + 2 * t;
+    float2 v0 = make_float2(0.f, 0.f), v1 = v0;
+    if (c < a.K) {
+      if (row0 < a.M) v0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.in + (long long)row0 * a.ld_in + c));
+      if (row1 < a.M) v1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.in + (long long)row1 * a.ld_in + c));
     }
+    tot[nt][0] = v0.x; tot[nt][1] = v0.y; tot[nt][2] = v1.x; tot[nt][3] = v1.y;
   }
-  const int r = a.r, r8 = r >> 3;
   for (int j = 0; j < a.n; ++j) {
     __syncthreads();
     for (int q = tid; q < r * (DX_COLS / 8); q += DX_THREADS) {
@@ -121,50 +129,62 @@ lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
       const int c = col_tile + cc * 8;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (c < a.K) v = *reinterpret_cast<const uint4*>(a.A[j] + (long long)k * a.K + c);
-      *reinterpret_cast<uint4*>(sA + k * DX_COLS + cc * 8) = v;
+      *reinterpret_cast<uint4*>(sA + k * DX_LDA + cc * 8) = v;
     }
     for (int q = tid; q < DX_ROWS * r8; q += DX_THREADS) {
       const int rw = q / r8, cc = q % r8;
       const int row = row_tile + rw;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (row < a.M) v = *reinterpret_cast<const uint4*>(a.in + (long long)row * a.ld_in + a.K + j * r + cc * 8);
-      *reinterpret_cast<uint4*>(sD + rw * r + cc * 8) = v;
+      *reinterpret_cast<uint4*>(sD + rw * ldd + cc * 8) = v;
     }
     __syncthreads();
-    float acc[4][8];
+    float acc[8][4];
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr)
+    for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[rr][e] = 0.f;
-    for (int k = 0; k < r; ++k) {
-      float av[8];
-      load8(sA + k * DX_COLS + cg * 8, av);
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    for (int k0 = 0; k0 < r; k0 += 16) {
+      const bf16* d0 = sD + (wr + g) * ldd + k0 + 2 * t;
+      const uint32_t a0 = *reinterpret_cast<const uint32_t*>(d0), a1 = *reinterpret_cast<const uint32_t*>(d0 + 8 * ldd);
+      const uint32_t a2 = *reinterpret_cast<const uint32_t*>(d0 + 8), a3 = *reinterpret_cast<const uint32_t*>(d0 + 8 * ldd + 8);
+      // ldmatrix.x4.trans: lanes 0-7 address rows k0..k0+7 of n-tile nt, 8-15 rows k0+8.., 16-23 / 24-31 the same for n-tile nt + 1
+      const uint32_t base = smem_u32(sA + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * DX_LDA + wc + (lane >> 4) * 8);
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const float d = __bfloat162float(sD[(rg * 4 + rr) * r + k]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[rr][e] = fmaf(d, av[e], acc[rr][e]);
+      for (int nt = 0; nt < 8; nt += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_trans(base + nt * 8 * 2, b0, b1, b2, b3);
+        mma_16816(acc[nt], a0, a1, a2, a3, b0, b1);
+        mma_16816(acc[nt + 1], a0, a1, a2, a3, b2, b3);
       }
     }
     if (a.use_mask) {
-      const uint64_t sm = (a.seed[j] + add) * kGold;
+      const uint64_t sm = (a.seed[j] + add) * kDropGold;
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const uint64_t base = (uint64_t)(row_tile + rg * 4 + rr) * (uint64_t)a.K + (uint64_t)c0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) tot[rr][e] += (mix32(sm + base + e) >= a.thresh) ? acc[rr][e] * a.scale : 0.f;
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = col_tile + wc + nt * 8 + 2 * t;    // elements c, c + 1 of rows row0 / row1; (c & 3) is 0 or 2
+        const uint64_t i0 = (uint64_t)row0 * (uint64_t)a.K + (uint64_t)c, i1 = (uint64_t)row1 * (uint64_t)a.K + (uint64_t)c;
+        const uint64_t h0 = drop_hash4(sm, i0 >> 2), h1 = drop_hash4(sm, i1 >> 2);
+        const int e = c & 3;
+        tot[nt][0] += drop_keep(h0, e, a.thresh) ? acc[nt][0] * a.scale : 0.f;
+        tot[nt][1] += drop_keep(h0, e + 1, a.thresh) ? acc[nt][1] * a.scale : 0.f;
+        tot[nt][2] += drop_keep(h1, e, a.thresh) ? acc[nt][2] * a.scale : 0.f;
+        tot[nt][3] += drop_keep(h1, e + 1, a.thresh) ? acc[nt][3] * a.scale : 0.f;
       }
     } else {
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr)
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) tot[rr][e] += acc[rr][e];
+        for (int e = 0; e < 4; ++e) tot[nt][e] += acc[nt][e];
     }
   }
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int row = row_tile + rg * 4 + rr;
-    if (row < a.M && col_ok) store8(a.out + (long long)row * a.ld_out + c0, tot[rr]);
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = col_tile + wc + nt * 8 + 2 * t;
+    if (c < a.K) {
+      if (row0 < a.M) *reinterpret_cast<uint32_t*>(a.out + (long long)row0 * a.ld_out + c) = pack_bf16(tot[nt][0], tot[nt][1]);
+      if (row1 < a.M) *reinterpret_cast<uint32_t*>(a.out + (long long)row1 * a.ld_out + c) = pack_bf16(tot[nt][2], tot[nt][3]);
+    }
   }
 }
 
@@ -219,8 +239,7 @@ extern "C" int slb_dropout_multi(const void* x, void* const* ys, const uint64_t*
     SLB_CHECK_ARG(j >= n_out || (ys[j] && ((uintptr_t)ys[j] & 15) == 0), "dropout_multi: output %d null or not 16-byte aligned", j);
   }
   a.n = n_out;
-  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
-  dropout_multi_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)x, a, n / 8, thresh, 1.0f / (1.0f - p), seed_dev);
+  dropout_multi_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)x, a, n / 8, drop_thresh16(p), drop_scale(p), seed_dev);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -235,8 +254,8 @@ extern "C" int slb_lora_pack(const int64_t* table_dev, int n_entries, int rank, 
 extern "C" int slb_lora_dx(const void* in, int64_t ld_in, void* out, int64_t ld_out, const void* const* A, const uint64_t* seeds,
                            int n_adapters, int M, int K, int rank, float p, const uint64_t* seed_dev, void* stream) {
   SLB_CHECK_ARG(in && out && A && n_adapters >= 1 && n_adapters <= kMaxAdapters, "lora_dx: n_adapters=%d (1..%d)", n_adapters, kMaxAdapters);
-  SLB_CHECK_ARG(M > 0 && K > 0 && (K % 8) == 0 && rank > 0 && (rank % 8) == 0 && rank <= DX_RMAX, "lora_dx: M=%d K=%d rank=%d (rank <= %d)", M, K,
-                rank, DX_RMAX);
+  SLB_CHECK_ARG(M > 0 && K > 0 && (K % 8) == 0 && rank > 0 && (rank % 16) == 0 && rank <= DX_RMAX, "lora_dx: M=%d K=%d rank=%d (multiple of 16, <= %d)", M,
+                K, rank, DX_RMAX);
   SLB_CHECK_ARG((ld_in % 8) == 0 && (ld_out % 8) == 0 && ld_in >= K + (int64_t)rank * n_adapters && ld_out >= K &&
                 ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "lora_dx: strides / alignment (ld_in=%lld ld_out=%lld)",
                 (long long)ld_in, (long long)ld_out);
@@ -250,8 +269,8 @@ extern "C" int slb_lora_dx(const void* in, int64_t ld_in, void* out, int64_t ld_
   }
   a.n = n_adapters; a.M = M; a.K = K; a.r = rank;
   a.use_mask = (seeds != nullptr && p > 0.f) ? 1 : 0;
-  a.thresh = (uint32_t)((double)p * 4294967296.0);
-  a.scale = 1.0f / (1.0f - p);
+  a.thresh = drop_thresh16(p);
+  a.scale = drop_scale(p);
   lora_dx_kernel<<<dim3(ceil_div(K, DX_COLS), ceil_div(M, DX_ROWS)), DX_THREADS, 0, ST(stream)>>>(a, seed_dev);
   SLB_LAUNCH_CHECK();
   return SLB_OK;

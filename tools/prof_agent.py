@@ -9,7 +9,7 @@ from torch.profiler import ProfilerActivity, profile
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 25
 spec = S.INTERNVL2_1B
 dev = torch.device("cuda", 0)
-model = Bn.build_planted_model(spec, dev)
+model = Bn.build_model(spec, dev)
 ex = Bn.make_example(Bn.host_agent_batch(spec, 1, 99, G), dev)
 for _ in range(4):
     model(ex)
