@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Host-side plumbing of the C ABI: error string, device query, TMA descriptor encoding.
 #include "common.cuh"
 #include "../../include/simlingo_b200.h"
@@ -25,6 +26,12 @@ extern "C" int slb_num_sms(void) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+int slb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SLB_NO_PDL"); v = (e && atoi(e)) ? 0 : 1; }
+  return v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -272,6 +272,8 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
                   const uint8_t* __restrict__ key_valid, int key_valid_ld, bf16* __restrict__ out, long long ldo, int lq, int past,
                   int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();   // q / the newest K, V rows are written by the RoPE kernel right before us
   if (past_dev) past = *past_dev;  // position counter kept on the device: the same CUDA graph serves every decode step
   float* qs = sm;                        // 64
   float* red = sm + 64;                  // 2 * kSmallWarps
@@ -374,6 +376,8 @@ attn_decode_group_kernel(const bf16* __restrict__ q, long long ldq, const bf16* 
                          const uint8_t* __restrict__ key_valid, int key_valid_ld, bf16* __restrict__ out, long long ldo, int lq, int past,
                          int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   if (past_dev) past = *past_dev;
   const int G = hq / hkv;
   float* qs = sm;                                   // [G][64]
@@ -561,19 +565,18 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
       SLB_CUDA(cudaFuncSetAttribute(attn_decode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set = smem;
     }
-    attn_decode_group_kernel<<<dim3(lq, hkv, batch), kGrpThreads, smem, (cudaStream_t)stream>>>(
-        (const bf16*)q, ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax,
-        hq, hkv, scale, past_dev);
-    SLB_LAUNCH_CHECK();
+    SLB_CUDA(slb_launch_pdl(attn_decode_group_kernel, dim3(lq, hkv, batch), dim3(kGrpThreads), smem, (cudaStream_t)stream, (const bf16*)q,
+                            (long long)ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq,
+                            past, lmax, hq, hkv, scale, (const int*)past_dev));
     return SLB_OK;
   }
   if (lq <= 32 && lse == nullptr) {
     dim3 grid(lq, hq, batch);
     const size_t smem = (64 + 2 * kSmallWarps + kSmallWarps * 64 + (size_t)lmax) * sizeof(float);
     SLB_CHECK_ARG(smem <= 48 * 1024, "attn_gqa: lmax=%d too long for the small-Lq kernel", lmax);
-    attn_small_kernel<<<grid, kSmallThreads, smem, (cudaStream_t)stream>>>((const bf16*)q, ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid,
-                                                               key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq, hkv, scale, past_dev);
-    SLB_LAUNCH_CHECK();
+    SLB_CUDA(slb_launch_pdl(attn_small_kernel, grid, dim3(kSmallThreads), smem, (cudaStream_t)stream, (const bf16*)q, (long long)ldq,
+                            (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq,
+                            hkv, scale, (const int*)past_dev));
     return SLB_OK;
   }
   SLB_CHECK_ARG(past_dev == nullptr, "attn_gqa: a device-side position is only supported for chunks of <= 32 queries without lse");

@@ -97,6 +97,8 @@ attn_gqa2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_trigger();
+  pdl_wait();   // q / K / V come from the RoPE kernel right before us
 
   // item k of this CTA -> (batch, kv head, query block, first head of the pair, number of heads in the pair); heaviest first
   auto decode = [&](int k, int& b, int& g, int& qb, int& h0, int& nh) {
@@ -406,8 +408,7 @@ int slb_attn_gqa2_try(const void* q, int64_t ldq, const void* kcache, const void
     if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_gqa2 attribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
-  attn_gqa2_kernel<<<grid, G2_THREADS, kSmTotal, stream>>>(tq, tk, tv, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = slb_launch_pdl(attn_gqa2_kernel, dim3(grid), dim3(G2_THREADS), (size_t)kSmTotal, stream, tq, tk, tv, p);
   if (e != cudaSuccess) *rc_out = slb_fail(SLB_ECUDA, "attn_gqa2 launch: %s", cudaGetErrorString(e));
   return 1;
 }

@@ -167,6 +167,8 @@ attn_vit2_kernel(const __grid_constant__ CUtensorMap tmap, Vit2Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_trigger();
+  pdl_wait();   // qkv comes from the projection GEMM right before us
 
   // item index -> (first patch-token row, head, tile)
   auto decode = [&](int k, int& q0, int& h, int& t) {
@@ -455,6 +457,8 @@ constexpr int kClsThreads = 512, kClsWarps = kClsThreads / 32, kClsHeads = 4;
 __global__ void __launch_bounds__(kClsThreads)
 attn_vit_cls_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int n_tokens, int heads, float scale) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   float* qs = sm;                                   // [4][64]
   float* red = qs + kClsHeads * 64;                 // [2][kClsWarps][4]
   float* part = red + 2 * kClsWarps * kClsHeads;    // [kClsWarps][256]
@@ -566,8 +570,7 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal);
     if (e != cudaSuccess) return e;
-    kern<<<grid, V2_THREADS, kSmTotal, stream>>>(tm, p);
-    return cudaGetLastError();
+    return slb_launch_pdl(kern, dim3(grid), dim3(V2_THREADS), (size_t)kSmTotal, stream, tm, p);
   };
   cudaError_t e;
   // software-exp2 share (pairs out of 16 per 32-score chunk): SLB_VIT2_EMU selects 0 / 4 / 5 / 6 / 8 for tuning runs; valid
@@ -608,8 +611,7 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
 #endif
   if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_vit2 launch: %s", cudaGetErrorString(e)); return 1; }
   const size_t smem = ((size_t)kClsHeads * 64 + 2 * kClsWarps * kClsHeads + kClsWarps * 256 + (size_t)kClsHeads * n_tokens) * sizeof(float);
-  attn_vit_cls_kernel<<<dim3(heads / kClsHeads, tiles), kClsThreads, smem, stream>>>((const bf16*)qkv, (bf16*)out, lse, n_tokens, heads, 0.125f);
-  e = cudaGetLastError();
+  e = slb_launch_pdl(attn_vit_cls_kernel, dim3(heads / kClsHeads, tiles), dim3(kClsThreads), smem, stream, (const bf16*)qkv, (bf16*)out, lse, n_tokens, heads, 0.125f);
   if (e != cudaSuccess) *rc_out = slb_fail(SLB_ECUDA, "attn_vit_cls launch: %s", cudaGetErrorString(e));
   return 1;
 }

@@ -392,6 +392,27 @@ __device__ __forceinline__ uint64_t gelu_erf_poly2(uint64_t x2) {
   const uint64_t h = f2mul(x2, f2splat(0.5f));     // un-clamped x / 2: gelu(x) -> x for large x, -> -0 * ... = 0 for large -x
   return f2fma(h, e, h);
 }
+// ---- programmatic dependent launch (decode chain: ~150 small dependent kernels per generated token) ----
+// A kernel launched through slb_launch_pdl may become resident while its predecessor in the stream is still running; everything it
+// does before pdl_wait() must be independent of the predecessor's output (weight prefetch), pdl_wait() returns once the predecessor
+// has completed and its writes are visible.  pdl_trigger() (early in the kernel) lets the successor start launching.  Both are
+// no-ops for a plain launch, and a predecessor that never triggers releases its successor when it exits (plain stream order).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+int slb_pdl_enabled();   // api.cu: 1 unless SLB_NO_PDL=1 (A/B timing)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t slb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = slb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- counter-based dropout mask (LoRA input dropout of the training path) ----
 // One 64-bit hash per aligned group of 4 consecutive elements, 16 bits per element: element i of the flat index space is kept
 // iff bits16(hash(seed', i >> 2), i & 3) >= thresh16, p quantised to 1 / 65536 (0.1 -> 6554 / 65536).  Every kernel that applies

@@ -35,6 +35,8 @@ template <int MAXV, bool RMS, typename XT = bf16>  // XT = float: the fp32 resid
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 norm_fwd_kernel(const XT* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b, bf16* __restrict__ y,
                 int rows, int cols, float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -192,13 +194,20 @@ __global__ void vit_assemble_kernel(const bf16* __restrict__ patch_out, const bf
 // (x[d..d+7] and its rotation partner x[d+32..d+39]); q is rotated in place, rotated k and plain v go to the caches.
 // ------------------------------------------------------------------------------------------------
 __global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, int batch, int lq,
-                                     int past, int lmax, int hq, int hkv, float log2_theta, const int* __restrict__ past_dev) {
+                                     int past, int lmax, int hq, int hkv, float log2_theta, const int* __restrict__ past_dev, int per_head) {
+  pdl_trigger();
+  pdl_wait();   // qkv comes from the projection kernel right before us
   if (past_dev) past = *past_dev;
   const int heads = hq + 2 * hkv;
-  const size_t total = (size_t)batch * lq * 4;
+  // few rows (decode, query append): one thread per (row, head, 8 pairs) - with one thread per (row, 8 pairs) walking over the 18
+  // heads the single-token call was a chain of 36 dependent 16-byte round trips (8 us); many rows: the head loop amortises sin / cos
+  const int hsplit = per_head ? heads : 1;
+  const size_t total = (size_t)batch * lq * 4 * hsplit;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx & 3);          // dims 8c .. 8c+7 (and +32)
-    const size_t row = idx >> 2;           // b*lq + i
+    const size_t rh = idx >> 2;
+    const size_t row = rh / hsplit;        // b*lq + i
+    const int h_lo = per_head ? (int)(rh % hsplit) : 0, h_hi = per_head ? h_lo + 1 : heads;
     const int i = (int)(row % lq), b = (int)(row / lq);
     float sn[8], cs[8];
 #pragma unroll
@@ -207,7 +216,7 @@ __global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, bf16* __restrict__ 
       sincosf((float)(past + i) * inv_freq, &sn[e], &cs[e]);
     }
     bf16* rowp = qkv + row * (size_t)(heads * 64);
-    for (int h = 0; h < heads; ++h) {
+    for (int h = h_lo; h < h_hi; ++h) {
       bf16* src = rowp + h * 64 + c * 8;
       const uint4 lo = *reinterpret_cast<const uint4*>(src), hi = *reinterpret_cast<const uint4*>(src + 32);
       if (h >= hq + hkv) {  // v: plain copy into the cache
@@ -351,8 +360,32 @@ __global__ void __launch_bounds__(1024)
 argmax_kernel(const float* __restrict__ logits, long long ld, int cols, long long* __restrict__ out_idx, float* __restrict__ margin) {
   __shared__ Top2 sh[32];
   const float* r = logits + (size_t)blockIdx.x * ld;
+  pdl_trigger();
+  pdl_wait();
   Top2 t{-INFINITY, 0x7fffffff, -INFINITY};
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) top2_push(t, r[i], i);
+  // 16-byte loads, four in flight per thread (the scalar loop was one dependent 4-byte round trip per 1024 logits: 68 us for the
+  // 151 655-wide vocabulary row of a decode step); scalar head / tail around the aligned body
+  const int mis = (int)((reinterpret_cast<uintptr_t>(r) & 15) >> 2);
+  const int head = min(cols, mis ? 4 - mis : 0);
+  const int nvec = (cols - head) >> 2;
+  if ((int)threadIdx.x < head) top2_push(t, r[threadIdx.x], threadIdx.x);
+  const float4* rv = reinterpret_cast<const float4*>(r + head);
+  for (int v0 = 0; v0 < nvec; v0 += 4 * blockDim.x) {
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = v0 + u * blockDim.x + threadIdx.x;
+      q[u] = v < nvec ? rv[v] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = v0 + u * (int)blockDim.x + (int)threadIdx.x;
+      if (v >= nvec) continue;
+      const int i0 = head + 4 * v;
+      top2_push(t, q[u].x, i0); top2_push(t, q[u].y, i0 + 1); top2_push(t, q[u].z, i0 + 2); top2_push(t, q[u].w, i0 + 3);
+    }
+  }
+  for (int i = head + 4 * nvec + threadIdx.x; i < cols; i += blockDim.x) top2_push(t, r[i], i);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     Top2 u;
@@ -499,9 +532,9 @@ extern "C" int slb_layernorm_fwd(const void* x, const void* w, const void* b, vo
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 4096, "layernorm: bad shape %d x %d", rows, cols);
   const int grid = ceil_div(rows, kWarpsPerBlock);
   if (cols <= 1024)
-    norm_fwd_kernel<4, false><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd);
+    SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<4, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd));
   else
-    norm_fwd_kernel<16, false><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd);
+    SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<16, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd));
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -510,7 +543,7 @@ extern "C" int slb_layernorm_fwd_f32(const float* x, const void* w, const void* 
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "layernorm_f32: bad shape %d x %d", rows, cols);
   SLB_CHECK_ARG(x && w && b && y && (((uintptr_t)x) & 15) == 0, "layernorm_f32: null / unaligned operand");
   const int grid = ceil_div(rows, kWarpsPerBlock);
-  norm_fwd_kernel<4, false, float><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>(x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, nullptr, nullptr);
+  SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<4, false, float>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, nullptr, nullptr));
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -519,7 +552,7 @@ extern "C" int slb_rmsnorm_fwd_f32(const float* x, const void* w, void* y, int r
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm_f32: bad shape %d x %d", rows, cols);
   SLB_CHECK_ARG(x && w && y && (((uintptr_t)x) & 15) == 0, "rmsnorm_f32: null / unaligned operand");
   const int grid = ceil_div(rows, kWarpsPerBlock);
-  norm_fwd_kernel<4, true, float><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>(x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd);
+  SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<4, true, float>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd));
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -527,7 +560,7 @@ extern "C" int slb_rmsnorm_fwd_f32(const float* x, const void* w, void* y, int r
 extern "C" int slb_rmsnorm_fwd(const void* x, const void* w, void* y, int rows, int cols, float eps, float* rstd, void* stream) {
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm: bad shape %d x %d", rows, cols);
   const int grid = ceil_div(rows, kWarpsPerBlock);
-  norm_fwd_kernel<4, true><<<grid, kWarpsPerBlock * 32, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd);
+  SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<4, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd));
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -579,9 +612,10 @@ extern "C" int slb_vit_assemble_f32(const void* patch_out, const void* cls, cons
 extern "C" int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, const int32_t* past_dev, int lmax,
                                  int hq, int hkv, float theta, void* stream) {
   SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax, "rope: batch=%d lq=%d past=%d lmax=%d", batch, lq, past, lmax);
-  const size_t total = (size_t)batch * lq * 4;
-  rope_kv_write_kernel<<<grid_for(total, 128), 128, 0, ST(stream)>>>((bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq, past, lmax, hq, hkv, log2f(theta), past_dev);
-  SLB_LAUNCH_CHECK();
+  const int per_head = (size_t)batch * lq * 4 < 4096 ? 1 : 0;
+  const size_t total = (size_t)batch * lq * 4 * (per_head ? hq + 2 * hkv : 1);
+  SLB_CUDA(slb_launch_pdl(rope_kv_write_kernel, dim3(grid_for(total, 128)), dim3(128), 0, ST(stream), (bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq,
+                          past, lmax, hq, hkv, log2f(theta), (const int*)past_dev, per_head));
   return SLB_OK;
 }
 
@@ -634,8 +668,7 @@ extern "C" int slb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* st
 
 extern "C" int slb_argmax_f32(const float* logits, int64_t ld, int rows, int cols, int64_t* out_idx, float* out_margin, void* stream) {
   SLB_CHECK_ARG(rows > 0 && cols > 0, "argmax: rows=%d cols=%d", rows, cols);
-  argmax_kernel<<<rows, 1024, 0, ST(stream)>>>(logits, ld, cols, (long long*)out_idx, out_margin);
-  SLB_LAUNCH_CHECK();
+  SLB_CUDA(slb_launch_pdl(argmax_kernel, dim3(rows), dim3(1024), 0, ST(stream), logits, (long long)ld, cols, (long long*)out_idx, out_margin));
   return SLB_OK;
 }
 

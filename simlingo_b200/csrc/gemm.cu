@@ -417,6 +417,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_trigger();
+  pdl_wait();   // barriers / TMEM are set up; the operands may come from the previous kernel in the stream
 
   if (warp == 0) {
     // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
@@ -557,8 +559,7 @@ int launch_gemm(const slb_gemm_args* a, cudaStream_t stream) {
   int grid = p.num_m * p.num_n;
   int sms = slb_num_sms();
   if (grid > sms) grid = sms;
-  kern<<<grid, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, ta2, p);
-  SLB_LAUNCH_CHECK();
+  SLB_CUDA(slb_launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)L::kTotal, stream, ta, tb, ta2, p));
   return SLB_OK;
 }
 
@@ -624,6 +625,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_trigger();
+  pdl_wait();   // barriers / TMEM are set up; the operands may come from the previous kernel in the stream
 
   if (warp == 0) {
     {
@@ -757,8 +760,7 @@ int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
   int clusters = p.num_m * p.num_n;
   const int max_clusters = slb_num_sms() / 2;
   if (clusters > max_clusters) clusters = max_clusters;
-  kern<<<clusters * 2, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, ta2, p);
-  SLB_LAUNCH_CHECK();
+  SLB_CUDA(slb_launch_pdl(kern, dim3(clusters * 2), dim3(GEMM_THREADS), (size_t)L::kTotal, stream, ta, tb, ta2, p));
   return SLB_OK;
 }
 

@@ -68,6 +68,7 @@ gemv_bf16_kernel(GemvParams p) {
     }
   };
 
+  pdl_trigger();   // the next kernel of the decode chain may become resident (it prefetches its own weights, then waits for us)
   int g = blockIdx.x * kGemvWarps + warp;
   int rows[kRows];
   uint4 wv[4][kRows];
@@ -75,6 +76,7 @@ gemv_bf16_kernel(GemvParams p) {
     group_rows(g, rows);
     load_w(rows, 0, wv);
   }
+  pdl_wait();      // the activations (and the residual read by the epilogue) come from the previous kernel
   if (p.a_fp32) {
     // fp32 activation rows (residual stream): RMSNorm in fp32 straight from global memory (M * K * 4 bytes, L2-resident), one
     // rounding to bf16 when the normalised row is staged
@@ -211,8 +213,7 @@ int launch_gemv(const GemvParams& p, cudaStream_t stream) {
   int grid = ceil_div(n_groups, kGemvWarps);
   const int cap = slb_num_sms() * 8;
   if (grid > cap) grid = cap;
-  kern<<<grid, kGemvWarps * 32, smem, stream>>>(p);
-  SLB_LAUNCH_CHECK();
+  SLB_CUDA(slb_launch_pdl(kern, dim3(grid), dim3(kGemvWarps * 32), smem, stream, p));
   return SLB_OK;
 }
 
@@ -302,6 +303,24 @@ skinny_gemm_kernel(GemvParams p, int M) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
   const int nchunks1 = p.K >> 5, nchunks = (p.K + p.K2) >> 5;
+  // programmatic dependent launch: pull this CTA's weight rows towards L2 while the producer of the activations is still running
+  pdl_trigger();
+  {
+    const int lines = ((p.K + p.K2) * 2 + 127) >> 7;   // 128-byte lines per weight row
+    for (int i = threadIdx.x; i < NT * 8 * lines; i += blockDim.x) {
+      const int rr = i / lines, ln = i % lines;
+      int row;
+      if (!p.swiglu) {
+        row = min(tile * (8 * NT) + rr, p.N - 1);
+      } else {
+        const int nt = rr >> 3, gg = rr & 7;
+        const int j = tile * (4 * NT) + (nt % (NT / 2)) * 8 + gg, t = j >> 7, w = j & 127;
+        row = 256 * t + (nt >= NT / 2 ? 128 : 0) + w;
+      }
+      prefetch_l2(reinterpret_cast<const uint8_t*>(p.W + (size_t)row * p.ldw) + (size_t)ln * 128);
+    }
+  }
+  pdl_wait();
 #pragma unroll(NT <= 2 ? 4 : 2)
   for (int c = warp; c < nchunks; c += 8) {
     uint4 bw[NT];
@@ -387,11 +406,11 @@ int slb_skinny_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
   const int rows_per_cta = wide ? 32 : 16;
   const int grid = a->swiglu ? a->N / rows_per_cta : ceil_div(a->N, rows_per_cta);
   if (a->M <= 16) {
-    if (wide) skinny_gemm_kernel<1, 4><<<grid, 256, 0, stream>>>(p, a->M);
-    else skinny_gemm_kernel<1, 2><<<grid, 256, 0, stream>>>(p, a->M);
+    if (wide) slb_launch_pdl(skinny_gemm_kernel<1, 4>, dim3(grid), dim3(256), 0, stream, p, a->M);
+    else slb_launch_pdl(skinny_gemm_kernel<1, 2>, dim3(grid), dim3(256), 0, stream, p, a->M);
   } else {
-    if (wide) skinny_gemm_kernel<2, 4><<<grid, 256, 0, stream>>>(p, a->M);
-    else skinny_gemm_kernel<2, 2><<<grid, 256, 0, stream>>>(p, a->M);
+    if (wide) slb_launch_pdl(skinny_gemm_kernel<2, 4>, dim3(grid), dim3(256), 0, stream, p, a->M);
+    else slb_launch_pdl(skinny_gemm_kernel<2, 2>, dim3(grid), dim3(256), 0, stream, p, a->M);
   }
   cudaError_t e = cudaGetLastError();
   *rc_out = (e == cudaSuccess) ? SLB_OK : slb_fail(SLB_ECUDA, "skinny gemm launch: %s", cudaGetErrorString(e));

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(DX_THREADS)
 lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
   __shared__ __align__(16) bf16 sA[DX_RMAX * DX_LDA];            // [r][128 + 8]
   __shared__ __align__(16) bf16 sD[DX_ROWS * (DX_RMAX + 8)];     // [64][r + 8]
+  __shared__ __align__(16) bf16 sT[DX_ROWS * DX_LDA];            // base dgrad tile in, result tile out
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int col_tile = blockIdx.x * DX_COLS, row_tile = blockIdx.y * DX_ROWS;
@@ -111,17 +112,20 @@ lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
   const int r = a.r, r8 = r >> 3, ldd = r + 8;
   const uint64_t add = seed_dev ? (*seed_dev << 16) : 0;
   const int row0 = row_tile + wr + g, row1 = row0 + 8;
+  // base dgrad tile -> shared memory with coalesced 16-byte loads (per-fragment 4-byte global accesses touch 8 rows per
+  // instruction: 8 L1 wavefronts each, which made the first mma.sync version as slow as the CUDA-core one)
+  for (int q = tid; q < DX_ROWS * (DX_COLS / 8); q += DX_THREADS) {
+    const int rw = q >> 4, cc = q & 15;
+    const int row = row_tile + rw, c = col_tile + cc * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < a.M && c < a.K) v = *reinterpret_cast<const uint4*>(a.in + (long long)row * a.ld_in + c);
+    *reinterpret_cast<uint4*>(sT + rw * DX_LDA + cc * 8) = v;
+  }
   float tot[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int c = col_tile + wc + nt * 8 + 2 * t;
-    float2 v0 = make_float2(0.f, 0.f), v1 = v0;
-    if (c < a.K) {
-      if (row0 < a.M) v0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.in + (long long)row0 * a.ld_in + c));
-      if (row1 < a.M) v1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.in + (long long)row1 * a.ld_in + c));
-    }
-    tot[nt][0] = v0.x; tot[nt][1] = v0.y; tot[nt][2] = v1.x; tot[nt][3] = v1.y;
-  }
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tot[nt][e] = 0.f;
   for (int j = 0; j < a.n; ++j) {
     __syncthreads();
     for (int q = tid; q < r * (DX_COLS / 8); q += DX_THREADS) {
@@ -178,13 +182,21 @@ lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
         for (int e = 0; e < 4; ++e) tot[nt][e] += acc[nt][e];
     }
   }
+  // result = base + sum over adapters (fp32), rounded once, back into the tile (each thread owns its fragment words), then
+  // coalesced 16-byte stores
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    const int c = col_tile + wc + nt * 8 + 2 * t;
-    if (c < a.K) {
-      if (row0 < a.M) *reinterpret_cast<uint32_t*>(a.out + (long long)row0 * a.ld_out + c) = pack_bf16(tot[nt][0], tot[nt][1]);
-      if (row1 < a.M) *reinterpret_cast<uint32_t*>(a.out + (long long)row1 * a.ld_out + c) = pack_bf16(tot[nt][2], tot[nt][3]);
-    }
+    uint32_t* w0 = reinterpret_cast<uint32_t*>(sT + (wr + g) * DX_LDA + wc + nt * 8 + 2 * t);
+    uint32_t* w1 = reinterpret_cast<uint32_t*>(sT + (wr + g + 8) * DX_LDA + wc + nt * 8 + 2 * t);
+    const float2 b0 = unpack_bf16(*w0), b1 = unpack_bf16(*w1);
+    *w0 = pack_bf16(b0.x + tot[nt][0], b0.y + tot[nt][1]);
+    *w1 = pack_bf16(b1.x + tot[nt][2], b1.y + tot[nt][3]);
+  }
+  __syncthreads();
+  for (int q = tid; q < DX_ROWS * (DX_COLS / 8); q += DX_THREADS) {
+    const int rw = q >> 4, cc = q & 15;
+    const int row = row_tile + rw, c = col_tile + cc * 8;
+    if (row < a.M && c < a.K) *reinterpret_cast<uint4*>(a.out + (long long)row * a.ld_out + c) = *reinterpret_cast<const uint4*>(sT + rw * DX_LDA + cc * 8);
   }
 }
 
