@@ -191,7 +191,7 @@ int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, c
  * slb_lora_pack: table_dev = int64 [n_entries][4] on the device {src bf16 [rows, rank] contiguous, dst bf16, rows, dst row
  *   stride in elements}; dst[row, 0:rank] = scale * src[row, :] for every entry, one launch.
  * slb_lora_dx: out[M, K] = in[:, 0:K] + sum_j mask_j o (in[:, K + rank*j : K + rank*(j+1)] @ A[j]) / (1 - p), A[j] bf16 [rank, K]
- *   contiguous; mask_j = the keep mask of slb_dropout(seed = seeds[j]) over the contiguous [M, K] index space (seeds == NULL or
+ *   contiguous, rank a multiple of 16 and <= 32; mask_j = the keep mask of slb_dropout(seed = seeds[j]) over the contiguous [M, K] index space (seeds == NULL or
  *   p == 0: no mask); fp32 accumulation, one rounding.  A / seeds are HOST arrays of n_adapters (<= 4) entries.
  * slb_silu_mul_cat(_bwd): SwiGLU on gate_up bf16 [rows, 2*inter] = [gate | up]: out = silu(gate) * up; dgate_up = [dgate | dup]. */
 int slb_dropout_multi(const void* x, void* const* ys, const uint64_t* seeds, int n_out, int64_t n, float p,

@@ -68,6 +68,22 @@ int slb_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return SLB_OK;
 }
 
+// fp32 2-D map (inner box = 32 elements = 128 bytes, 128B swizzle): the residual-stream tiles the GEMM epilogue moves with TMA
+int slb_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                         uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return slb_fail(SLB_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {outer_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return slb_fail(SLB_ECUDA, "cuTensorMapEncodeTiled(2d f32) failed: %d", (int)r);
+  return SLB_OK;
+}
+
 int slb_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                      uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
   EncodeTiledFn enc = get_encode();

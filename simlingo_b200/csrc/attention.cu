@@ -565,7 +565,7 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
       SLB_CUDA(cudaFuncSetAttribute(attn_decode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set = smem;
     }
-    SLB_CUDA(slb_launch_pdl(attn_decode_group_kernel, dim3(lq, hkv, batch), dim3(kGrpThreads), smem, (cudaStream_t)stream, (const bf16*)q,
+    SLB_CUDA(slb_launch_pdl(true, attn_decode_group_kernel, dim3(lq, hkv, batch), dim3(kGrpThreads), smem, (cudaStream_t)stream, (const bf16*)q,
                             (long long)ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq,
                             past, lmax, hq, hkv, scale, (const int*)past_dev));
     return SLB_OK;
@@ -574,7 +574,7 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
     dim3 grid(lq, hq, batch);
     const size_t smem = (64 + 2 * kSmallWarps + kSmallWarps * 64 + (size_t)lmax) * sizeof(float);
     SLB_CHECK_ARG(smem <= 48 * 1024, "attn_gqa: lmax=%d too long for the small-Lq kernel", lmax);
-    SLB_CUDA(slb_launch_pdl(attn_small_kernel, grid, dim3(kSmallThreads), smem, (cudaStream_t)stream, (const bf16*)q, (long long)ldq,
+    SLB_CUDA(slb_launch_pdl(true, attn_small_kernel, grid, dim3(kSmallThreads), smem, (cudaStream_t)stream, (const bf16*)q, (long long)ldq,
                             (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq,
                             hkv, scale, (const int*)past_dev));
     return SLB_OK;

@@ -408,7 +408,7 @@ int slb_attn_gqa2_try(const void* q, int64_t ldq, const void* kcache, const void
     if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_gqa2 attribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
-  cudaError_t e = slb_launch_pdl(attn_gqa2_kernel, dim3(grid), dim3(G2_THREADS), (size_t)kSmTotal, stream, tq, tk, tv, p);
+  cudaError_t e = slb_launch_pdl((long long)batch * lq <= 4096, attn_gqa2_kernel, dim3(grid), dim3(G2_THREADS), (size_t)kSmTotal, stream, tq, tk, tv, p);
   if (e != cudaSuccess) *rc_out = slb_fail(SLB_ECUDA, "attn_gqa2 launch: %s", cudaGetErrorString(e));
   return 1;
 }

@@ -570,7 +570,7 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal);
     if (e != cudaSuccess) return e;
-    return slb_launch_pdl(kern, dim3(grid), dim3(V2_THREADS), (size_t)kSmTotal, stream, tm, p);
+    return slb_launch_pdl(tiles <= 8, kern, dim3(grid), dim3(V2_THREADS), (size_t)kSmTotal, stream, tm, p);
   };
   cudaError_t e;
   // software-exp2 share (pairs out of 16 per 32-score chunk): SLB_VIT2_EMU selects 0 / 4 / 5 / 6 / 8 for tuning runs; valid
@@ -611,7 +611,7 @@ int slb_attn_vit2_try(const void* qkv, void* out, float* lse, int tiles, int n_t
 #endif
   if (e != cudaSuccess) { *rc_out = slb_fail(SLB_ECUDA, "attn_vit2 launch: %s", cudaGetErrorString(e)); return 1; }
   const size_t smem = ((size_t)kClsHeads * 64 + 2 * kClsWarps * kClsHeads + kClsWarps * 256 + (size_t)kClsHeads * n_tokens) * sizeof(float);
-  e = slb_launch_pdl(attn_vit_cls_kernel, dim3(heads / kClsHeads, tiles), dim3(kClsThreads), smem, stream, (const bf16*)qkv, (bf16*)out, lse, n_tokens, heads, 0.125f);
+  e = slb_launch_pdl(tiles <= 8, attn_vit_cls_kernel, dim3(heads / kClsHeads, tiles), dim3(kClsThreads), smem, stream, (const bf16*)qkv, (bf16*)out, lse, n_tokens, heads, 0.125f);
   if (e != cudaSuccess) *rc_out = slb_fail(SLB_ECUDA, "attn_vit_cls launch: %s", cudaGetErrorString(e));
   return 1;
 }

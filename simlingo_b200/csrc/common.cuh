@@ -401,15 +401,18 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 int slb_pdl_enabled();   // api.cu: 1 unless SLB_NO_PDL=1 (A/B timing)
+// `small`: only launch-bound problems ask for the overlap (decode steps, the batch-1 agent chain).  For kernels that run for hundreds
+// of microseconds it was measured neutral to slightly negative (training step 76.0 -> 76.9 ms, offline step 145.3 -> 146.4 ms):
+// early-resident successor CTAs take warp slots and registers from the running kernel.
 template <typename... KArgs, typename... Args>
-static inline cudaError_t slb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+static inline cudaError_t slb_launch_pdl(bool small, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = slb_pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (small && slb_pdl_enabled()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -431,6 +434,8 @@ __device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.0f
 // host: build a 2-D (or 3-D) bf16 TMA descriptor with 128B swizzle (inner box = 64 elements = 128 bytes)
 int slb_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
                      uint32_t box_inner, uint32_t box_outer);
+int slb_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                         uint32_t box_inner, uint32_t box_outer);
 int slb_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                      uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
 // fp32 variant (inner box = 32 elements = 128 bytes, 128B swizzle) for TMA reduce-add targets

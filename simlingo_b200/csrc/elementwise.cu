@@ -532,9 +532,9 @@ extern "C" int slb_layernorm_fwd(const void* x, const void* w, const void* b, vo
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 4096, "layernorm: bad shape %d x %d", rows, cols);
   const int grid = ceil_div(rows, kWarpsPerBlock);
   if (cols <= 1024)
-    SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<4, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd));
+    SLB_CUDA(slb_launch_pdl(rows <= 4096, norm_fwd_kernel<4, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd));
   else
-    SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<16, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd));
+    SLB_CUDA(slb_launch_pdl(rows <= 4096, norm_fwd_kernel<16, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, mean, rstd));
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -543,7 +543,7 @@ extern "C" int slb_layernorm_fwd_f32(const float* x, const void* w, const void* 
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "layernorm_f32: bad shape %d x %d", rows, cols);
   SLB_CHECK_ARG(x && w && b && y && (((uintptr_t)x) & 15) == 0, "layernorm_f32: null / unaligned operand");
   const int grid = ceil_div(rows, kWarpsPerBlock);
-  SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<4, false, float>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, nullptr, nullptr));
+  SLB_CUDA(slb_launch_pdl(rows <= 4096, norm_fwd_kernel<4, false, float>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, nullptr, nullptr));
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -552,7 +552,7 @@ extern "C" int slb_rmsnorm_fwd_f32(const float* x, const void* w, void* y, int r
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm_f32: bad shape %d x %d", rows, cols);
   SLB_CHECK_ARG(x && w && y && (((uintptr_t)x) & 15) == 0, "rmsnorm_f32: null / unaligned operand");
   const int grid = ceil_div(rows, kWarpsPerBlock);
-  SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<4, true, float>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd));
+  SLB_CUDA(slb_launch_pdl(rows <= 4096, norm_fwd_kernel<4, true, float>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd));
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -560,7 +560,7 @@ extern "C" int slb_rmsnorm_fwd_f32(const float* x, const void* w, void* y, int r
 extern "C" int slb_rmsnorm_fwd(const void* x, const void* w, void* y, int rows, int cols, float eps, float* rstd, void* stream) {
   SLB_CHECK_ARG(rows > 0 && cols > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm: bad shape %d x %d", rows, cols);
   const int grid = ceil_div(rows, kWarpsPerBlock);
-  SLB_CUDA(slb_launch_pdl(norm_fwd_kernel<4, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd));
+  SLB_CUDA(slb_launch_pdl(rows <= 4096, norm_fwd_kernel<4, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, ST(stream), (const bf16*)x, (const bf16*)w, nullptr, (bf16*)y, rows, cols, eps, nullptr, rstd));
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
@@ -614,7 +614,7 @@ extern "C" int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batc
   SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax, "rope: batch=%d lq=%d past=%d lmax=%d", batch, lq, past, lmax);
   const int per_head = (size_t)batch * lq * 4 < 4096 ? 1 : 0;
   const size_t total = (size_t)batch * lq * 4 * (per_head ? hq + 2 * hkv : 1);
-  SLB_CUDA(slb_launch_pdl(rope_kv_write_kernel, dim3(grid_for(total, 128)), dim3(128), 0, ST(stream), (bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq,
+  SLB_CUDA(slb_launch_pdl(per_head != 0 || (size_t)batch * lq <= 4096, rope_kv_write_kernel, dim3(grid_for(total, 128)), dim3(128), 0, ST(stream), (bf16*)qkv, (bf16*)kcache, (bf16*)vcache, batch, lq,
                           past, lmax, hq, hkv, log2f(theta), (const int*)past_dev, per_head));
   return SLB_OK;
 }
@@ -668,7 +668,7 @@ extern "C" int slb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* st
 
 extern "C" int slb_argmax_f32(const float* logits, int64_t ld, int rows, int cols, int64_t* out_idx, float* out_margin, void* stream) {
   SLB_CHECK_ARG(rows > 0 && cols > 0, "argmax: rows=%d cols=%d", rows, cols);
-  SLB_CUDA(slb_launch_pdl(argmax_kernel, dim3(rows), dim3(1024), 0, ST(stream), logits, (long long)ld, cols, (long long*)out_idx, out_margin));
+  SLB_CUDA(slb_launch_pdl(true, argmax_kernel, dim3(rows), dim3(1024), 0, ST(stream), logits, (long long)ld, cols, (long long*)out_idx, out_margin));
   return SLB_OK;
 }
 

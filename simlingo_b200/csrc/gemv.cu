@@ -213,7 +213,7 @@ int launch_gemv(const GemvParams& p, cudaStream_t stream) {
   int grid = ceil_div(n_groups, kGemvWarps);
   const int cap = slb_num_sms() * 8;
   if (grid > cap) grid = cap;
-  SLB_CUDA(slb_launch_pdl(kern, dim3(grid), dim3(kGemvWarps * 32), smem, stream, p));
+  SLB_CUDA(slb_launch_pdl(true, kern, dim3(grid), dim3(kGemvWarps * 32), smem, stream, p));
   return SLB_OK;
 }
 
@@ -406,11 +406,11 @@ int slb_skinny_try(const slb_gemm_args* a, cudaStream_t stream, int* rc_out) {
   const int rows_per_cta = wide ? 32 : 16;
   const int grid = a->swiglu ? a->N / rows_per_cta : ceil_div(a->N, rows_per_cta);
   if (a->M <= 16) {
-    if (wide) slb_launch_pdl(skinny_gemm_kernel<1, 4>, dim3(grid), dim3(256), 0, stream, p, a->M);
-    else slb_launch_pdl(skinny_gemm_kernel<1, 2>, dim3(grid), dim3(256), 0, stream, p, a->M);
+    if (wide) slb_launch_pdl(true, skinny_gemm_kernel<1, 4>, dim3(grid), dim3(256), 0, stream, p, a->M);
+    else slb_launch_pdl(true, skinny_gemm_kernel<1, 2>, dim3(grid), dim3(256), 0, stream, p, a->M);
   } else {
-    if (wide) slb_launch_pdl(skinny_gemm_kernel<2, 4>, dim3(grid), dim3(256), 0, stream, p, a->M);
-    else slb_launch_pdl(skinny_gemm_kernel<2, 2>, dim3(grid), dim3(256), 0, stream, p, a->M);
+    if (wide) slb_launch_pdl(true, skinny_gemm_kernel<2, 4>, dim3(grid), dim3(256), 0, stream, p, a->M);
+    else slb_launch_pdl(true, skinny_gemm_kernel<2, 2>, dim3(grid), dim3(256), 0, stream, p, a->M);
   }
   cudaError_t e = cudaGetLastError();
   *rc_out = (e == cudaSuccess) ? SLB_OK : slb_fail(SLB_ECUDA, "skinny gemm launch: %s", cudaGetErrorString(e));

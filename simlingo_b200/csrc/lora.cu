@@ -81,7 +81,7 @@ __global__ void lora_pack_kernel(const PackEntry* __restrict__ tab, int r8, floa
 // mma.sync.m16n8k16 (bf16, fp32 accumulators): dt tile [64, r] and A_j tile [r, 128] staged in padded shared memory (conflict-free
 // 32-bit A-fragment loads / ldmatrix.trans B fragments), one pass per adapter, mask applied on the accumulator fragment, fp32 sum
 // over the adapters on top of the base dgrad, one rounding.  (A first CUDA-core version was LSU / FMA bound at 51 us per call.)
-constexpr int DX_ROWS = 64, DX_COLS = 128, DX_THREADS = 256, DX_RMAX = 64;
+constexpr int DX_ROWS = 64, DX_COLS = 128, DX_THREADS = 256, DX_RMAX = 64;   // the kernel takes rank <= DX_RMAX / 2 (double-buffered operands)
 constexpr int DX_LDA = DX_COLS + 8;   // bf16 elements per sA row (272 B: 8 consecutive rows hit 32 distinct banks)
 struct LoraDxArgs {
   const bf16* in; long long ld_in;   // [M, >= K + r*n]: base dgrad in columns [0, K), dt_j in columns [K + r*j, K + r*(j+1))
@@ -100,10 +100,19 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {   // 16-byte async copy, zero-fill when !pred
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(pred ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// All global reads are asynchronous copies: the base tile and adapter 0's operands leave together, adapter j + 1 is in flight while
+// adapter j is multiplied (double-buffered sA / sD) - the block's dependent global round trips drop from n + 2 to 2 (the kernel is
+// latency-bound: 2 blocks per SM, a few microseconds of work each).
 __global__ void __launch_bounds__(DX_THREADS)
 lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
-  __shared__ __align__(16) bf16 sA[DX_RMAX * DX_LDA];            // [r][128 + 8]
-  __shared__ __align__(16) bf16 sD[DX_ROWS * (DX_RMAX + 8)];     // [64][r + 8]
+  __shared__ __align__(16) bf16 sA[2][DX_RMAX / 2 * DX_LDA];      // [r][128 + 8], r <= 32, double-buffered over the adapters
+  __shared__ __align__(16) bf16 sD[2][DX_ROWS * (DX_RMAX / 2 + 8)];  // [64][r + 8]
   __shared__ __align__(16) bf16 sT[DX_ROWS * DX_LDA];            // base dgrad tile in, result tile out
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -112,48 +121,52 @@ lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
   const int r = a.r, r8 = r >> 3, ldd = r + 8;
   const uint64_t add = seed_dev ? (*seed_dev << 16) : 0;
   const int row0 = row_tile + wr + g, row1 = row0 + 8;
-  // base dgrad tile -> shared memory with coalesced 16-byte loads (per-fragment 4-byte global accesses touch 8 rows per
-  // instruction: 8 L1 wavefronts each, which made the first mma.sync version as slow as the CUDA-core one)
+  auto stage = [&](int j, int buf) {
+    for (int q = tid; q < r * (DX_COLS / 8); q += DX_THREADS) {
+      const int k = q >> 4, cc = q & 15;
+      const int c = col_tile + cc * 8;
+      const bool ok = c < a.K;
+      cp_async16(sA[buf] + k * DX_LDA + cc * 8, a.A[j] + (ok ? (long long)k * a.K + c : 0), ok);
+    }
+    for (int q = tid; q < DX_ROWS * r8; q += DX_THREADS) {
+      const int rw = q / r8, cc = q % r8;
+      const int row = row_tile + rw;
+      const bool ok = row < a.M;
+      cp_async16(sD[buf] + rw * ldd + cc * 8, a.in + (ok ? (long long)row * a.ld_in + a.K + j * r + cc * 8 : 0), ok);
+    }
+  };
   for (int q = tid; q < DX_ROWS * (DX_COLS / 8); q += DX_THREADS) {
     const int rw = q >> 4, cc = q & 15;
     const int row = row_tile + rw, c = col_tile + cc * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < a.M && c < a.K) v = *reinterpret_cast<const uint4*>(a.in + (long long)row * a.ld_in + c);
-    *reinterpret_cast<uint4*>(sT + rw * DX_LDA + cc * 8) = v;
+    const bool ok = row < a.M && c < a.K;
+    cp_async16(sT + rw * DX_LDA + cc * 8, a.in + (ok ? (long long)row * a.ld_in + c : 0), ok);
   }
+  stage(0, 0);
+  cp_async_commit();
   float tot[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) tot[nt][e] = 0.f;
   for (int j = 0; j < a.n; ++j) {
+    const int buf = j & 1;
+    if (j + 1 < a.n) stage(j + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait_1();     // everything but the group just committed has landed: the base tile and adapter j
     __syncthreads();
-    for (int q = tid; q < r * (DX_COLS / 8); q += DX_THREADS) {
-      const int k = q >> 4, cc = q & 15;
-      const int c = col_tile + cc * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (c < a.K) v = *reinterpret_cast<const uint4*>(a.A[j] + (long long)k * a.K + c);
-      *reinterpret_cast<uint4*>(sA + k * DX_LDA + cc * 8) = v;
-    }
-    for (int q = tid; q < DX_ROWS * r8; q += DX_THREADS) {
-      const int rw = q / r8, cc = q % r8;
-      const int row = row_tile + rw;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (row < a.M) v = *reinterpret_cast<const uint4*>(a.in + (long long)row * a.ld_in + a.K + j * r + cc * 8);
-      *reinterpret_cast<uint4*>(sD + rw * ldd + cc * 8) = v;
-    }
-    __syncthreads();
+    const bf16* sa = sA[buf];
+    const bf16* sd = sD[buf];
     float acc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
     for (int k0 = 0; k0 < r; k0 += 16) {
-      const bf16* d0 = sD + (wr + g) * ldd + k0 + 2 * t;
+      const bf16* d0 = sd + (wr + g) * ldd + k0 + 2 * t;
       const uint32_t a0 = *reinterpret_cast<const uint32_t*>(d0), a1 = *reinterpret_cast<const uint32_t*>(d0 + 8 * ldd);
       const uint32_t a2 = *reinterpret_cast<const uint32_t*>(d0 + 8), a3 = *reinterpret_cast<const uint32_t*>(d0 + 8 * ldd + 8);
       // ldmatrix.x4.trans: lanes 0-7 address rows k0..k0+7 of n-tile nt, 8-15 rows k0+8.., 16-23 / 24-31 the same for n-tile nt + 1
-      const uint32_t base = smem_u32(sA + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * DX_LDA + wc + (lane >> 4) * 8);
+      const uint32_t base = smem_u32(sa + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * DX_LDA + wc + (lane >> 4) * 8);
 #pragma unroll
       for (int nt = 0; nt < 8; nt += 2) {
         uint32_t b0, b1, b2, b3;
@@ -181,6 +194,7 @@ lora_dx_kernel(LoraDxArgs a, const uint64_t* __restrict__ seed_dev) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) tot[nt][e] += acc[nt][e];
     }
+    __syncthreads();       // buffer `buf` is refilled by the stage issued at the top of iteration j + 1
   }
   // result = base + sum over adapters (fp32), rounded once, back into the tile (each thread owns its fragment words), then
   // coalesced 16-byte stores
@@ -266,8 +280,8 @@ extern "C" int slb_lora_pack(const int64_t* table_dev, int n_entries, int rank, 
 extern "C" int slb_lora_dx(const void* in, int64_t ld_in, void* out, int64_t ld_out, const void* const* A, const uint64_t* seeds,
                            int n_adapters, int M, int K, int rank, float p, const uint64_t* seed_dev, void* stream) {
   SLB_CHECK_ARG(in && out && A && n_adapters >= 1 && n_adapters <= kMaxAdapters, "lora_dx: n_adapters=%d (1..%d)", n_adapters, kMaxAdapters);
-  SLB_CHECK_ARG(M > 0 && K > 0 && (K % 8) == 0 && rank > 0 && (rank % 16) == 0 && rank <= DX_RMAX, "lora_dx: M=%d K=%d rank=%d (multiple of 16, <= %d)", M,
-                K, rank, DX_RMAX);
+  SLB_CHECK_ARG(M > 0 && K > 0 && (K % 8) == 0 && rank > 0 && (rank % 16) == 0 && rank <= DX_RMAX / 2, "lora_dx: M=%d K=%d rank=%d (multiple of 16, <= %d)", M,
+                K, rank, DX_RMAX / 2);
   SLB_CHECK_ARG((ld_in % 8) == 0 && (ld_out % 8) == 0 && ld_in >= K + (int64_t)rank * n_adapters && ld_out >= K &&
                 ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "lora_dx: strides / alignment (ld_in=%lld ld_out=%lld)",
                 (long long)ld_in, (long long)ld_out);

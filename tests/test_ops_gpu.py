@@ -137,6 +137,25 @@ def test_gemm_second_a_source(lib, M, N, K, K2, kw):
     assert relerr(got, ref) < (1e-2 if kw.get("swiglu") else 5e-3)
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(4200, 1024, 1024, 0), (8200, 896, 4864, 0), (4100, 1024, 512, 2192), (4097, 256, 128, 0)])
+def test_gemm_tma_residual_stream_epilogue(lib, M, N, K, bn):
+    """2-CTA kernel, fp32 residual stream moved by TMA (32 x 32 boxes per epilogue warp): bias * layer-scale + residual in place,
+    out-of-place, alpha, ragged last row tile (rows beyond M are zero-filled on load and clipped on store)"""
+    a, b = rnd(M, K, seed=1, scale=0.5), rnd(N, K, seed=2, scale=0.05)
+    bias, ls = rnd(N, seed=3), rnd(N, seed=4, scale=0.2)
+    acc = a.float() @ b.float().t()
+    x = torch.randn(M + 3, N, device="cuda")           # guard rows behind the tensor must stay untouched
+    guard = x[M:].clone()
+    ref = x[:M] + ls.float() * (acc + bias.float())
+    lib.gemm(a, b, out=x[:M], bias=bias, scale_n=ls, residual=x[:M], out_fp32=True, block_n=bn)
+    assert relerr(x[:M], ref) < 2e-3 and torch.equal(x[M:], guard)
+    res = torch.randn(M, N, device="cuda")
+    out = lib.gemm(a, b, residual=res, out_fp32=True, alpha=0.5, block_n=bn)
+    assert relerr(out, res + 0.5 * acc) < 2e-3
+    out = lib.gemm(a, b, bias=bias, residual=res, out_fp32=True, block_n=bn)
+    assert relerr(out, res + acc + bias.float()) < 2e-3
+
+
 def test_gemm_strided_views(lib):
     """A as a column slice of a wider buffer (q part of the fused qkv), out as a slice."""
     M, K, N = 545, 896, 896

@@ -114,3 +114,30 @@ if not ONLY or "llm" in ONLY:
     row("llm.gate|up SwiGLU K=896+64", timeit(lambda: lib.gemm(h, wg, a2=t, swiglu=True)), 2.0 * M * 9728 * 960)
     wd, t = bf(896, 4896), bf(M, 32)
     row("llm.down K=4864+32 fp32 stream", timeit(lambda: lib.gemm(act, wd, a2=t, out=x32, residual=x32, out_fp32=True)), 2.0 * M * 896 * 4896)
+
+if "lora" in ONLY:
+    # training-path LoRA side kernels at the B=8 training shapes (M = 8 * 591)
+    M, r = 4728, 32
+    sd = torch.zeros(1, device=dev, dtype=torch.int64)
+    for name, K, n in (("qkv", 896, 3), ("o", 896, 1), ("gate|up", 896, 2), ("down", 4864, 1)):
+        cat = bf(M, K + r * n)
+        A = [bf(r, K) for _ in range(n)]
+        seeds = list(range(100, 100 + n))
+        out = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+        us = timeit(lambda: lib.lora_dx(cat, K, A, p=0.1, seeds=seeds, seed_dev=sd, out=out))
+        row(f"lora_dx {name} K={K} n={n} (masked)", us, note=f"{(cat.numel() + out.numel()) * 2 / us / 1e3:.0f} GB/s")
+        us = timeit(lambda: lib.lora_dx(cat, K, A, out=out))
+        row(f"lora_dx {name} K={K} n={n} (no mask)", us)
+    x = bf(M, 896)
+    row("dropout_multi x3 [4728, 896]", timeit(lambda: lib.dropout_multi(x, 0.1, [1, 2, 3], seed_dev=sd)))
+    dy, t = bf(M, 896), bf(M, 32)
+    g = torch.zeros(896, 32, device=dev, dtype=torch.bfloat16)
+    row("LoRA dB wgrad [896 x 32] K=4728", timeit(lambda: lib.gemm(dy, t, out=g, a_t=True, b_t=True)))
+    g2 = torch.zeros(32, 896, device=dev, dtype=torch.bfloat16)
+    row("LoRA dA wgrad [32 x 896] K=4728", timeit(lambda: lib.gemm(t, dy, out=g2, a_t=True, b_t=True)))
+    wx = bf(896, 4864 + 32)
+    dx = bf(M, 896)
+    row("llm down dgrad [4728 x 4896] K=896 (b_t)", timeit(lambda: lib.gemm(dx, wx, b_t=True)), 2.0 * M * 4896 * 896)
+    wgu = bf(9728, 896 + 64)
+    dgu = bf(M, 9728)
+    row("llm gate|up dgrad [4728 x 960] K=9728 (b_t)", timeit(lambda: lib.gemm(dgu, wgu, b_t=True)), 2.0 * M * 960 * 9728)

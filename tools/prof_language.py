@@ -10,7 +10,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 spec = S.INTERNVL2_1B
 dev = torch.device("cuda", 0)
-model = Bn.build_planted_model(spec, dev)
+model = Bn.build_model(spec, dev)
 eng = model._engine()
 hb = Bn.host_agent_batch(spec, B, 500, None)
 ids, fr, vd = hb["ids"].to(dev), hb["frames"].to(dev), hb["valid"].to(dev)
