@@ -44,7 +44,7 @@ from simlingo_b200 import spec as S  # noqa: E402
 
 FRAMES_PER_GPU = 64
 # (0.275+0.760 + 0.540+0.230 + 0.279+1.030 + 1.640+0.258) GB / 4 launches, measured once with `ncu --set full` (profiles/)
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 1.253e9
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 1.526e9   # profiles/r02_ncu_gemm2_offline64_summary.txt (ncu --set full, fp32 residual streams)
 PROMPT_LEN = 545
 
 
@@ -301,8 +301,9 @@ def gemm_roofline(peaks, step_fn, traffic=None):
     return {"bound": "tensor", "kernel": dom + " (tcgen05, TMA-fed, TMEM accumulators)", "achieved": round(ach, 1), "peak": peaks["tflops"],
             "unit": "TFLOP/s", "frac": round(ach / peaks["tflops"], 4), "traffic": traffic,
             "traffic_note": None if traffic is None else
-            "dram read+write bytes per launch, mean over the 4 GEMMs of one InternViT layer at M=131200 (qkv, proj, fc1, fc2) from "
-            "profiles/r01_ncu_gemm2_offline64_summary.txt (ncu --set full); algorithmic bytes of the same 4 launches: 1.216e9",
+            "dram read+write bytes per launch, mean over the 4 GEMMs of one InternViT layer at M=131200 (fc2, qkv, proj, fc1) from "
+            "profiles/r02_ncu_gemm2_offline64_summary.txt (ncu --set full); algorithmic bytes of the same 4 launches with the fp32 residual "
+            "stream (proj / fc2 read and write it): 1.479e9 mean",
             "launches_per_step": dn, "gemm_flops_per_step": dflops, "gemm_ms_per_step": round(dsecs * 1e3, 3),
             "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
             "all_gemm_launches": {"launches_per_step": len(rec), "flops_per_step": flops, "ms_per_step": round(secs * 1e3, 3),

@@ -79,6 +79,13 @@ int slb_pixel_shuffle_ln_f32(const float* x, const void* w, const void* b, void*
 /* ---- ViT embeddings (UPSTREAM InternVisionEmbeddings, intern_vit.py:103-115) ---------------------
  * im2col: pixels [T,3,448,448] -> patches [T*1024, kpad] (k = c*196 + py*14 + px, zero padded);
  * assemble: x[t,0] = cls + pos[0]; x[t,1+p] = patch_out[t*1024+p] + pos[1+p] */
+/* Patch embedding as an implicit GEMM (UPSTREAM InternVisionEmbeddings.forward: patch_embedding conv + class token + position
+ * embedding, intern_vit.py:59-64): the A operand is gathered from pixels bf16 [tiles,3,448,448] inside the kernel, weight = conv weight
+ * flattened to [1024, 588] and zero-padded to ldw >= 640 columns; x [tiles*1025, 1024] (fp32 or bf16) receives
+ * conv + bias + pos[1 + p] at row t*1025 + 1 + p and cls + pos[0] at row t*1025.  The explicit pair slb_im2col_patch + slb_gemm_bf16
+ * (+ slb_vit_assemble) remains for the training forward, whose weight gradient needs the patch matrix. */
+int slb_patch_embed(const void* pixels, const void* weight, int64_t ldw, const void* bias, const void* cls, const void* pos, void* x,
+                    int tiles, int out_fp32, void* stream);
 int slb_im2col_patch(const void* pixels, void* patches, int tiles, int kpad, void* stream);
 int slb_vit_assemble(const void* patch_out, const void* cls, const void* pos, void* x, int tiles, void* stream);
 /* ---- projector front: drop CLS + pixel_shuffle(0.5, v2) + LayerNorm(4096) fused

@@ -650,14 +650,13 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& p, const CUte
         v23 = f2mul(v23, alpha2);
       }
       const uint64_t r01 = f2pack(__uint_as_float(rv[k].x), __uint_as_float(rv[k].y)), r23 = f2pack(__uint_as_float(rv[k].z), __uint_as_float(rv[k].w));
-      if (p.scale_n) {
+      if (p.scale_n) {   // multiply, then add (not fused): bit-identical to the direct-store epilogue the small-M shapes take
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(sq);
-        v01 = f2fma(v01, bf2_to_f2(sw[2 * k]), r01);
-        v23 = f2fma(v23, bf2_to_f2(sw[2 * k + 1]), r23);
-      } else {
-        v01 = f2add(v01, r01);
-        v23 = f2add(v23, r23);
+        v01 = f2mul(v01, bf2_to_f2(sw[2 * k]));
+        v23 = f2mul(v23, bf2_to_f2(sw[2 * k + 1]));
       }
+      v01 = f2add(v01, r01);
+      v23 = f2add(v23, r23);
       float a, b, cc, d;
       f2unpack(v01, a, b);
       f2unpack(v23, cc, d);

@@ -212,10 +212,10 @@ class Engine:
         s, w = self.spec, self._w
         T = pixels.shape[0]
         e = VIT_PREFIX + "embeddings."
-        cols = lib.im2col_patch(pixels.contiguous(), PATCH_KPAD)
-        po = lib.gemm(cols, self.patch_w, bias=w(e + "patch_embedding.bias"))
-        x = lib.vit_assemble(po, w(e + "class_embedding"), w(e + "position_embedding"), T, fp32=True)
-        del cols, po
+        # patch embedding as an implicit GEMM: the operand tile is gathered from the pixels inside the kernel, class token and
+        # position embedding are added in the epilogue (one launch instead of im2col + GEMM + assemble, no [T*1024, 640] matrix in HBM)
+        x = lib.patch_embed(pixels.contiguous(), self.patch_w, w(e + "patch_embedding.bias"), w(e + "class_embedding").reshape(-1),
+                            w(e + "position_embedding").reshape(-1, s.vit_hidden))
         N = s.vit_tokens
         h = torch.empty((T * N, s.vit_hidden), device=self.dev, dtype=torch.bfloat16)
         qkv = torch.empty((T * N, 3 * s.vit_hidden), device=self.dev, dtype=torch.bfloat16)
@@ -232,7 +232,7 @@ class Engine:
             lib.gemm(f, w(p + "mlp.fc2.weight"), out=x, bias=w(p + "mlp.fc2.bias"), scale_n=w(p + "ls2"), residual=x, out_fp32=True)
             if collect is not None:
                 collect.append(x.clone())
-        self.launches += 3 + 7 * s.vit_layers
+        self.launches += 1 + 7 * s.vit_layers
         return x
 
     def extract_feature(self, pixels: Tensor) -> Tensor:

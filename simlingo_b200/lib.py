@@ -171,6 +171,18 @@ def im2col_patch(pixels, kpad=640, out=None):
     return out
 
 
+def patch_embed(pixels, weight_padded, bias, cls, pos, fp32=True, out=None):
+    """implicit-GEMM patch embedding: pixels bf16 [T,3,448,448], weight_padded bf16 [1024, >= 640] -> token stream [T*1025, 1024]"""
+    _bf16(pixels, weight_padded, bias, cls, pos)
+    tiles = pixels.shape[0]
+    assert pixels.shape[1:] == (3, 448, 448) and pixels.is_contiguous() and weight_padded.shape[0] == 1024 and weight_padded.stride(1) == 1
+    out = torch.empty((tiles * 1025, 1024), device=pixels.device, dtype=torch.float32 if fp32 else torch.bfloat16) if out is None else out
+    assert out.is_contiguous() and out.dtype == (torch.float32 if fp32 else torch.bfloat16)
+    _check(load().slb_patch_embed(_p(pixels), _p(weight_padded), C.c_int64(weight_padded.stride(0)), _p(bias), _p(cls.contiguous()), _p(pos.contiguous()),
+                                  _p(out), tiles, int(fp32), _stream()), "patch_embed")
+    return out
+
+
 def vit_assemble(patch_out, cls, pos, tiles, out=None, fp32=False):
     _bf16(patch_out, cls, pos)
     if fp32:

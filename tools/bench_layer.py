@@ -141,3 +141,35 @@ if "lora" in ONLY:
     wgu = bf(9728, 896 + 64)
     dgu = bf(M, 9728)
     row("llm gate|up dgrad [4728 x 960] K=9728 (b_t)", timeit(lambda: lib.gemm(dgu, wgu, b_t=True)), 2.0 * M * 960 * 9728)
+
+if "decode" in ONLY:
+    # batched decode step (language mode, B = 32, ~600 cached positions): weight-streaming kernels, HBM-bound by design
+    B, D, I, V, L = 32, 896, 4864, 151655, 608
+    x = bf(B, D)
+    act = bf(B, I)
+    xf = torch.randn(B, D, device=dev)
+    for name, w, a, kw in (("qkv   [32 x 1152] K=896 +bias", bf(1152, D), x, dict(bias=bf(1152))),
+                           ("o     [32 x 896] K=896 fp32 += ", bf(D, D), x, dict(residual=xf, out=xf, out_fp32=True)),
+                           ("gu    [32 x 9728] K=896 SwiGLU", bf(2 * I, D), x, dict(swiglu=True)),
+                           ("down  [32 x 896] K=4864 fp32 +=", bf(D, I), act, dict(residual=xf, out=xf, out_fp32=True)),
+                           ("lm_head [32 x 151655] K=896 fp32", bf(V, D), x, dict(out_fp32=True))):
+        us = timeit(lambda: lib.gemm(a, w, **kw))
+        row("skinny " + name, us, note=f"{w.numel() * 2 / us / 1e3:.0f} GB/s of weights")
+    kc, vc = bf(B, 2, 640, 64), bf(B, 2, 640, 64)
+    qkv = bf(B, 1152)
+    att = torch.empty(B, 896, device=dev, dtype=torch.bfloat16)
+    us = timeit(lambda: lib.attn_gqa(qkv, 1152, kc, vc, B, 1, L, 14, 2, out=att))
+    row("attn_decode_group B=32 L=608", us, note=f"{B * 2 * L * 64 * 2 * 2 / us / 1e3:.0f} GB/s of K/V")
+    row("rope_kv_write B=32", timeit(lambda: lib.rope_kv_write(qkv, kc, vc, B, 1, L)))
+    w = bf(D)
+    h = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
+    row("rmsnorm fp32 -> bf16 [32 x 896]", timeit(lambda: lib.rmsnorm(xf, w, 1e-6, out=h)))
+    lg = torch.randn(B, V, device=dev)
+    row("argmax [32 x 151655]", timeit(lambda: lib.argmax(lg)))
+    kc1, vc1 = bf(1, 2, 640, 64), bf(1, 2, 640, 64)
+    q1 = bf(1, 1152)
+    a1 = torch.empty(1, 896, device=dev, dtype=torch.bfloat16)
+    row("attn_small B=1 L=608", timeit(lambda: lib.attn_gqa(q1, 1152, kc1, vc1, 1, 1, L, 14, 2, out=a1)))
+    x1 = torch.randn(1, D, device=dev)
+    for name, w_, kw in (("qkv+norm", bf(1152, D), dict(bias=bf(1152), rms_weight=w, rms_eps=1e-6)), ("gu+norm SwiGLU", bf(2 * I, D), dict(swiglu=True, rms_weight=w, rms_eps=1e-6))):
+        row("gemv B=1 " + name, timeit(lambda: lib.gemm(x1, w_, **kw)), note=f"{w_.numel() * 2 / 1e6:.1f} MB")
