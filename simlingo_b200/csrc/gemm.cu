@@ -924,22 +924,33 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
   SLB_CHECK_ARG(a->rms_weight == nullptr, "gemm: the fused RMSNorm prologue exists only on the M <= 4 weight-streaming path");
   SLB_CHECK_ARG(!a->a_fp32, "gemm: fp32 activation rows (a_fp32) are only taken by the fused RMSNorm prologue of the M <= 4 path");
   int bn = a->block_n;
-  if (a->swiglu && bn != 2256 && bn != 256) bn = (a->M >= 4096) ? 2256 : 256;
+  if (a->swiglu && bn != 2256 && bn != 256) bn = 0;
   if (bn == 0) {
     const int sms = slb_num_sms();
-    const int mt = ceil_div(a->M, BM);
-    if (!a->a_t && !a->b_t && a->M >= 4096 && (a->swiglu || (a->N % 256) == 0 || a->N >= 2048)) {
-      bn = 2256;  // cluster of two CTAs per 256 x 256 tile: 6-stage pipeline, half the L2->smem operand traffic
-    } else if (!a->a_t && !a->b_t && a->M >= 4096 && (a->N % 224) == 0) {
-      bn = 2224;
-    } else if (!a->a_t && !a->b_t && a->N <= 64 && a->M >= 1024) {
+    const int mt = ceil_div(a->M, BM), mt2 = ceil_div(a->M, 2 * BM);
+    const bool kmajor = !a->a_t && !a->b_t;
+    if (kmajor && a->N <= 64 && a->M >= 1024) {
       bn = a->N <= 32 ? 32 : 64;  // tall-skinny (LoRA down-projection): the A stream is the whole cost
     } else {
-      // 1-CTA kernel: pick the tile width with the fewer (weighted) waves; 256-wide tiles halve A re-reads and are
-      // ~10 % more efficient per flop, but quantise worse on small problems
-      const float c256 = 2.0f * (float)ceil_div(mt * ceil_div(a->N, 256), sms);
-      const float c128 = 1.1f * (float)ceil_div(mt * ceil_div(a->N, 128), sms);
-      bn = (c256 <= c128) ? 256 : 128;
+      // Tile shape by estimated time = waves x (tile area per SM) / (relative efficiency of the kernel): the cluster kernel does
+      // ~10 % more per SM-cycle than the 1-CTA 256-wide tile (6-stage ring, half the operand traffic per SM), the 128-wide tile
+      // ~10 % less; what decides mid-size problems is wave quantisation (M = 4728, N = 896: 76 cluster tiles of 256 x 224 on 74
+      // clusters = two waves for 1.03 waves of work, 148 tiles of 128 x 256 = exactly one).
+      auto cost = [&](int tiles, int units, int area, float eff) { return (float)ceil_div(tiles, units) * (float)area / eff; };
+      float best = cost(mt * ceil_div(a->N, 256), sms, 128 * 256, 1.0f);
+      bn = 256;
+      if (!a->swiglu) {
+        const float c = cost(mt * ceil_div(a->N, 128), sms, 128 * 128, 0.9f);
+        if (c < best) { best = c; bn = 128; }
+      }
+      if (kmajor && a->M >= 2048) {
+        const float c256 = cost(mt2 * ceil_div(a->N, 256), sms / 2, 128 * 256, 1.1f);
+        if (c256 <= best) { best = c256; bn = 2256; }
+        if (!a->swiglu && (a->N % 224) == 0) {
+          const float c224 = cost(mt2 * (a->N / 224), sms / 2, 128 * 224, 1.08f);
+          if (c224 < best) { best = c224; bn = 2224; }
+        }
+      }
     }
   }
   if (bn == 2256 || bn == 2224 || bn == 2192) {

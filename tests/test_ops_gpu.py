@@ -156,6 +156,24 @@ def test_gemm_tma_residual_stream_epilogue(lib, M, N, K, bn):
     assert relerr(out, res + acc + bias.float()) < 2e-3
 
 
+@pytest.mark.parametrize("tiles,fp32", [(2, True), (3, False)])
+def test_patch_embed_implicit_gemm(lib, tiles, fp32):
+    """implicit-GEMM patch embedding (operand gathered from the pixels inside the kernel, class token + position embedding in the
+    epilogue) against conv2d in fp32 and against the explicit im2col + GEMM + assemble path"""
+    px = rnd(tiles, 3, 448, 448, seed=1)
+    wconv = rnd(1024, 3, 14, 14, seed=2, scale=0.05)
+    bias, cls, pos = rnd(1024, seed=3), rnd(1024, seed=4), rnd(1025, 1024, seed=5)
+    wp = torch.zeros(1024, 640, device="cuda", dtype=torch.bfloat16)
+    wp[:, :588] = wconv.reshape(1024, 588)
+    got = lib.patch_embed(px, wp, bias, cls, pos, fp32=fp32)
+    conv = F.conv2d(px.float(), wconv.float(), bias.float(), stride=14)                   # [T, 1024, 32, 32]
+    ref = torch.cat([cls.float().expand(tiles, 1, 1024), conv.flatten(2).transpose(1, 2)], 1) + pos.float()
+    assert got.shape == (tiles * 1025, 1024) and got.dtype == (torch.float32 if fp32 else torch.bfloat16)
+    assert relerr(got.view(tiles, 1025, 1024), ref) < (1e-3 if fp32 else 1e-2)
+    old = lib.vit_assemble(lib.gemm(lib.im2col_patch(px, 640), wp, bias=bias), cls, pos, tiles, fp32=fp32)
+    assert relerr(got, old) < 1e-2
+
+
 def test_gemm_strided_views(lib):
     """A as a column slice of a wider buffer (q part of the fused qkv), out as a slice."""
     M, K, N = 545, 896, 896
