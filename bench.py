@@ -253,10 +253,24 @@ def _gemm_kernel_name(M, N, K, kw):
             return "gemv_bf16_kernel"
         if M <= 32 and K % 32 == 0:
             return "skinny_gemm_kernel"
-    if bn == 0 and kmajor and M >= 4096 and (kw.get("swiglu") or N % 256 == 0 or N >= 2048):
-        return "gemm2_bf16_kernel<256>"
-    if bn == 0 and kmajor and M >= 4096 and N % 224 == 0:
-        return "gemm2_bf16_kernel<224>"
+    if bn == 0:   # tile shape by estimated waves x tile area / kernel efficiency (slb_gemm_bf16)
+        if kmajor and N <= 64 and M >= 1024:
+            return "gemm_bf16_kernel<narrow>"
+        cd = lambda a, b: -(-a // b)
+        sms, mt, mt2 = 148, cd(M, 128), cd(M, 256)
+        cost = lambda tiles, units, area, eff: cd(tiles, units) * area / eff
+        best, name = cost(mt * cd(N, 256), sms, 128 * 256, 1.0), "gemm_bf16_kernel<1-CTA>"
+        if not kw.get("swiglu"):
+            best = min(best, cost(mt * cd(N, 128), sms, 128 * 128, 0.9))
+        if M >= 2048 and not (kw.get("a_t") and not kw.get("b_t")):
+            c = cost(mt2 * cd(N, 256), sms // 2, 128 * 256, 1.1)
+            if c <= best:
+                best, name = c, "gemm2_bf16_kernel<256>"
+            if kmajor and not kw.get("swiglu") and N % 224 == 0:
+                c = cost(mt2 * (N // 224), sms // 2, 128 * 224, 1.08)
+                if c < best:
+                    best, name = c, "gemm2_bf16_kernel<224>"
+        return name
     return "gemm_bf16_kernel<1-CTA>"
 
 

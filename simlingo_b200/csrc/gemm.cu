@@ -672,7 +672,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& p, const CUte
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int TA = 0, int TB = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_res,
@@ -743,9 +743,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint8_t* sb = sa + L::kABytes;
           if (elect_one_sync()) {
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-            if (kb < num_kb1) tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-            else tma_load_2d_2sm(sa, &tmap_a2, &full_bar[stage], (kb - num_kb1) * BK, m0);
-            tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+            if (TA == 0) {
+              if (kb < num_kb1) tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+              else tma_load_2d_2sm(sa, &tmap_a2, &full_bar[stage], (kb - num_kb1) * BK, m0);
+            } else {   // MN-major A ([K, M] in memory): this CTA's 128 rows as two 64-row groups of [64 k][64 m]
+#pragma unroll
+              for (int g = 0; g < BM / 64; ++g) tma_load_2d_2sm(sa + g * (64 * BK * 2), &tmap_a, &full_bar[stage], m0 + g * 64, kb * BK);
+            }
+            if (TB == 0) {
+              tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+            } else {   // MN-major B ([K, N] in memory): this CTA's BN / 2 columns as 64-column groups
+#pragma unroll
+              for (int g = 0; g < BN / 2 / 64; ++g) tma_load_2d_2sm(sb + g * (64 * BK * 2), &tmap_b, &full_bar[stage], n0 + g * 64, kb * BK);
+            }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -755,7 +765,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, TA, TB);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -773,11 +783,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           w_full += clock64() - c0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint64_t da = umma_desc_kmajor_sw128(sa);
-          const uint64_t db = umma_desc_kmajor_sw128(sa + L::kABytes);
+          const uint64_t da = TA ? umma_desc_mnmajor_sw128(sa, 64 * BK * 2) : umma_desc_kmajor_sw128(sa);
+          const uint64_t db = TB ? umma_desc_mnmajor_sw128(sa + L::kABytes, 64 * BK * 2) : umma_desc_kmajor_sw128(sa + L::kABytes);
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // K-major: +32 bytes per UMMA_K inside the swizzle row; MN-major: +16 k-rows * 128 B
+              const uint64_t ka = TA ? (uint64_t)(k * (UMMA_K * 128 >> 4)) : (uint64_t)(2 * k);
+              const uint64_t kbo = TB ? (uint64_t)(k * (UMMA_K * 128 >> 4)) : (uint64_t)(2 * k);
+              tc_mma_bf16_2sm(tmem_d, da + ka, db + kbo, idesc, (kb | k) != 0);
+            }
             tc_commit_2sm(&empty_bar[stage], 3);
             if (kb == num_kb - 1) tc_commit_2sm(&tfull_bar[acc], 3);
           }
@@ -834,14 +849,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int TA = 0, int TB = 0>
 int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
   using L = Smem2<BN, EPI>;
+  static_assert(!TB || (BN / 2) % 64 == 0, "MN-major B: the CTA's half tile must be whole 64-column groups");
   CUtensorMap ta, tb, ta2, tres, tout;
   const int K2 = (a->A2 && a->K2 > 0) ? a->K2 : 0;
-  int rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM);
+  int rc;
+  if (!TA) rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM);
+  else     rc = slb_make_tmap_2d(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, BK);
   if (rc) return rc;
-  rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)(a->K + K2), (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN / 2);
+  if (!TB) rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)(a->K + K2), (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN / 2);
+  else     rc = slb_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, BK);
   if (rc) return rc;
   ta2 = ta;
   if (K2) {
@@ -866,7 +885,7 @@ int launch_gemm2(const slb_gemm_args* a, cudaStream_t stream) {
   p.res_prefetch = slb_gemm_res_prefetch();
   p.num_m = ceil_div(a->M, 2 * BM);
   p.num_n = ceil_div(a->N, BN);
-  auto kern = gemm2_bf16_kernel<BN, EPI>;
+  auto kern = gemm2_bf16_kernel<BN, EPI, TA, TB>;
   static bool attr_set = false;
   if (!attr_set) {
     SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -943,18 +962,22 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
         const float c = cost(mt * ceil_div(a->N, 128), sms, 128 * 128, 0.9f);
         if (c < best) { best = c; bn = 128; }
       }
-      if (kmajor && a->M >= 2048) {
+      if (a->M >= 2048 && !(a->a_t && !a->b_t)) {   // the cluster kernel also takes the dgrad (b_t) and wgrad (a_t + b_t) operand forms
         const float c256 = cost(mt2 * ceil_div(a->N, 256), sms / 2, 128 * 256, 1.1f);
         if (c256 <= best) { best = c256; bn = 2256; }
-        if (!a->swiglu && (a->N % 224) == 0) {
+        if (kmajor && !a->swiglu && (a->N % 224) == 0) {
           const float c224 = cost(mt2 * (a->N / 224), sms / 2, 128 * 224, 1.08f);
           if (c224 < best) { best = c224; bn = 2224; }
         }
       }
     }
   }
+  if (bn == 2256 && (a->a_t || a->b_t)) {
+    SLB_CHECK_ARG(!a->swiglu && !(a->A2 && a->K2 > 0), "gemm: SwiGLU / a second A source need K-major operands");
+    return a->a_t ? launch_gemm2<256, 0, 1, 1>(a, stream) : launch_gemm2<256, 0, 0, 1>(a, stream);
+  }
   if (bn == 2256 || bn == 2224 || bn == 2192) {
-    SLB_CHECK_ARG(!a->a_t && !a->b_t, "gemm: the 2-CTA kernel takes K-major operands only");
+    SLB_CHECK_ARG(!a->a_t && !a->b_t, "gemm: the 224 / 192-wide cluster tiles take K-major operands only");
     SLB_CHECK_ARG(!a->swiglu || bn == 2256, "gemm: swiglu needs 256-wide tiles");
     if (tma_epilogue_ok(a)) {
       if (bn == 2256) return launch_gemm2<256, 1>(a, stream);

@@ -174,6 +174,26 @@ def test_patch_embed_implicit_gemm(lib, tiles, fp32):
     assert relerr(got, old) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(4728, 992, 1152), (16400, 1024, 4096), (4100, 304, 136)])
+def test_gemm_cluster_kernel_mn_major_dgrad(lib, M, N, K):
+    """dX = dY W (b_t: W is [K, N] in memory) on the cta_group::2 kernel"""
+    dy, w = rnd(M, K, seed=1, scale=0.5), rnd(K, N + 8, seed=2, scale=0.05)[:, :N]
+    ref = dy.float() @ w.float()
+    assert relerr(lib.gemm(dy, w, b_t=True, block_n=2256), ref) < 5e-3
+    assert relerr(lib.gemm(dy, w, b_t=True), ref) < 5e-3            # whatever the tile selection picks
+
+
+@pytest.mark.parametrize("M,N,K", [(3072, 1024, 16400), (2048, 4096, 4728), (2100, 640, 1000)])
+def test_gemm_cluster_kernel_mn_major_wgrad(lib, M, N, K):
+    """dW = dY^T X (a_t + b_t: both operands [K, *] in memory), accumulating into the output"""
+    dy, x = rnd(K, M, seed=1, scale=0.5), rnd(K, N, seed=2, scale=0.5)
+    ref = dy.float().t() @ x.float()
+    assert relerr(lib.gemm(dy, x, a_t=True, b_t=True, block_n=2256), ref) < 5e-3
+    g = rnd(M, N, seed=3)
+    got = lib.gemm(dy, x, out=g.clone(), a_t=True, b_t=True, residual=g, alpha=0.5)
+    assert relerr(got, g.float() + 0.5 * ref) < 5e-3
+
+
 def test_gemm_strided_views(lib):
     """A as a column slice of a wider buffer (q part of the fused qkv), out as a slice."""
     M, K, N = 545, 896, 896
