@@ -183,7 +183,7 @@ def test_gemm_cluster_kernel_mn_major_dgrad(lib, M, N, K):
     assert relerr(lib.gemm(dy, w, b_t=True), ref) < 5e-3            # whatever the tile selection picks
 
 
-@pytest.mark.parametrize("M,N,K", [(3072, 1024, 16400), (2048, 4096, 4728), (2100, 640, 1000)])
+@pytest.mark.parametrize("M,N,K", [(3072, 1024, 16400), (2048, 4096, 4728), (2104, 640, 1000)])
 def test_gemm_cluster_kernel_mn_major_wgrad(lib, M, N, K):
     """dW = dY^T X (a_t + b_t: both operands [K, *] in memory), accumulating into the output"""
     dy, x = rnd(K, M, seed=1, scale=0.5), rnd(K, N, seed=2, scale=0.5)
