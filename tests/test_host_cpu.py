@@ -142,14 +142,15 @@ sys.path.insert(0, {root!r})
 from simlingo_b200.dist import env_rank_world, gather_predictions, max_over_ranks, shard_range
 rank, world, _ = env_rank_world()
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-lo, hi = shard_range(7, rank, world)
+n_items = 7 if world <= 7 else 2 * world - 1      # ragged shards at every world size
+lo, hi = shard_range(n_items, rank, world)
 local = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1).expand(-1, 2, 2).contiguous()
 ms = max_over_ranks(10.0 + rank)
 assert ms == 10.0 + world - 1, ms
-out = gather_predictions(local, [shard_range(7, r, world)[1] - shard_range(7, r, world)[0] for r in range(world)])
+out = gather_predictions(local, [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)])
 if rank == 0:
     full = torch.cat(out)
-    assert full[:, 0, 0].tolist() == [float(i) for i in range(7)], full
+    assert full[:, 0, 0].tolist() == [float(i) for i in range(n_items)], full
 # gradient all-reduce semantics of the training path (sum then / world), bf16 buckets
 g = torch.full((16,), float(rank + 1), dtype=torch.bfloat16)
 dist.all_reduce(g)
@@ -212,16 +213,31 @@ print("ok", rank)
 """
 
 
-def test_world_size_2_gloo():
-    port = 29500 + (os.getpid() % 500)
+def _run_gloo_world(world: int) -> None:
+    port = 29500 + (os.getpid() % 400) + 10 * world
     code = _WORKER.format(root=ROOT, port=port)
     procs = []
-    for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
         procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    for p in procs:
-        out, _ = p.communicate(timeout=300)
-        assert p.returncode == 0, out
+    try:
+        for p in procs:
+            out, _ = p.communicate(timeout=600)
+            assert p.returncode == 0, out
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+
+
+def test_world_size_2_gloo():
+    _run_gloo_world(2)
+
+
+def test_world_size_8_gloo():
+    """the same shard / max-over-ranks / bucket-protocol checks at the reference's training world size (8 ranks, train_simlingo_seed1.sh:3-5):
+    every range of the flat gradient buffer reduced exactly once, sum over 8 ranks exact, no_sync accumulation, double-reduction refusal"""
+    _run_gloo_world(8)
 
 
 def test_store_tracks_which_parameters_received_gradients():
