@@ -176,10 +176,11 @@ int slb_wp_encoder(const float* coords, const slb_wp_weights* w, void* out, int 
 /* ================================ training-only entry points ===================================
  * The reference trains through torch autograd + flash-attn backward + torch.optim.AdamW under Lightning
  * (driving.py:236-271,718-732; train.py:160-217).  dgrad / wgrad GEMMs use slb_gemm_bf16 with b_t / a_t+b_t. */
+/* dx_add (optional, bf16 [rows, cols]): the gradient arriving over the residual connection, added to dx before its one rounding */
 int slb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                      float* dw_accum, float* db_accum, int rows, int cols, void* stream);
+                      float* dw_accum, float* db_accum, int rows, int cols, const void* dx_add, void* stream);
 int slb_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw_accum, int rows,
-                    int cols, void* stream);
+                    int cols, const void* dx_add, void* stream);
 int slb_pixel_shuffle_ln_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                              void* dx, float* dw_accum, float* db_accum, int tiles, void* stream);
 int slb_gelu_fwd(const void* x, void* y, int64_t n, void* stream);

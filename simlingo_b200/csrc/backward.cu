@@ -31,7 +31,9 @@ inline int grid_for(size_t work, int block) {
 template <int MAXV, bool RMS, bool ACC>
 __global__ void __launch_bounds__(kWarps * 32, ACC ? 2 : 1)
 norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ mean,
-                const float* __restrict__ rstd, bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int rows, int cols) {
+                const float* __restrict__ rstd, bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int rows, int cols,
+                const bf16* __restrict__ dx_add) {
+  // dx_add (optional): gradient arriving over the residual connection, added before the single rounding of dx.
   // ACC: per-thread fp32 partials of dw / db over the warp's rows, combined per block in shared memory (bank-conflict
   // free [e][vec] layout) and flushed with one global atomicAdd per column per block.  Pass 2 re-reads dy / x from L1
   // instead of holding them in registers, which keeps the kernel at two blocks per SM.
@@ -83,6 +85,12 @@ norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const b
         load8(w + vi * 8, wv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = rs * (dyv[e] * wv[e] - m1 - (xv[e] - mu) * rs * m2);
+        if (dx_add) {
+          float av[8];
+          load8(dx_add + (size_t)row * cols + vi * 8, av);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += av[e];
+        }
         store8(dx + (size_t)row * cols + vi * 8, o);
       }
     }
@@ -523,22 +531,22 @@ ce_kernel(const float* __restrict__ logits, long long ld, const long long* __res
 #define ST(s) ((cudaStream_t)(s))
 
 extern "C" int slb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                                 float* dw_accum, float* db_accum, int rows, int cols, void* stream) {
+                                 float* dw_accum, float* db_accum, int rows, int cols, const void* dx_add, void* stream) {
   SLB_CHECK_ARG(rows > 0 && (cols % 8) == 0 && cols <= 4096, "layernorm_bwd: bad shape %d x %d", rows, cols);
   const int grid = min(ceil_div(rows, kWarps), slb_num_sms() * (cols <= 1024 ? 4 : 2));
   if (cols <= 1024)
-    norm_bwd_kernel<4, false, true><<<grid, kWarps * 32, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw_accum, db_accum, rows, cols);
+    norm_bwd_kernel<4, false, true><<<grid, kWarps * 32, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw_accum, db_accum, rows, cols, (const bf16*)dx_add);
   else
-    norm_bwd_kernel<16, false, false><<<grid, kWarps * 32, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw_accum, db_accum, rows, cols);
+    norm_bwd_kernel<16, false, false><<<grid, kWarps * 32, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw_accum, db_accum, rows, cols, (const bf16*)dx_add);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }
 
 extern "C" int slb_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw_accum, int rows,
-                               int cols, void* stream) {
+                               int cols, const void* dx_add, void* stream) {
   SLB_CHECK_ARG(rows > 0 && (cols % 8) == 0 && cols <= 1024, "rmsnorm_bwd: bad shape %d x %d", rows, cols);
   const int grid = min(ceil_div(rows, kWarps), slb_num_sms() * 4);
-  norm_bwd_kernel<4, true, true><<<grid, kWarps * 32, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, nullptr, rstd, (bf16*)dx, dw_accum, nullptr, rows, cols);
+  norm_bwd_kernel<4, true, true><<<grid, kWarps * 32, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, nullptr, rstd, (bf16*)dx, dw_accum, nullptr, rows, cols, (const bf16*)dx_add);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

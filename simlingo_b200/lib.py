@@ -327,18 +327,21 @@ def _f32(*ts):
             assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), (t.device, t.dtype)
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dw_acc, db_acc, dx=None):
-    _bf16(dy, x, w); _f32(mean, rstd, dw_acc, db_acc)
+def layernorm_bwd(dy, x, w, mean, rstd, dw_acc, db_acc, dx=None, add=None):
+    """add: gradient arriving over the residual connection (bf16, same shape), summed into dx before its one rounding"""
+    _bf16(dy, x, w, add); _f32(mean, rstd, dw_acc, db_acc)
     dx = torch.empty_like(x) if dx is None else dx
-    _check(load().slb_layernorm_bwd(_p(dy), _p(x), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw_acc), _p(db_acc), x.shape[0], x.shape[1], _stream()),
+    assert add is None or (add.is_contiguous() and add.shape == x.shape)
+    _check(load().slb_layernorm_bwd(_p(dy), _p(x), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw_acc), _p(db_acc), x.shape[0], x.shape[1], _p(add), _stream()),
            "layernorm_bwd")
     return dx
 
 
-def rmsnorm_bwd(dy, x, w, rstd, dx=None):
-    _bf16(dy, x, w); _f32(rstd)
+def rmsnorm_bwd(dy, x, w, rstd, dx=None, add=None):
+    _bf16(dy, x, w, add); _f32(rstd)
     dx = torch.empty_like(x) if dx is None else dx
-    _check(load().slb_rmsnorm_bwd(_p(dy), _p(x), _p(w), _p(rstd), _p(dx), None, x.shape[0], x.shape[1], _stream()), "rmsnorm_bwd")
+    assert add is None or (add.is_contiguous() and add.shape == x.shape)
+    _check(load().slb_rmsnorm_bwd(_p(dy), _p(x), _p(w), _p(rstd), _p(dx), None, x.shape[0], x.shape[1], _p(add), _stream()), "rmsnorm_bwd")
     return dx
 
 

@@ -740,13 +740,15 @@ class TrainEngine:
             qkv = lib.gemm(h1, w(p + "attn.qkv.weight"), bias=w(p + "attn.qkv.bias"))
             lse = torch.empty((T, s.vit_heads, N), device=dev, dtype=torch.float32)
             att = lib.attn_vit(qkv, T, N, s.vit_heads, lse=lse)
-            p1 = lib.gemm(att, w(p + "attn.proj.weight"), bias=w(p + "attn.proj.bias"))
-            xm = lib.scale_cols_add(p1, w(p + "ls1"), x)
+            # layer-scale + residual in the GEMM epilogue; the un-scaled branch output (needed by the layer-scale backward) leaves through
+            # the epilogue's second output (aux_mode 1 = alpha * acc + bias)
+            p1 = torch.empty((M, Dv), device=dev, dtype=bf)
+            xm = lib.gemm(att, w(p + "attn.proj.weight"), bias=w(p + "attn.proj.bias"), scale_n=w(p + "ls1"), residual=x, aux=p1, aux_mode=1)
             h2 = lib.layernorm(xm, w(p + "norm2.weight"), w(p + "norm2.bias"), s.vit_eps, stats=st2)
             fpre = torch.empty((M, s.vit_mlp), device=dev, dtype=bf)   # GELU input, kept for backward (second epilogue output)
             fact = lib.gemm(h2, w(p + "mlp.fc1.weight"), bias=w(p + "mlp.fc1.bias"), act=lib.ACT_GELU, aux=fpre, aux_mode=1)
-            p2 = lib.gemm(fact, w(p + "mlp.fc2.weight"), bias=w(p + "mlp.fc2.bias"))
-            xo = lib.scale_cols_add(p2, w(p + "ls2"), xm)
+            p2 = torch.empty((M, Dv), device=dev, dtype=bf)
+            xo = lib.gemm(fact, w(p + "mlp.fc2.weight"), bias=w(p + "mlp.fc2.bias"), scale_n=w(p + "ls2"), residual=xm, aux=p2, aux_mode=1)
             if self.vit_trainable:
                 layers.append(dict(x=x, st1=st1, h1=h1, qkv=qkv, lse=lse, att=att, p1=p1, xm=xm, st2=st2, h2=h2, fpre=fpre, fact=fact, p2=p2))
             x = xo
@@ -789,8 +791,7 @@ class TrainEngine:
             self._wgrad(dfpre, a["h2"], p + "mlp.fc1.weight")
             dh2 = lib.gemm(dfpre, w(p + "mlp.fc1.weight"), b_t=True, out=dp2)
             dxm = lib.layernorm_bwd(dh2, a["xm"], w(p + "norm2.weight"), a["st2"][0], a["st2"][1],
-                                    self._acc(p + "norm2.weight"), self._acc(p + "norm2.bias"))
-            lib.add_inplace(dxm, dx)
+                                    self._acc(p + "norm2.weight"), self._acc(p + "norm2.bias"), add=dx)   # + the residual path's gradient
             dp1 = lib.layerscale_bwd(dxm, a["p1"], w(p + "ls1"), self._acc(p + "ls1"), self._acc(p + "attn.proj.bias"), out=dx)
             self._wgrad(dp1, a["att"], p + "attn.proj.weight")
             datt = lib.gemm(dp1, w(p + "attn.proj.weight"), b_t=True, out=dh2)
@@ -800,8 +801,7 @@ class TrainEngine:
             self._wgrad(dqkv, a["h1"], p + "attn.qkv.weight")
             dh1 = lib.gemm(dqkv, w(p + "attn.qkv.weight"), b_t=True, out=dp1)
             dxi = lib.layernorm_bwd(dh1, a["x"], w(p + "norm1.weight"), a["st1"][0], a["st1"][1],
-                                    self._acc(p + "norm1.weight"), self._acc(p + "norm1.bias"), dx=datt)
-            lib.add_inplace(dxi, dxm)
+                                    self._acc(p + "norm1.weight"), self._acc(p + "norm1.bias"), dx=datt, add=dxm)
             dx = dxi
             st.flush_group(f"vit{i}")
         # ---- embeddings ----
@@ -927,8 +927,7 @@ class TrainEngine:
             dgu = lib.silu_mul_cat_bwd(a["gu"], dact)                   # [dgate | dup]
             cat = lib.gemm(dgu, ly["gu"], b_t=True)                     # [dh2_base | dt_gate dt_up]
             dh2 = self._lora_bwd(dgu, cat, D, pm, ("gate_proj", "up_proj"), lgu, sg, sd_t)
-            dxm = lib.rmsnorm_bwd(dh2, a["xm"], w(p + "post_attention_layernorm.weight"), a["r2"])
-            lib.add_inplace(dxm, dx)
+            dxm = lib.rmsnorm_bwd(dh2, a["xm"], w(p + "post_attention_layernorm.weight"), a["r2"], add=dx)   # + the residual path's gradient
             # ---- attention ----
             cat = lib.gemm(dxm, ly["o"], b_t=True)                      # [datt_base | dt_o]
             datt = self._lora_bwd(dxm, cat, Hq * s.head_dim, pa, ("o_proj",), lo, so, sd_t)
@@ -938,8 +937,7 @@ class TrainEngine:
             del dq, dk, dv
             cat = lib.gemm(dqkv, ly["qkv"], b_t=True)                   # [dh1_base | dt_q dt_k dt_v]
             dh1 = self._lora_bwd(dqkv, cat, D, pa, ("q_proj", "k_proj", "v_proj"), lqkv, sq, sd_t)
-            dxi = lib.rmsnorm_bwd(dh1, a["x"], w(p + "input_layernorm.weight"), a["r1"])
-            lib.add_inplace(dxi, dxm)
+            dxi = lib.rmsnorm_bwd(dh1, a["x"], w(p + "input_layernorm.weight"), a["r1"], add=dxm)
             dx = dxi
             self._join()   # the layer's LoRA wgrads (side streams) are complete before the group is declared final
             st.flush_group(f"llm{i}")

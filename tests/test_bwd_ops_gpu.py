@@ -34,6 +34,9 @@ def test_layernorm_bwd(lib):
         xr, wr, br = x.float().requires_grad_(), w.float().requires_grad_(), b.float().requires_grad_()
         F.layer_norm(xr, (cols,), wr, br, 1e-6).backward(dy.float())
         assert relerr(dx, xr.grad) < 2e-2 and relerr(dw, wr.grad) < 1e-3 and relerr(db, br.grad) < 1e-3
+        res = rnd(rows, cols, seed=9)   # gradient of the residual path, summed into dx before the single rounding
+        dx2 = lib.layernorm_bwd(dy, x, w, mean, rstd, torch.zeros_like(dw), torch.zeros_like(db), add=res)
+        assert relerr(dx2, xr.grad + res.float()) < 2e-2
 
 
 def test_rmsnorm_bwd(lib):
@@ -45,6 +48,8 @@ def test_rmsnorm_bwd(lib):
     xr = x.float().requires_grad_()
     (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()).backward(dy.float())
     assert relerr(dx, xr.grad) < 2e-2
+    res = rnd(rows, cols, seed=9)
+    assert relerr(lib.rmsnorm_bwd(dy, x, w, rstd, add=res), xr.grad + res.float()) < 2e-2
 
 
 def test_pixel_shuffle_ln_bwd(lib):
