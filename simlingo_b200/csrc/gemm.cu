@@ -1,10 +1,13 @@
-// bf16 GEMM for sm_100a: TMA (128B swizzle) -> smem ring -> tcgen05.mma (cta_group::1, 128 x BN x 16,
-// fp32 accumulators in TMEM, two accumulator stages) -> tcgen05.ld epilogue with fused
-// bias / activation / layer-scale / residual / SwiGLU.  Persistent, warp-specialised:
+// bf16 GEMM for sm_100a: TMA (128B swizzle) -> smem ring -> tcgen05.mma (fp32 accumulators in TMEM, two accumulator stages) ->
+// tcgen05.ld epilogue with fused bias / activation / layer-scale / residual / SwiGLU.  Persistent, warp-specialised:
 //   warp 0     TMA producer (one elected lane)
 //   warp 1     TMEM allocator + MMA issuer (one elected lane)
-//   warps 2-5  epilogue (warp w reads TMEM lanes 32*(w%4) .. +31 = accumulator rows)
-// Covers K1,K3,K5,K7,K10,K13,K14 of SURVEY.md section 2.2 and their dgrad/wgrad (a_t / b_t operands).
+//   warps 2-9  epilogue (warp w reads TMEM lanes 32*(w%4) .. +31 = accumulator rows; two warps per quadrant split the columns)
+// Two kernels: gemm_bf16_kernel<BN,TA,TB> (cta_group::1, 128 x BN tiles, BN = 32 / 64 / 128 / 256) and gemm2_bf16_kernel<BN,EPI,TA,TB>
+// (cta_group::2: a cluster of two CTAs per 256 x BN tile, BN = 256 / 224 / 192; EPI = 1: fp32 residual stream moved by TMA).
+// Operand forms: K-major (forward), b_t (dgrad), a_t + b_t (wgrad); a second A source appended along k (un-merged LoRA).
+// slb_gemm_bf16 picks the kernel and tile shape by estimated waves x tile area / kernel efficiency; M <= 32 goes to the
+// weight-streaming kernels of gemv.cu.  Covers K1,K3,K5,K7,K10,K13,K14 of SURVEY.md section 2.2 and their dgrad / wgrad.
 #include <cstdlib>
 #include "common.cuh"
 #include "../../include/simlingo_b200.h"
