@@ -60,13 +60,18 @@ assert rel(got_g, 2 * ref_g) < 2e-2, rel(got_g, 2 * ref_g)                 # sum
 du, dr = got_p - p0.float(), ref_p - p0.float()
 cos = (du * dr).sum() / (du.norm() * dr.norm())
 assert cos > 0.98, cos.item()
-# ... and element-wise where the gradient is well above that noise (>= 5 % of the largest element of its group)
+# ... and element-wise where the gradient is well above that noise (>= 5 % of the largest element of its group).  Three Adam steps
+# amplify the run-to-run noise of the fp32-atomic reductions in the norm / bias gradients (measured: outliers of 5-11 % on a
+# handful of elements while every group's gradient agrees to 2 %), so the check is on the distribution: a systematic error (a range reduced
+# twice, a missed 1/world) moves the median, not just the tail
 for g in store.groups:
     b = ref_g[g.start:g.end]
     big = b.abs() >= 0.05 * b.abs().max()
     if big.any():
         a, c = du[g.start:g.end][big], dr[g.start:g.end][big]
-        assert rel(a, c) < 1e-1, (g.name, rel(a, c))   # three Adam steps amplify the fp32-atomics ordering noise of the gradients (measured 0.054 on mlp1)
+        dev = ((a - c).abs() / c.abs().clamp_min(1e-12)).float()
+        assert dev.median().item() < 2e-2, (g.name, dev.median().item())
+        assert torch.quantile(dev[:1_000_000], 0.99).item() < 0.25, (g.name, torch.quantile(dev[:1_000_000], 0.99).item())
 # gradient accumulation under data parallelism (ADVICE r1): two micro-batches, the first under no_sync(), reduce once
 store.flat_param.copy_(p0)
 opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], store, lr=1e-3, weight_decay=0.1, max_grad_norm=0.3)
