@@ -234,6 +234,9 @@ class ParamStore:
         backend = backend or os.environ.get("SLB_DP_BACKEND") or ("native" if self.flat_grad.is_cuda else "torch")
         if backend not in ("native", "native-graph", "torch"):
             raise ValueError(f"unknown data-parallel backend {backend!r}")
+        if backend == "native-graph" and os.environ.get("SLB_ALLOW_NATIVE_GRAPH") != "1":
+            raise RuntimeError("simlingo_b200: the 'native-graph' exchange (all-reduces captured inside the backward CUDA graphs) is experimental: "
+                               "its 2-GPU test hung on the B200 box (profiles/r02_dp_tests_2gpu_v4.log); set SLB_ALLOW_NATIVE_GRAPH=1 to try it")
         self.pg = process_group if process_group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.pg)
         self.dp_backend = backend
