@@ -262,7 +262,8 @@ def _gemm_kernel_name(M, N, K, kw):
         best, name = cost(mt * cd(N, 256), sms, 128 * 256, 1.0), "gemm_bf16_kernel<1-CTA>"
         if not kw.get("swiglu"):
             best = min(best, cost(mt * cd(N, 128), sms, 128 * 128, 0.9))
-        if M >= 2048 and not (kw.get("a_t") and not kw.get("b_t")):
+        min_m2 = 1024 if (kw.get("a_t") and kw.get("b_t") and M % 256 == 0) else 2048
+        if M >= min_m2 and not (kw.get("a_t") and not kw.get("b_t")):
             c = cost(mt2 * cd(N, 256), sms // 2, 128 * 256, 1.1)
             if c <= best:
                 best, name = c, "gemm2_bf16_kernel<256>"

@@ -112,6 +112,11 @@ size_t slb_attn_gqa_fwd_workspace(int batch, int lq);
 /* ---- RoPE + KV-cache write (modeling_qwen2.py:102-146 rotate_half convention, theta 1e6) --------
  * qkv [B*Lq, (Hq+2Hkv)*64] from the fused QKV GEMM; rotates q in place, writes rotated k and v
  * into the caches at positions past..past+Lq-1 (positions are arange over the padded sequence). */
+/* Decode step (one new position per sequence) in one launch: qkv bf16 [batch, ldq] holds the un-rotated q | k | v of the new position;
+ * the kernel rotates q (fp32) and the new key, writes the new key / value rows into the caches at position `past` (*past_dev when given)
+ * and attends over positions 0 .. past.  Equivalent to slb_rope_kv_write + slb_attn_gqa_fwd with lq = 1 (llm.py:217-248 per token). */
+int slb_attn_decode_rope(void* qkv, int64_t ldq, void* kcache, void* vcache, const uint8_t* key_valid, int key_valid_ld, void* out,
+                         int batch, int past, const int32_t* past_dev, int lmax, int hq, int hkv, float theta, void* stream);
 int slb_rope_kv_write(void* qkv, void* kcache, void* vcache, int batch, int lq, int past, const int32_t* past_dev, int lmax,
                       int hq, int hkv, float theta, void* stream);
 /* ---- embeddings / placeholder substitution (adaptors.py:256; internvl2_model.py:54-91,119-131) --
@@ -162,6 +167,30 @@ int slb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 /* ---- LM head tail: argmax over fp32 logits (llm.py:157-158) ---- */
 int slb_argmax_f32(const float* logits, int64_t ld, int rows, int cols, int64_t* out_idx, float* out_margin,
                    void* stream);
+/* ---- greedy decode loop (llm.py:217-248: embed the last sampled token, all decoder layers against the KV cache, final norm,
+ * lm_head, argmax, EOS bookkeeping - per generated token) as ONE persistent kernel: one CTA per SM, grid-wide barriers between the
+ * phases of a layer, token loop / position counter / EOS test on the device.  Replaces, per token, the chain
+ * slb_gather_rows -> n_layers x {slb_rmsnorm, slb_gemm_bf16 (qkv), slb_attn_decode_rope, slb_gemm_bf16 (o), slb_rmsnorm,
+ * slb_gemm_bf16 (gate|up SwiGLU), slb_gemm_bf16 (down)} -> slb_rmsnorm -> slb_gemm_bf16 (lm_head) -> slb_argmax_f32.
+ * Weights per layer (LoRA folded): qkv [(hq+2hkv)*64, hidden] + bias, o [hidden, hidden], gate|up interleaved in groups of 128 rows
+ * [2*mlp, hidden] (the slb_gemm_bf16 swiglu layout), down [hidden, mlp], the two RMSNorm weights.
+ * State (device): *pos = number of cached positions (= position of the next token), nxt[batch] = last sampled ids (in: to embed;
+ * out: newest), sampled [batch, ld_sampled] / *step / done[batch] / n_gen[batch] as llm.py:232-248 keeps them; runs at most n_steps
+ * tokens and stops early once every done[b] is set (eos >= 0).  *status is set non-zero if a grid barrier timed out. */
+typedef struct { const void *qkv, *bqkv, *o, *gu, *d, *ln1, *ln2; } slb_decode_layer;
+typedef struct {
+  const slb_decode_layer* layers;   /* DEVICE array [n_layers] */
+  int32_t n_layers, batch, hidden, mlp, vocab, hq, hkv, lmax, n_steps, max_new;
+  int64_t emb_rows, eos /* < 0: none */, ld_sampled;
+  const void *emb, *norm_w, *lm_head;   /* bf16 [emb_rows, hidden], [hidden], [vocab, hidden] */
+  void *kcache, *vcache;                /* bf16 [n_layers, batch, hkv, lmax, 64] */
+  int32_t* pos; int64_t* nxt; int64_t* sampled; int64_t* step; uint8_t* done; int64_t* n_gen;
+  float rope_theta, rms_eps;
+  void* workspace; size_t workspace_bytes;   /* slb_decode_workspace_bytes(), 256-byte aligned */
+  uint32_t* status;
+} slb_decode_args;
+size_t slb_decode_workspace_bytes(int batch, int hidden, int mlp, int hq, int hkv);
+int slb_decode_loop(const slb_decode_args* a, void* stream);
 /* ---- driving heads (adaptors.py:113-115,130-132,163-180) and wp encoder (adaptors.py:64-93) ----
  * feats [B,30,896] -> route [B,20,2] (896->512->256->2 SiLU, cumsum), speed [B,10,2] (896->256->2), fp32 out */
 typedef struct {

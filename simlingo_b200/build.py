@@ -14,7 +14,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libsimlingo_b200.so"
-SOURCES = ["api.cu", "gemm.cu", "patch_embed.cu", "gemv.cu", "attention.cu", "attention_gqa.cu", "attention_vit.cu", "elementwise.cu", "backward.cu", "lora.cu", "attention_bwd.cu", "optim.cu", "comm.cu", "preprocess.cu", "postprocess.cu"]
+SOURCES = ["api.cu", "gemm.cu", "patch_embed.cu", "gemv.cu", "decode.cu", "attention.cu", "attention_gqa.cu", "attention_vit.cu", "elementwise.cu", "backward.cu", "lora.cu", "attention_bwd.cu", "optim.cu", "comm.cu", "preprocess.cu", "postprocess.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -267,13 +267,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 //            128-byte warp load; 4 keys in flight; the 8 partial outputs are combined through smem
 // ------------------------------------------------------------------------------------------------
 constexpr int kSmallThreads = 1024, kSmallWarps = kSmallThreads / 32;  // one key per thread for the 545..700-key agent prompts
+// ROPE (decode step, lq == 1): q still holds the UN-rotated projection output; the kernel rotates q on the fly (fp32), rotates the new
+// key, writes it and the new value row into the caches (one block per kv head does the writes) and takes the newest key / value from
+// shared memory instead of the cache - the separate RoPE + KV-write launch of every layer disappears (24 launches per token).
+template <bool ROPE>
 __global__ void __launch_bounds__(kSmallThreads)
-attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* kc, const bf16* vc,
                   const uint8_t* __restrict__ key_valid, int key_valid_ld, bf16* __restrict__ out, long long ldo, int lq, int past,
-                  int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev) {
+                  int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev, float log2_theta) {
   extern __shared__ float sm[];
+  __shared__ float rcs[32], rsn[32], knew[64], vnew[64];
   pdl_trigger();
-  pdl_wait();   // q / the newest K, V rows are written by the RoPE kernel right before us
+  pdl_wait();   // q / the newest K, V rows are written by the kernel right before us
   if (past_dev) past = *past_dev;  // position counter kept on the device: the same CUDA graph serves every decode step
   float* qs = sm;                        // 64
   float* red = sm + 64;                  // 2 * kSmallWarps
@@ -283,14 +288,42 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
   const int hk = h / (hq / hkv);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nkeys = past + i + 1;
+  const int nk_c = ROPE ? nkeys - 1 : nkeys;   // keys taken from the cache
   const bf16* qr = q + ((size_t)b * lq + i) * ldq + h * 64;
-  if (tid < 64) qs[tid] = __bfloat162float(qr[tid]) * scale;
-  __syncthreads();
   const bf16* kbase = kc + ((size_t)b * hkv + hk) * lmax * 64;
   const bf16* vbase = vc + ((size_t)b * hkv + hk) * lmax * 64;
+  if (ROPE) {
+    if (tid < 32) {   // same arithmetic as rope_kv_write_kernel
+      const float inv_freq = exp2f(-(float)(2 * tid) / 64.0f * log2_theta);
+      sincosf((float)(past + i) * inv_freq, &rsn[tid], &rcs[tid]);
+    }
+    __syncthreads();
+    const bf16* krow = q + ((size_t)b * lq + i) * ldq + (hq + hk) * 64;
+    const bf16* vrow = krow + hkv * 64;
+    const bool writer = (h % (hq / hkv)) == 0;
+    if (tid < 64) {
+      const int d = tid & 31;
+      const float x0 = __bfloat162float(qr[d]), x1 = __bfloat162float(qr[d + 32]);
+      qs[tid] = (tid < 32 ? x0 * rcs[d] - x1 * rsn[d] : x1 * rcs[d] + x0 * rsn[d]) * scale;
+    } else if (tid < 128) {
+      const int t = tid - 64, d = t & 31;
+      const float x0 = __bfloat162float(krow[d]), x1 = __bfloat162float(krow[d + 32]);
+      const bf16 kr16 = __float2bfloat16(t < 32 ? x0 * rcs[d] - x1 * rsn[d] : x1 * rcs[d] + x0 * rsn[d]);
+      knew[t] = __bfloat162float(kr16);   // the value later steps will read back from the cache
+      if (writer) const_cast<bf16*>(kbase)[(size_t)(nkeys - 1) * 64 + t] = kr16;
+    } else if (tid < 192) {
+      const int t = tid - 128;
+      const bf16 v16 = vrow[t];
+      vnew[t] = __bfloat162float(v16);
+      if (writer) const_cast<bf16*>(vbase)[(size_t)(nkeys - 1) * 64 + t] = v16;
+    }
+  } else {
+    if (tid < 64) qs[tid] = __bfloat162float(qr[tid]) * scale;
+  }
+  __syncthreads();
   const uint8_t* kv_ok = key_valid ? key_valid + (size_t)b * key_valid_ld : nullptr;
   float mx = -INFINITY;
-  for (int j = tid; j < nkeys; j += kSmallThreads) {
+  for (int j = tid; j < nk_c; j += kSmallThreads) {
     float s = -INFINITY;
     if (!kv_ok || kv_ok[j]) {
       s = 0.f;
@@ -306,6 +339,13 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
       }
     }
     sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  if (ROPE && tid == 0) {   // the newest key (always valid) comes from shared memory
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 64; ++e) s += knew[e] * qs[e];
+    sc[nkeys - 1] = s;
     mx = fmaxf(mx, s);
   }
   mx = warp_max(mx);
@@ -328,8 +368,8 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
 #pragma unroll
   for (int w = 0; w < kSmallWarps; ++w) sum += red[kSmallWarps + w];
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
-  const int chunk = (nkeys + kSmallWarps - 1) / kSmallWarps;
-  const int j0 = warp * chunk, j1 = min(nkeys, j0 + chunk);
+  const int chunk = (nk_c + kSmallWarps - 1) / kSmallWarps;
+  const int j0 = warp * chunk, j1 = min(nk_c, j0 + chunk);
   float a0 = 0.f, a1 = 0.f;
   const uint32_t* v32 = reinterpret_cast<const uint32_t*>(vbase) + lane;  // dims 2*lane, 2*lane+1 of every row (32 words per row)
   int j = j0;
@@ -361,7 +401,7 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
   part[warp * 64 + 2 * lane + 1] = a1;
   __syncthreads();
   if (tid < 64) {
-    float o = 0.f;
+    float o = ROPE ? sc[nkeys - 1] * vnew[tid] : 0.f;
 #pragma unroll
     for (int w = 0; w < kSmallWarps; ++w) o += part[w * 64 + tid];
     out[((size_t)b * lq + i) * ldo + h * 64 + tid] = __float2bfloat16(o * inv);
@@ -371,11 +411,13 @@ attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restr
 // Batched decode: one block per (query, kv head, batch) serving all q heads of the GQA group, so a key / value row is
 // read once for the 7 heads that share it (the per-head kernel above re-reads it 7 times: 69 MB per layer at batch 32).
 constexpr int kGrpThreads = 512, kGrpWarps = kGrpThreads / 32, kMaxGroup = 8;
+template <bool ROPE>   // see attn_small_kernel: fused RoPE + KV write for the decode step (lq == 1)
 __global__ void __launch_bounds__(kGrpThreads)
-attn_decode_group_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+attn_decode_group_kernel(const bf16* __restrict__ q, long long ldq, const bf16* kc, const bf16* vc,
                          const uint8_t* __restrict__ key_valid, int key_valid_ld, bf16* __restrict__ out, long long ldo, int lq, int past,
-                         int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev) {
+                         int lmax, int hq, int hkv, float scale, const int* __restrict__ past_dev, float log2_theta) {
   extern __shared__ float sm[];
+  __shared__ float rcs[32], rsn[32], knew[64], vnew[64];
   pdl_trigger();
   pdl_wait();
   if (past_dev) past = *past_dev;
@@ -387,16 +429,53 @@ attn_decode_group_kernel(const bf16* __restrict__ q, long long ldq, const bf16* 
   const int i = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nkeys = past + i + 1;
-  for (int t = tid; t < G * 64; t += kGrpThreads)
-    qs[t] = __bfloat162float(q[((size_t)b * lq + i) * ldq + (hk * G + t / 64) * 64 + (t & 63)]) * scale;
-  __syncthreads();
+  const int nk_c = ROPE ? nkeys - 1 : nkeys;   // keys taken from the cache
   const bf16* kbase = kc + ((size_t)b * hkv + hk) * lmax * 64;
   const bf16* vbase = vc + ((size_t)b * hkv + hk) * lmax * 64;
+  if (ROPE) {
+    if (tid < 32) {
+      const float inv_freq = exp2f(-(float)(2 * tid) / 64.0f * log2_theta);
+      sincosf((float)(past + i) * inv_freq, &rsn[tid], &rcs[tid]);
+    }
+    __syncthreads();
+    const bf16* row = q + ((size_t)b * lq + i) * ldq;
+    for (int t = tid; t < G * 64; t += kGrpThreads) {
+      const int hh = t / 64, e = t & 63, d = e & 31;
+      const bf16* qr = row + (hk * G + hh) * 64;
+      const float x0 = __bfloat162float(qr[d]), x1 = __bfloat162float(qr[d + 32]);
+      qs[t] = (e < 32 ? x0 * rcs[d] - x1 * rsn[d] : x1 * rcs[d] + x0 * rsn[d]) * scale;
+    }
+    if (tid < 64) {
+      const bf16* krow = row + (hq + hk) * 64;
+      const int d = tid & 31;
+      const float x0 = __bfloat162float(krow[d]), x1 = __bfloat162float(krow[d + 32]);
+      const bf16 kr16 = __float2bfloat16(tid < 32 ? x0 * rcs[d] - x1 * rsn[d] : x1 * rcs[d] + x0 * rsn[d]);
+      knew[tid] = __bfloat162float(kr16);
+      const_cast<bf16*>(kbase)[(size_t)(nkeys - 1) * 64 + tid] = kr16;
+    } else if (tid < 128) {
+      const int t = tid - 64;
+      const bf16 v16 = row[(hq + hkv + hk) * 64 + t];
+      vnew[t] = __bfloat162float(v16);
+      const_cast<bf16*>(vbase)[(size_t)(nkeys - 1) * 64 + t] = v16;
+    }
+  } else {
+    for (int t = tid; t < G * 64; t += kGrpThreads)
+      qs[t] = __bfloat162float(q[((size_t)b * lq + i) * ldq + (hk * G + t / 64) * 64 + (t & 63)]) * scale;
+  }
+  __syncthreads();
   const uint8_t* kv_ok = key_valid ? key_valid + (size_t)b * key_valid_ld : nullptr;
   float mx[kMaxGroup];
 #pragma unroll
   for (int h = 0; h < kMaxGroup; ++h) mx[h] = -INFINITY;
-  for (int j = tid; j < nkeys; j += kGrpThreads) {
+  if (ROPE && tid < G) {   // the newest key (always valid) comes from shared memory: thread h scores head h
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 64; ++e) s += knew[e] * qs[tid * 64 + e];
+    sc[(size_t)tid * lmax + nkeys - 1] = s;
+#pragma unroll
+    for (int h = 0; h < kMaxGroup; ++h) mx[h] = (h == tid) ? s : mx[h];
+  }
+  for (int j = tid; j < nk_c; j += kGrpThreads) {
     const bool ok = !kv_ok || kv_ok[j];
     float kf[64];
     const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)j * 64);
@@ -450,8 +529,8 @@ attn_decode_group_kernel(const bf16* __restrict__ q, long long ldq, const bf16* 
   }
   __syncthreads();
   // weighted V: each warp a contiguous chunk of keys, lanes own dims (2 lane, 2 lane + 1), all heads of the group at once
-  const int chunk = (nkeys + kGrpWarps - 1) / kGrpWarps;
-  const int j0 = warp * chunk, j1 = min(nkeys, j0 + chunk);
+  const int chunk = (nk_c + kGrpWarps - 1) / kGrpWarps;
+  const int j0 = warp * chunk, j1 = min(nk_c, j0 + chunk);
   const uint32_t* v32 = reinterpret_cast<const uint32_t*>(vbase) + lane;
   float a0[kMaxGroup], a1[kMaxGroup];
 #pragma unroll
@@ -495,7 +574,7 @@ attn_decode_group_kernel(const bf16* __restrict__ q, long long ldq, const bf16* 
   __syncthreads();
   for (int t = tid; t < G * 64; t += kGrpThreads) {
     const int h = t / 64, d = t & 63;
-    float o = 0.f, sm_ = 0.f;
+    float o = ROPE ? sc[(size_t)h * lmax + nkeys - 1] * vnew[d] : 0.f, sm_ = 0.f;
     for (int w = 0; w < kGrpWarps; ++w) { o += part[(w * kMaxGroup + h) * 64 + d]; sm_ += red[(kGrpWarps + w) * kMaxGroup + h]; }
     out[((size_t)b * lq + i) * ldo + (hk * G + h) * 64 + d] = __float2bfloat16(sm_ > 0.f ? o / sm_ : 0.f);
   }
@@ -549,36 +628,54 @@ int slb_attn_gqa2_try(const void* q, int64_t ldq, const void* kcache, const void
 
 extern "C" size_t slb_attn_gqa_fwd_workspace(int batch, int lq) { return slb_attn_gqa2_workspace(batch, lq); }
 
+// decode / query-append attention over the KV cache (lq <= 32, no lse); rope_log2_theta > 0 (lq == 1 only): fused RoPE + KV write
+static int launch_decode_attn(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid, int key_valid_ld,
+                              void* out, int batch, int lq, int past, const int32_t* past_dev, int lmax, int hq, int hkv, float rope_log2_theta,
+                              void* stream) {
+  const float scale = 0.125f;
+  const bool rope = rope_log2_theta > 0.f;
+  if (batch >= 4 && hq / hkv <= kMaxGroup) {
+    // batched decode / query append: one block per kv head serves its whole GQA group
+    const size_t smem = ((size_t)kMaxGroup * 64 + 2 * kGrpWarps * kMaxGroup + (size_t)kGrpWarps * kMaxGroup * 64 + (size_t)(hq / hkv) * lmax) * sizeof(float);
+    SLB_CHECK_ARG(smem <= 200 * 1024, "attn_gqa: lmax=%d too long for the grouped decode kernel", lmax);
+    static size_t smem_set[2] = {0, 0};
+    if (smem > smem_set[rope]) {
+      if (rope) SLB_CUDA(cudaFuncSetAttribute(attn_decode_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else SLB_CUDA(cudaFuncSetAttribute(attn_decode_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[rope] = smem;
+    }
+    auto kern = rope ? attn_decode_group_kernel<true> : attn_decode_group_kernel<false>;
+    SLB_CUDA(slb_launch_pdl(true, kern, dim3(lq, hkv, batch), dim3(kGrpThreads), smem, (cudaStream_t)stream, (const bf16*)q, (long long)ldq,
+                            (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq,
+                            hkv, scale, (const int*)past_dev, rope_log2_theta));
+    return SLB_OK;
+  }
+  dim3 grid(lq, hq, batch);
+  const size_t smem = (64 + 2 * kSmallWarps + kSmallWarps * 64 + (size_t)lmax) * sizeof(float);
+  SLB_CHECK_ARG(smem <= 46 * 1024, "attn_gqa: lmax=%d too long for the small-Lq kernel", lmax);
+  auto kern = rope ? attn_small_kernel<true> : attn_small_kernel<false>;
+  SLB_CUDA(slb_launch_pdl(true, kern, grid, dim3(kSmallThreads), smem, (cudaStream_t)stream, (const bf16*)q, (long long)ldq, (const bf16*)kcache,
+                          (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq, hkv, scale,
+                          (const int*)past_dev, rope_log2_theta));
+  return SLB_OK;
+}
+
+extern "C" int slb_attn_decode_rope(void* qkv, int64_t ldq, void* kcache, void* vcache, const uint8_t* key_valid, int key_valid_ld, void* out,
+                                    int batch, int past, const int32_t* past_dev, int lmax, int hq, int hkv, float theta, void* stream) {
+  SLB_CHECK_ARG(qkv && kcache && vcache && out && batch > 0 && past >= 0 && past + 1 <= lmax && hkv > 0 && hq % hkv == 0, "attn_decode_rope: bad shape");
+  SLB_CHECK_ARG((ldq % 8) == 0 && ldq >= (int64_t)(hq + 2 * hkv) * HD && theta > 1.f, "attn_decode_rope: qkv rows must hold q | k | v (ldq=%lld), theta > 1",
+                (long long)ldq);
+  return launch_decode_attn(qkv, ldq, kcache, vcache, key_valid, key_valid_ld, out, batch, 1, past, past_dev, lmax, hq, hkv, log2f(theta), stream);
+}
+
 extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, const uint8_t* key_valid,
                                 int key_valid_ld, void* out, float* lse, int batch, int lq, int past, const int32_t* past_dev, int lmax,
                                 int hq, int hkv, void* workspace, size_t workspace_bytes, void* stream) {
   SLB_CHECK_ARG(batch > 0 && lq > 0 && past >= 0 && past + lq <= lmax && hq % hkv == 0, "attn_gqa: bad shape");
   SLB_CHECK_ARG((ldq % 8) == 0, "attn_gqa: ldq must be a multiple of 8");
   SLB_CHECK_ARG(past + lq <= kMaxKvBlocks * BKV, "attn_gqa: at most %d keys", kMaxKvBlocks * BKV);
-  const float scale = 0.125f;
-  if (lq <= 32 && lse == nullptr && batch >= 4 && hq / hkv <= kMaxGroup) {
-    // batched decode / query append: one block per kv head serves its whole GQA group
-    const size_t smem = ((size_t)kMaxGroup * 64 + 2 * kGrpWarps * kMaxGroup + (size_t)kGrpWarps * kMaxGroup * 64 + (size_t)(hq / hkv) * lmax) * sizeof(float);
-    SLB_CHECK_ARG(smem <= 200 * 1024, "attn_gqa: lmax=%d too long for the grouped decode kernel", lmax);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      SLB_CUDA(cudaFuncSetAttribute(attn_decode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
-    SLB_CUDA(slb_launch_pdl(true, attn_decode_group_kernel, dim3(lq, hkv, batch), dim3(kGrpThreads), smem, (cudaStream_t)stream, (const bf16*)q,
-                            (long long)ldq, (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq,
-                            past, lmax, hq, hkv, scale, (const int*)past_dev));
-    return SLB_OK;
-  }
-  if (lq <= 32 && lse == nullptr) {
-    dim3 grid(lq, hq, batch);
-    const size_t smem = (64 + 2 * kSmallWarps + kSmallWarps * 64 + (size_t)lmax) * sizeof(float);
-    SLB_CHECK_ARG(smem <= 48 * 1024, "attn_gqa: lmax=%d too long for the small-Lq kernel", lmax);
-    SLB_CUDA(slb_launch_pdl(true, attn_small_kernel, grid, dim3(kSmallThreads), smem, (cudaStream_t)stream, (const bf16*)q, (long long)ldq,
-                            (const bf16*)kcache, (const bf16*)vcache, key_valid, key_valid_ld, (bf16*)out, (long long)hq * HD, lq, past, lmax, hq,
-                            hkv, scale, (const int*)past_dev));
-    return SLB_OK;
-  }
+  if (lq <= 32 && lse == nullptr)
+    return launch_decode_attn(q, ldq, kcache, vcache, key_valid, key_valid_ld, out, batch, lq, past, past_dev, lmax, hq, hkv, 0.f, stream);
   SLB_CHECK_ARG(past_dev == nullptr, "attn_gqa: a device-side position is only supported for chunks of <= 32 queries without lse");
   {  // prefill / teacher-forced pass: the persistent head-pair kernel (attention_gqa.cu)
     int rc2 = SLB_OK;
@@ -600,6 +697,6 @@ extern "C" int slb_attn_gqa_fwd(const void* q, int64_t ldq, const void* kcache, 
   p.kv_head_col_stride = 0; p.kv_batch_stride = hkv; p.kv_head_batch_stride = 1;
   p.key_valid = key_valid; p.key_valid_ld = key_valid_ld;
   p.out = (bf16*)out; p.ldo = (long long)hq * HD; p.lse = lse;
-  p.scale_log2 = scale * 1.4426950408889634f;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
   return launch_attn(tq, tk, tv, p, batch, (cudaStream_t)stream);
 }

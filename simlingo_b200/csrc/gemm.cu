@@ -965,7 +965,11 @@ extern "C" int slb_gemm_bf16(const slb_gemm_args* a, void* stream_) {
         const float c = cost(mt * ceil_div(a->N, 128), sms, 128 * 128, 0.9f);
         if (c < best) { best = c; bn = 128; }
       }
-      if (a->M >= 2048 && !(a->a_t && !a->b_t)) {   // the cluster kernel also takes the dgrad (b_t) and wgrad (a_t + b_t) operand forms
+      // the cluster kernel also takes the dgrad (b_t) and wgrad (a_t + b_t) operand forms.  In the wgrad form M is a weight dimension
+      // (a multiple of 256 for every matrix on the path), so there is no row padding to lose at 1024 <= M < 2048: the InternViT fc2
+      // wgrad [1024 x 4096], K = 16 400 becomes 64 cluster tiles on 74 clusters instead of 128 tiles of the 1-CTA MN-major kernel
+      const int min_m2 = (a->a_t && a->b_t && (a->M % 256) == 0) ? 1024 : 2048;
+      if (a->M >= min_m2 && !(a->a_t && !a->b_t)) {
         const float c256 = cost(mt2 * ceil_div(a->N, 256), sms / 2, 128 * 256, 1.1f);
         if (c256 <= best) { best = c256; bn = 2256; }
         if (kmajor && !a->swiglu && (a->N % 224) == 0) {

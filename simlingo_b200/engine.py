@@ -48,6 +48,8 @@ class Engine:
         # with a shape runs eagerly, the second captures, later ones replay.  SLB_INFER_GRAPHS=0 disables.
         import os
         self.graphs_enabled = os.environ.get("SLB_INFER_GRAPHS", "1") != "0"
+        # greedy decode as one persistent kernel (csrc/decode.cu) instead of ~125 launches per token; SLB_DECODE_MEGA=0 keeps the chain
+        self.decode_mega = os.environ.get("SLB_DECODE_MEGA", "1") != "0"
         self._graphs: Dict[tuple, dict] = {}
         self._seen: Dict[tuple, int] = {}
         self._pool = None
@@ -351,9 +353,13 @@ class Engine:
             else:
                 lib.rmsnorm(x, ly["ln1"], s.rms_eps, out=h)
                 lib.gemm(h, ly["qkv"], out=qkv, bias=ly["bqkv"])
-            lib.rope_kv_write(qkv, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, s.rope_theta, past_dev=past_dev)
-            lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, key_valid=key_valid, out=att,
-                         past_dev=past_dev)
+            if lq == 1:   # decode step: RoPE + KV write + attention in one launch
+                lib.attn_decode_rope(qkv, kc[i], vc[i], batch, past, s.llm_heads, s.llm_kv_heads, s.rope_theta, key_valid=key_valid, out=att,
+                                     past_dev=past_dev)
+            else:
+                lib.rope_kv_write(qkv, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, s.rope_theta, past_dev=past_dev)
+                lib.attn_gqa(qkv, s.qkv_dim, kc[i], vc[i], batch, lq, past, s.llm_heads, s.llm_kv_heads, key_valid=key_valid, out=att,
+                             past_dev=past_dev)
             if exact:
                 t = lib.gemm(att, ly["a_o"])
                 lib.gemm(att, ly["o_x"], out=x, residual=x, out_fp32=True, a2=t)
@@ -372,7 +378,7 @@ class Engine:
                 lib.gemm(act, ly["d"], out=x, residual=x, out_fp32=True)
             if collect is not None:
                 collect.append(x.clone())
-        self.launches += (12 if exact else 8) * s.llm_layers - (0 if not fuse_norm else 2 * s.llm_layers)
+        self.launches += (12 if exact else 8) * s.llm_layers - (0 if not fuse_norm else 2 * s.llm_layers) - (s.llm_layers if lq == 1 else 0)
         return x
 
     def final_norm(self, x: Tensor) -> Tensor:
@@ -404,14 +410,18 @@ class Engine:
         B, L, D = lang_embeds.shape
         nq = s.n_queries
         key = ("gen", B, L, max_new_tokens, eos_token_id)
+        mega = self.decode_mega and B <= 32 and max_new_tokens > 1
         rec = self._graphs.get(key)
+        if rec is not None and rec["mega"] != mega:
+            rec = None
         if rec is None:
             dev = self.dev
             lmax = L + max_new_tokens + nq
+            ngb = torch.zeros(B + 1, device=dev, dtype=torch.int64)   # per-sequence counts + the decode kernel's status word
             rec = dict(x=torch.empty_like(lang_embeds), cache=self.new_cache(B, lmax), pos=torch.zeros(1, device=dev, dtype=torch.int32),
                        nxt=torch.zeros(B, device=dev, dtype=torch.int64), step=torch.zeros(1, device=dev, dtype=torch.int64),
                        sampled=torch.zeros((B, max_new_tokens), device=dev, dtype=torch.int64), done=torch.zeros(B, device=dev, dtype=torch.bool),
-                       n_gen=torch.zeros(B, device=dev, dtype=torch.int64))
+                       n_gen=ngb[:B], n_gen_buf=ngb, status=ngb[B:], mega=mega)
             emb_w = self._w(LLM_PREFIX + "model.embed_tokens.weight")
             lm_cap = rec["cache"][0].shape[3]
 
@@ -429,7 +439,7 @@ class Engine:
 
             def prefill():
                 rec["pos"].fill_(L)
-                rec["step"].zero_(); rec["done"].zero_(); rec["n_gen"].zero_()
+                rec["step"].zero_(); rec["done"].zero_(); rec["n_gen_buf"].zero_()
                 rec["sampled"].fill_(eos_token_id if eos_token_id is not None else 0)
                 x = self.llm_chunk(rec["x"].reshape(B * L, D).clone(), B, L, 0, rec["cache"], None)
                 sample(self.final_norm(x.view(B, L, D)[:, -1].contiguous()))
@@ -442,6 +452,16 @@ class Engine:
                     sample(x, residual=True)
                 else:
                     sample(self.final_norm(x))
+
+            if mega:
+                rec["table"] = lib.decode_layer_table(self.llm_layers, dev)
+                rec["ws"] = lib.decode_workspace(B, s.llm_hidden, s.llm_mlp, s.llm_heads, s.llm_kv_heads, dev)
+
+                def decode():   # every remaining token in one persistent launch: token loop, position counter and EOS test on the device
+                    lib.decode_loop(rec["table"], s.llm_layers, B, s.llm_hidden, s.llm_mlp, s.llm_heads, s.llm_kv_heads, emb_w,
+                                    self._w(LLM_PREFIX + "model.norm.weight"), self._w(LLM_PREFIX + "lm_head.weight"), rec["cache"][0],
+                                    rec["cache"][1], rec["pos"], rec["nxt"], rec["sampled"], rec["step"], rec["done"], rec["n_gen"],
+                                    rec["status"], rec["ws"], max_new_tokens - 1, eos_token_id, s.rope_theta, s.rms_eps)
 
             def queries():
                 e = lib.gather_rows(emb_w, rec["nxt"])
@@ -458,15 +478,18 @@ class Engine:
             self._graphs[key] = rec
         rec["x"].copy_(lang_embeds)
         self._replay(rec["g_pre"], rec["n_pre"])
-        steps = 1
-        for i in range(1, max_new_tokens):
-            if eos_token_id is not None and bool(rec["done"].all()):  # host sync, as llm.py:245
-                break
+        if rec["mega"]:
             self._replay(rec["g_dec"], rec["n_dec"])
-            steps += 1
+        else:
+            for i in range(1, max_new_tokens):
+                if eos_token_id is not None and bool(rec["done"].all()):  # host sync, as llm.py:245
+                    break
+                self._replay(rec["g_dec"], rec["n_dec"])
         self._replay(rec["g_q"], rec["n_q"])
         route, speed = rec["out"]
-        n_gen_cpu = rec["n_gen"].tolist()
+        n_gen_cpu = rec["n_gen_buf"].tolist()
+        if n_gen_cpu[B] != 0:
+            raise RuntimeError("simlingo_b200: the persistent decode kernel reported a grid-barrier timeout (slb_decode_loop status != 0)")
         toks = [rec["sampled"][b, : max(n_gen_cpu[b], 1)].clone() for b in range(B)]
         return speed.clone(), route.clone(), toks
 

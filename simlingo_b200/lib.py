@@ -35,6 +35,22 @@ class GemmArgs(C.Structure):
     ]
 
 
+class DecodeArgs(C.Structure):
+    """slb_decode_args (include/simlingo_b200.h)"""
+    _fields_ = [
+        ("layers", C.c_void_p),
+        ("n_layers", C.c_int32), ("batch", C.c_int32), ("hidden", C.c_int32), ("mlp", C.c_int32), ("vocab", C.c_int32),
+        ("hq", C.c_int32), ("hkv", C.c_int32), ("lmax", C.c_int32), ("n_steps", C.c_int32), ("max_new", C.c_int32),
+        ("emb_rows", C.c_int64), ("eos", C.c_int64), ("ld_sampled", C.c_int64),
+        ("emb", C.c_void_p), ("norm_w", C.c_void_p), ("lm_head", C.c_void_p),
+        ("kcache", C.c_void_p), ("vcache", C.c_void_p),
+        ("pos", C.c_void_p), ("nxt", C.c_void_p), ("sampled", C.c_void_p), ("step", C.c_void_p), ("done", C.c_void_p), ("n_gen", C.c_void_p),
+        ("rope_theta", C.c_float), ("rms_eps", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("status", C.c_void_p),
+    ]
+
+
 class HeadsWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("r0w", "r0b", "r2w", "r2b", "r4w", "s0w", "s0b", "s2w")]
 
@@ -239,6 +255,22 @@ def attn_gqa(q, ldq, kcache, vcache, batch, lq, past, hq=14, hkv=2, key_valid=No
     return out
 
 
+def attn_decode_rope(qkv, kcache, vcache, batch, past, hq=14, hkv=2, theta=1.0e6, key_valid=None, out=None, past_dev=None):
+    """one decode step in one launch: RoPE on q / the new key, KV-cache write at ``past`` and attention over positions 0..past"""
+    _bf16(qkv, kcache, vcache)
+    lmax = kcache.shape[2]
+    assert qkv.is_contiguous() and qkv.shape == (batch, (hq + 2 * hkv) * 64)
+    assert kcache.shape == (batch, hkv, lmax, 64) and kcache.is_contiguous() and vcache.is_contiguous()
+    out = torch.empty((batch, hq * 64), device=qkv.device, dtype=torch.bfloat16) if out is None else out
+    kv_ld = 0
+    if key_valid is not None:
+        assert key_valid.dtype == torch.uint8 and key_valid.dim() == 2 and key_valid.stride(1) == 1
+        kv_ld = key_valid.stride(0)
+    _check(load().slb_attn_decode_rope(_p(qkv), C.c_int64(qkv.stride(0)), _p(kcache), _p(vcache), _p(key_valid), kv_ld, _p(out), batch, past,
+                                       _p(past_dev), lmax, hq, hkv, C.c_float(theta), _stream()), "attn_decode_rope")
+    return out
+
+
 def rope_kv_write(qkv, kcache, vcache, batch, lq, past, hq=14, hkv=2, theta=1.0e6, past_dev=None):
     _bf16(qkv, kcache, vcache)
     assert qkv.is_contiguous() and qkv.shape == (batch * lq, (hq + 2 * hkv) * 64)
@@ -298,6 +330,56 @@ def argmax(logits, out_idx=None, out_margin=None):
     _check(load().slb_argmax_f32(_p(logits), C.c_int64(logits.stride(0)), rows, cols, _p(out_idx), _p(out_margin), _stream()),
            "argmax_f32")
     return out_idx
+
+
+def decode_workspace(batch: int, hidden: int, mlp: int, hq: int, hkv: int, device) -> torch.Tensor:
+    """scratch of the persistent decode kernel (residual stream, q|k|v, attention partials, arg-max partials, barrier counters)"""
+    f = load().slb_decode_workspace_bytes
+    f.restype = C.c_size_t
+    n = int(f(batch, hidden, mlp, hq, hkv))
+    if n <= 0:
+        raise RuntimeError("simlingo_b200: decode_workspace_bytes rejected the shape")
+    return torch.zeros((n + 256,), device=device, dtype=torch.uint8)
+
+
+def decode_layer_table(layers, device) -> torch.Tensor:
+    """device array of slb_decode_layer (7 pointers per layer) from the engine's folded per-layer weights"""
+    rows = []
+    for ly in layers:
+        ts = [ly[k] for k in ("qkv", "bqkv", "o", "gu", "d", "ln1", "ln2")]
+        for t in ts:
+            assert t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()
+        rows.append([t.data_ptr() for t in ts])
+    return torch.tensor(rows, dtype=torch.int64).to(device)
+
+
+def decode_loop(table, n_layers, batch, hidden, mlp, hq, hkv, emb, norm_w, lm_head, kcache, vcache, pos, nxt, sampled, step, done, n_gen,
+                status, workspace, n_steps, eos, theta, eps):
+    """greedy decode of up to ``n_steps`` tokens in ONE persistent launch (slb_decode_loop; llm.py:217-248 per token).  All state
+    tensors live on the device and are updated in place; stops early once every ``done`` flag is set (``eos`` not None)."""
+    _bf16(emb, norm_w, lm_head, kcache, vcache)
+    assert table.dtype == torch.int64 and table.is_cuda and table.shape == (n_layers, 7) and table.is_contiguous()
+    assert kcache.dim() == 5 and kcache.shape[:3] == (n_layers, batch, hkv) and kcache.shape[4] == 64 and kcache.is_contiguous()
+    assert vcache.shape == kcache.shape and vcache.is_contiguous()
+    assert emb.is_contiguous() and lm_head.is_contiguous() and emb.shape[1] == hidden and lm_head.shape[1] == hidden
+    assert pos.dtype == torch.int32 and step.dtype == torch.int64 and nxt.dtype == torch.int64 and nxt.numel() == batch
+    assert sampled.dtype == torch.int64 and sampled.dim() == 2 and sampled.shape[0] == batch and sampled.stride(1) == 1
+    assert done.dtype in (torch.bool, torch.uint8) and done.numel() == batch and n_gen.dtype == torch.int64 and n_gen.numel() == batch
+    assert status.dtype in (torch.int32, torch.int64) and status.is_cuda and workspace.dtype == torch.uint8
+    ws_ptr = (workspace.data_ptr() + 255) // 256 * 256
+    a = DecodeArgs()
+    a.layers = table.data_ptr()
+    a.n_layers, a.batch, a.hidden, a.mlp, a.vocab, a.hq, a.hkv = n_layers, batch, hidden, mlp, lm_head.shape[0], hq, hkv
+    a.lmax, a.n_steps, a.max_new = kcache.shape[3], n_steps, sampled.shape[1]
+    a.emb_rows, a.eos, a.ld_sampled = emb.shape[0], (-1 if eos is None else int(eos)), sampled.stride(0)
+    a.emb, a.norm_w, a.lm_head = emb.data_ptr(), norm_w.data_ptr(), lm_head.data_ptr()
+    a.kcache, a.vcache = kcache.data_ptr(), vcache.data_ptr()
+    a.pos, a.nxt, a.sampled, a.step, a.done, a.n_gen = (pos.data_ptr(), nxt.data_ptr(), sampled.data_ptr(), step.data_ptr(),
+                                                          done.data_ptr(), n_gen.data_ptr())
+    a.rope_theta, a.rms_eps = theta, eps
+    a.workspace, a.workspace_bytes = ws_ptr, workspace.numel() - (ws_ptr - workspace.data_ptr())
+    a.status = status.data_ptr()
+    _check(load().slb_decode_loop(C.byref(a), _stream()), "decode_loop")
 
 
 def driving_heads(feats, ld_batch, hw: HeadsWeights, batch, route=None, speed=None, ws=None):

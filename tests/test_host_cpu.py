@@ -47,6 +47,10 @@ def test_invalid_arguments_return_error_codes_not_crashes():
     assert L.slb_equal_spacing_route(ptr, 0, 20, 20, ptr, None) != 0 and L.slb_equal_spacing_route(ptr, 1, 64, 20, ptr, None) != 0
     assert L.slb_attn_delta(ctypes.c_void_p(ptr.value + 2), ptr, ptr, 1, 1, 1, None) != 0          # operands must be 16-byte aligned
     assert b"16-byte" in L.slb_last_error()
+    # persistent decode kernel: argument validation precedes any CUDA call
+    assert L.slb_decode_loop(None, None) != 0
+    d = lib.DecodeArgs(n_layers=2, batch=33)
+    assert L.slb_decode_loop(ctypes.byref(d), None) != 0 and b"decode_loop" in L.slb_last_error()
 
 
 def test_state_dict_schema_matches_dropin_module_tree():
