@@ -48,8 +48,10 @@ class Engine:
         # with a shape runs eagerly, the second captures, later ones replay.  SLB_INFER_GRAPHS=0 disables.
         import os
         self.graphs_enabled = os.environ.get("SLB_INFER_GRAPHS", "1") != "0"
-        # greedy decode as one persistent kernel (csrc/decode.cu) instead of ~125 launches per token; SLB_DECODE_MEGA=0 keeps the chain
-        self.decode_mega = os.environ.get("SLB_DECODE_MEGA", "1") != "0"
+        # greedy decode as ONE persistent kernel (csrc/decode.cu: token loop, grid barriers and EOS test on the device) instead of the
+        # per-token chain of ~100 launches.  Opt-in (SLB_DECODE_MEGA=1): correct (tests/test_decode_gpu.py) but measured 1.14 ms per
+        # token at batch 1 against 0.93 ms for the PDL-chained kernels and level with them at batch 32 (profiles/r02_trace_decode_v7.log)
+        self.decode_mega = os.environ.get("SLB_DECODE_MEGA", "0") == "1"
         self._graphs: Dict[tuple, dict] = {}
         self._seen: Dict[tuple, int] = {}
         self._pool = None

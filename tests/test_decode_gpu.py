@@ -1,6 +1,6 @@
 """Decode path on a B200: (1) the fused RoPE + KV-write + attention launch of the per-kernel chain against the two launches it
-replaces, (2) the persistent decode kernel (``slb_decode_loop``: token loop, grid barriers, device-side EOS) against the per-kernel
-chain on the same engine - tokens identical, caches / waypoints within bf16 noise - for batch 1 (key segments over many CTAs),
+replaces, (2) the opt-in persistent decode kernel (``slb_decode_loop``: token loop, grid barriers, device-side EOS) against the
+per-kernel chain on the same engine - tokens identical, caches / waypoints within bf16 noise - for batch 1 (key segments over many CTAs),
 a ragged batch (5) and the largest batch (32, two 16-row MMA tiles).  Both paths are pinned against the fp32 oracle elsewhere
 (test_model_gpu, test_dropin_gpu, test_fullscale_gpu); this file pins them against each other at sizes the oracle would not finish."""
 import pytest
@@ -107,10 +107,13 @@ def test_persistent_decode_kernel_against_oracle(setup):
     fr, ph = synth_frames(spec, 1, 77), synth_placeholders(spec, 1, 77)
     with torch.no_grad():
         sp_ref, rt_ref, tok_ref = O.driving_forward(sd, spec, fr, ids, valid, ph, max_new_tokens=8, eos_token_id=eos)
-    assert eng.decode_mega
-    for _ in range(2):
-        sp, rt, tok = eng.driving_forward(fr.to("cuda", torch.bfloat16), ids.cuda(), valid.cuda(), ph, max_new_tokens=8, eos_token_id=eos,
-                                          ids_cpu=ids)
-    assert eng._graphs[("gen", 1, ids.shape[1], 8, eos)]["mega"]
+    old, eng.decode_mega = eng.decode_mega, True
+    try:
+        for _ in range(2):
+            sp, rt, tok = eng.driving_forward(fr.to("cuda", torch.bfloat16), ids.cuda(), valid.cuda(), ph, max_new_tokens=8, eos_token_id=eos,
+                                              ids_cpu=ids)
+        assert eng._graphs[("gen", 1, ids.shape[1], 8, eos)]["mega"]
+    finally:
+        eng.decode_mega = old
     assert [t.cpu().tolist() for t in tok] == [t.tolist() for t in tok_ref]
     assert relerr(sp, sp_ref) < 2e-2 and relerr(rt, rt_ref) < 2e-2

@@ -119,11 +119,11 @@ def test_cuda_graph_generation_equals_eager_launches(setup):
     """From the second call with a shape the engine replays CUDA graphs (ViT on few tiles, prefill, one decode-step graph
     per token with the position counter on the device, query append): tokens identical and waypoints equal to the
     eagerly launched kernels, for the agent case (batch 1, stops at EOS) and the language case (batch 3, EOS suppressed).
-    This pins the per-kernel chain (bit-equal to its eager launches); the persistent decode kernel that replaces the per-token
-    graphs by default is compared with the chain in test_decode_gpu.py."""
+    This pins the per-kernel chain (bit-equal to its eager launches); the opt-in persistent decode kernel is compared with the
+    chain in test_decode_gpu.py."""
     spec, sd, eng = setup
     eos = spec.eos_id
-    eng.decode_mega = False
+    mega_default, eng.decode_mega = eng.decode_mega, False
     for B, G, use_eos, max_new in [(1, 5, True, 9), (3, 6, False, 6)]:
         ids = synth_prompt_ids(spec, B, seed=31)
         ids[:, -1] = (eos - G * LMHEAD_SHIFT) % spec.vocab
@@ -141,4 +141,4 @@ def test_cuda_graph_generation_equals_eager_launches(setup):
         assert [t.cpu().tolist() for t in tok] == [t.cpu().tolist() for t in tok0]
         assert len(tok[0]) == (G if use_eos else max_new)
         assert torch.equal(sp, sp0) and torch.equal(rt, rt0)
-    eng.decode_mega = True
+    eng.decode_mega = mega_default

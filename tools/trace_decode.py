@@ -15,7 +15,8 @@ model = Bn.build_model(spec, dev)
 eng = model._engine()
 L = lib.load()
 grid = L.slb_num_sms()
-buf = torch.zeros(8192 + grid * NB * 2 + 16, dtype=torch.int64, device=dev)
+FS = 32   # kFineStamps
+buf = torch.zeros(8192 + grid * NB * 2 + 16 + grid * FS, dtype=torch.int64, device=dev)
 L.slb_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
 PH = ["1 norm+qkv", "2 attention", "3 o-proj", "4 norm+gate|up", "5 down"]
 
@@ -50,6 +51,24 @@ def analyse(tag, n_layers):
     for r in rows:
         print(f"    {r[0]:20s} {r[1]:12.2f} {r[2]:10.2f} {r[3]:9.2f} {r[4]:10.2f}")
     print(f"    critical path of the second token: {tot:.1f} us")
+    # stamps inside the phases of (second token, second layer): the CTA that was slowest in each phase
+    f = buf[8192 + grid * NB * 2 + 16:][:grid * FS].view(grid, FS).cpu().double()
+    us = lambda a, b: (b - a) / ghz * 1e-3
+
+    def show(name, ids, labels, cta):
+        r = f[cta]
+        parts = [f"{lb} {us(r[i0], r[i1]):.2f}" for (i0, i1), lb in zip(ids, labels) if r[i0] > 0 and r[i1] > 0]
+        print(f"    {name} (CTA {cta}): " + ", ".join(parts))
+    att = (f[:, 8] - f[:, 0]).clamp_min(0) * (f[:, 8] > 0)
+    show("attention", [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8)],
+         ["q load + sincos", "rotate + K/V wait", "scores", "softmax", "PV", "partial store", "counter", "merge"], int(att.argmax()))
+    print(f"      merged by this CTA: {int(f[int(att.argmax()), 9])}; CTAs with an item: {int((f[:, 8] > 0).sum())}")
+    g4 = (f[:, 19] if (f[:, 19] > 0).any() else f[:, 15]) - f[:, 10]
+    c4 = int(((f[:, 19].clamp_min(0) + f[:, 15]) - f[:, 10]).argmax())
+    show("norm + gate|up", [(10, 11), (11, 12), (12, 13), (13, 14), (14, 15), (15, 16), (16, 17), (17, 18), (18, 19)],
+         ["norm", "weights wait r0", "MMA r0", "stage next", "reduce r0", "weights wait r1", "MMA r1", "stage next", "reduce r1"], c4)
+    c1 = int((f[:, 25] - f[:, 20]).argmax())
+    show("norm + qkv", [(20, 21), (21, 22), (22, 23), (23, 24), (24, 25)], ["norm", "weights wait", "MMA", "stage next", "reduce"], c1)
 
 
 def timed(fn, n=3):
@@ -69,7 +88,7 @@ ex1b = Bn.make_example(Bn.host_agent_batch(spec, 1, 99, 1), dev)
 hb = Bn.host_agent_batch(spec, 32, 500, None)
 ids, fr, vd = hb["ids"].to(dev), hb["frames"].to(dev), hb["valid"].to(dev)
 lang = lambda: eng.driving_forward(fr, ids, vd, hb["placeholders"], max_new_tokens=16, eos_token_id=None, ids_cpu=hb["ids"])
-for mega in (False, True):
+for mega in ((False, True) if os.environ.get("TRACE_CHAIN", "0") == "1" else (True,)):
     for flags in (flags_list if mega else [0]):
         os.environ["SLB_DECODE_FLAGS"] = str(flags)
         eng.decode_mega = mega
