@@ -234,6 +234,11 @@ int slb_dropout_add(const void* x, void* y, int64_t n, float p, uint64_t seed, c
 int slb_dropout_multi(const void* x, void* const* ys, const uint64_t* seeds, int n_out, int64_t n, float p,
                       const uint64_t* seed_dev, void* stream);
 int slb_lora_pack(const int64_t* table_dev, int n_entries, int rank, float scale, void* stream);
+/* slb_lora_wgrad_grouped: the adapters' parameter gradients of one group of linears in ONE launch (PEFT lora.Linear backward:
+ * dB = s dy^T t, dA = dt^T dropout(x); llm.py:106-118 wraps q/k/v/o/gate/up/down):  out [mo, no] (+)= alpha * P^T Q  with
+ * P bf16 [rows, mo] (row stride ldp), Q bf16 [rows, no] (ldq), out bf16 (ldo), mo / no multiples of 32, <= 16 problems (HOST array). */
+typedef struct { const void* P; const void* Q; void* out; int64_t ldp, ldq, ldo; int32_t mo, no; float alpha; int32_t accumulate; } slb_wgrad_problem;
+int slb_lora_wgrad_grouped(const slb_wgrad_problem* probs, int n, int rows, void* stream);
 int slb_lora_dx(const void* in, int64_t ld_in, void* out, int64_t ld_out, const void* const* A, const uint64_t* seeds,
                 int n_adapters, int M, int K, int rank, float p, const uint64_t* seed_dev, void* stream);
 int slb_silu_mul_cat(const void* gate_up, void* out, int rows, int inter, void* stream);

@@ -250,6 +250,113 @@ __global__ void silu_mul_cat_bwd_kernel(const bf16* __restrict__ gu, const bf16*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Grouped parameter-gradient products of the adapters:  out_j [mo_j x no_j] (+)= alpha_j P_j^T Q_j  over the `rows` token rows
+// (dB_j = s dy_j^T t_j : [out_f x r],  dA_j = dt_j^T dropout_j(x) : [r x in_f]).  As 14 single-tile tcgen05 GEMMs per layer
+// (K = batch * length = 4728 deep, 1-7 CTAs each, ~25 us each) they cost 9 ms of a 75 ms training step
+// (profiles/r02_kernel_breakdown_train_v3.log); here every 32 x 32 output tile of every problem of a group is one CTA of one
+// launch: 8 warps = 2 row halves x 4 k16 slices of a 64-row chunk, operands [k][m] / [k][n] staged by a 4-stage cp.async ring,
+// both fragments by ldmatrix.trans, mma.sync.m16n8k16, the four k-slice partial tiles summed through shared memory.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxWgProbs = 16;
+constexpr int WG_THREADS = 256, WG_KC = 64, WG_STAGES = 4, WG_ROWB = 80;   // 80 B per staged row (32 bf16 + 16 B): conflict-free ldmatrix
+struct WgProb { const bf16* P; const bf16* Q; bf16* out; long long ldp, ldq, ldo; int tiles_n, tile0; float alpha; int acc; };
+struct WgArgs { WgProb pr[kMaxWgProbs]; int n, rows; };
+
+__device__ __forceinline__ void wg_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void wg_ldsm_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ void wg_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(WG_THREADS)
+lora_wgrad_kernel(const __grid_constant__ WgArgs a) {
+  extern __shared__ __align__(16) uint8_t wsm[];   // [WG_STAGES][2 operands][WG_KC rows][WG_ROWB]; afterwards the partial tiles
+  int j = 0;
+  while (j + 1 < a.n && (int)blockIdx.x >= a.pr[j + 1].tile0) ++j;
+  const bf16* Pg; const bf16* Qg; bf16* og; long long ldp, ldq, ldo; float alpha; int acc_out;
+  {
+    const WgProb& pb = a.pr[j];
+    const int tl = blockIdx.x - pb.tile0, tm = tl / pb.tiles_n, tn = tl - tm * pb.tiles_n;
+    Pg = pb.P + tm * 32; Qg = pb.Q + tn * 32; ldp = pb.ldp; ldq = pb.ldq; ldo = pb.ldo;
+    og = pb.out + (size_t)tm * 32 * ldo + tn * 32; alpha = pb.alpha; acc_out = pb.acc;
+  }
+  const int rows = a.rows, nchunks = (rows + WG_KC - 1) / WG_KC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto load_chunk = [&](int ch, int stage) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int id = tid + i * WG_THREADS, op = id >> 8, r = (id & 255) >> 2, c = id & 3;
+      const int row = ch * WG_KC + r;
+      uint8_t* dst = wsm + (size_t)((stage * 2 + op) * WG_KC + r) * WG_ROWB + c * 16;
+      if (row < rows) wg_cp_async16(dst, (op ? Qg + (size_t)row * ldq : Pg + (size_t)row * ldp) + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);   // tail rows of the last chunk
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < WG_STAGES - 1; ++s) {
+    if (s < nchunks) load_chunk(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int ks = warp & 3, mt = warp >> 2;
+  float acc[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+  const int mat = lane >> 3, r8 = lane & 7;
+  const int a_off = (ks * 16 + (mat >> 1) * 8 + r8) * WG_ROWB + (mt * 16 + (mat & 1) * 8) * 2;   // A = P^T: (k0|k0+8, m0|m0+8) blocks
+  const int b_off = (ks * 16 + (mat & 1) * 8 + r8) * WG_ROWB + ((mat >> 1) * 8) * 2;             // B = Q: (k0|k0+8, n0|n0+8) blocks
+  for (int ch = 0; ch < nchunks; ++ch) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(WG_STAGES - 2) : "memory");
+    __syncthreads();
+    if (ch + WG_STAGES - 1 < nchunks) load_chunk(ch + WG_STAGES - 1, (ch + WG_STAGES - 1) % WG_STAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const uint8_t* Ps = wsm + (size_t)((ch % WG_STAGES) * 2) * WG_KC * WG_ROWB;
+    const uint8_t* Qs = Ps + (size_t)WG_KC * WG_ROWB;
+    uint32_t a0, a1, a2, a3;
+    wg_ldsm_x4_trans(a0, a1, a2, a3, Ps + a_off);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      wg_ldsm_x4_trans(b0, b1, b2, b3, Qs + b_off + np * 32);
+      wg_mma(acc[2 * np], a0, a1, a2, a3, b0, b1);
+      wg_mma(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(wsm);   // [8 warps][16 rows][33]
+  {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      red[(warp * 16 + g) * 33 + nt * 8 + 2 * q] = acc[nt][0];
+      red[(warp * 16 + g) * 33 + nt * 8 + 2 * q + 1] = acc[nt][1];
+      red[(warp * 16 + 8 + g) * 33 + nt * 8 + 2 * q] = acc[nt][2];
+      red[(warp * 16 + 8 + g) * 33 + nt * 8 + 2 * q + 1] = acc[nt][3];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * WG_THREADS, m = idx >> 5, n = idx & 31;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v += red[(((m >> 4) * 4 + k) * 16 + (m & 15)) * 33 + n];
+    v *= alpha;
+    bf16* o = og + (size_t)m * ldo + n;
+    if (acc_out) v += __bfloat162float(*o);
+    *o = __float2bfloat16(v);
+  }
+}
+
 }  // namespace
 
 #define ST(s) ((cudaStream_t)(s))
@@ -312,6 +419,29 @@ extern "C" int slb_silu_mul_cat_bwd(const void* gate_up, const void* dout, void*
   SLB_CHECK_ARG(gate_up && dout && dgate_up && rows > 0 && inter > 0 && (inter % 8) == 0, "silu_mul_cat_bwd: %d x %d", rows, inter);
   silu_mul_cat_bwd_kernel<<<grid_for((size_t)rows * (inter / 8), 256), 256, 0, ST(stream)>>>((const bf16*)gate_up, (const bf16*)dout, (bf16*)dgate_up,
                                                                                              (size_t)rows, inter / 8);
+  SLB_LAUNCH_CHECK();
+  return SLB_OK;
+}
+
+extern "C" int slb_lora_wgrad_grouped(const slb_wgrad_problem* probs, int n, int rows, void* stream) {
+  SLB_CHECK_ARG(probs && n >= 1 && n <= kMaxWgProbs && rows > 0, "lora_wgrad_grouped: 1..%d problems, rows > 0 (n=%d rows=%d)", kMaxWgProbs, n, rows);
+  WgArgs a;
+  a.n = n; a.rows = rows;
+  int tiles = 0;
+  for (int j = 0; j < n; ++j) {
+    const slb_wgrad_problem& q = probs[j];
+    SLB_CHECK_ARG(q.P && q.Q && q.out && q.mo > 0 && q.no > 0 && (q.mo % 32) == 0 && (q.no % 32) == 0,
+                  "lora_wgrad_grouped: problem %d: output %d x %d must be whole 32 x 32 tiles", j, q.mo, q.no);
+    SLB_CHECK_ARG((q.ldp % 8) == 0 && (q.ldq % 8) == 0 && q.ldp >= q.mo && q.ldq >= q.no && q.ldo >= q.no &&
+                  (((uintptr_t)q.P | (uintptr_t)q.Q) & 15) == 0,
+                  "lora_wgrad_grouped: problem %d: operand rows must be 16-byte aligned (ldp=%lld ldq=%lld)", j, (long long)q.ldp, (long long)q.ldq);
+    WgProb& w = a.pr[j];
+    w.P = (const bf16*)q.P; w.Q = (const bf16*)q.Q; w.out = (bf16*)q.out; w.ldp = q.ldp; w.ldq = q.ldq; w.ldo = q.ldo;
+    w.tiles_n = q.no / 32; w.tile0 = tiles; w.alpha = q.alpha; w.acc = q.accumulate;
+    tiles += (q.mo / 32) * (q.no / 32);
+  }
+  const size_t smem = (size_t)WG_STAGES * 2 * WG_KC * WG_ROWB;   // 40 KB (>= the 16.5 KB of partial tiles)
+  lora_wgrad_kernel<<<tiles, WG_THREADS, smem, ST(stream)>>>(a);
   SLB_LAUNCH_CHECK();
   return SLB_OK;
 }

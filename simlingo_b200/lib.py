@@ -51,6 +51,12 @@ class DecodeArgs(C.Structure):
     ]
 
 
+class WgradProblem(C.Structure):
+    """slb_wgrad_problem (include/simlingo_b200.h)"""
+    _fields_ = [("P", C.c_void_p), ("Q", C.c_void_p), ("out", C.c_void_p), ("ldp", C.c_int64), ("ldq", C.c_int64), ("ldo", C.c_int64),
+                ("mo", C.c_int32), ("no", C.c_int32), ("alpha", C.c_float), ("accumulate", C.c_int32)]
+
+
 class HeadsWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("r0w", "r0b", "r2w", "r2b", "r4w", "s0w", "s0b", "s2w")]
 
@@ -505,6 +511,22 @@ def lora_dx(cat, K, a_list, p=0.0, seeds=None, seed_dev=None, out=None):
     _check(load().slb_lora_dx(_p(cat), C.c_int64(cat.stride(0)), _p(out), C.c_int64(out.stride(0)), ap, sd, n, M, K, r, C.c_float(p),
                               _p(seed_dev), _stream()), "lora_dx")
     return out
+
+
+def lora_wgrad_grouped(problems, rows: int) -> None:
+    """One launch for the parameter gradients of a group of adapters: for every (P [rows, mo], Q [rows, no], out [mo, no], alpha,
+    accumulate) in ``problems`` (at most 16):  out (+)= alpha * P^T Q.  P / Q may be column slices of wider matrices."""
+    n = len(problems)
+    arr = (WgradProblem * n)()
+    for k, (P, Q, out, alpha, acc) in enumerate(problems):
+        _bf16(P, Q, out)
+        assert P.dim() == 2 and Q.dim() == 2 and out.dim() == 2 and P.stride(1) == 1 and Q.stride(1) == 1 and out.stride(1) == 1
+        assert P.shape[0] == rows and Q.shape[0] == rows and out.shape == (P.shape[1], Q.shape[1]), (P.shape, Q.shape, out.shape, rows)
+        a = arr[k]
+        a.P, a.Q, a.out = P.data_ptr(), Q.data_ptr(), out.data_ptr()
+        a.ldp, a.ldq, a.ldo = P.stride(0), Q.stride(0), out.stride(0)
+        a.mo, a.no, a.alpha, a.accumulate = P.shape[1], Q.shape[1], float(alpha), int(bool(acc))
+    _check(load().slb_lora_wgrad_grouped(arr, n, rows, _stream()), "lora_wgrad_grouped")
 
 
 def silu_mul_cat(gu, out=None):

@@ -845,11 +845,24 @@ class TrainEngine:
         a_list = [self.w(pre + m + ".lora_A.default.weight") for m in mods]
         rows = [a.shape[0] for a in (self.w(pre + m + ".lora_B.default.weight") for m in mods)]
 
-        o = 0
-        for j, m in enumerate(mods):   # parameter gradients: off the critical path (side streams, joined at the end of the layer)
-            self._defer(lambda j=j, m=m, o=o: self._wgrad(dy[:, o:o + rows[j]], t[:, r * j:r * (j + 1)], pre + m + ".lora_B.default.weight", alpha=sc), dy, t)
-            self._defer(lambda j=j, m=m: self._wgrad(cat[:, K + r * j:K + r * (j + 1)], xds[j], pre + m + ".lora_A.default.weight"), cat, xds[j])
-            o += rows[j]
+        # parameter gradients: off the critical path (a side stream, joined at the end of the layer).  All 2 n products of the group in
+        # one launch (slb_lora_wgrad_grouped); as single-tile tcgen05 GEMMs they were 14 launches of ~25 us per layer = 9 ms per step
+        grouped = r % 32 == 0 and all(x % 32 == 0 for x in rows) and K % 32 == 0 and 2 * n <= 16
+        if grouped:
+            probs, o = [], 0
+            for j, m in enumerate(mods):
+                gB, accB = self.store.target(pre + m + ".lora_B.default.weight")
+                gA, accA = self.store.target(pre + m + ".lora_A.default.weight")
+                probs.append((dy[:, o:o + rows[j]], t[:, r * j:r * (j + 1)], gB.view(gB.shape[0], -1), sc, accB))
+                probs.append((cat[:, K + r * j:K + r * (j + 1)], xds[j], gA.view(gA.shape[0], -1), 1.0, accA))
+                o += rows[j]
+            self._defer(lambda: lib.lora_wgrad_grouped(probs, dy.shape[0]), dy, t, cat, *xds)
+        else:
+            o = 0
+            for j, m in enumerate(mods):
+                self._defer(lambda j=j, m=m, o=o: self._wgrad(dy[:, o:o + rows[j]], t[:, r * j:r * (j + 1)], pre + m + ".lora_B.default.weight", alpha=sc), dy, t)
+                self._defer(lambda j=j, m=m: self._wgrad(cat[:, K + r * j:K + r * (j + 1)], xds[j], pre + m + ".lora_A.default.weight"), cat, xds[j])
+                o += rows[j]
         use = seeds[0] is not None
         return lib.lora_dx(cat, K, a_list, p=self.spec.lora_dropout if use else 0.0, seeds=seeds if use else None, seed_dev=seed_t, out=out)
 

@@ -246,6 +246,41 @@ def test_lora_pack(lib):
     assert float(wx[:, :K].abs().max()) == 0.0 and float(wx[:896, K + r:].abs().max()) == 0.0 and float(wd[:, :64].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("rows", [4728, 64, 37, 1000])
+def test_lora_wgrad_grouped(lib, rows):
+    """one launch for the adapters' parameter gradients of a group: out_j (+)= alpha_j P_j^T Q_j with P / Q column slices of wider
+    matrices (dy, t, [dx | dt]), a row count that is no multiple of the 64-row chunk, accumulation into an existing gradient"""
+    r = 32
+    dy = rnd(rows, 896 + 128 + 128, seed=1)            # q | k | v output gradients
+    t = rnd(rows, 3 * r, seed=2, scale=0.3)
+    cat = rnd(rows, 896 + 3 * r + 8, seed=3)[:, :896 + 3 * r]
+    xs = [rnd(rows, 896, seed=4 + j) for j in range(3)]
+    wide = rnd(rows, 4864, seed=9)                     # a 152-tile problem (down_proj lora_A / gate lora_B shapes)
+    outs, probs, refs = [], [], []
+    o = 0
+    for j, w in enumerate((896, 128, 128)):
+        P, Q = dy[:, o:o + w], t[:, r * j:r * (j + 1)]
+        out = rnd(w, r, seed=20 + j)
+        acc = j == 1
+        refs.append(2.0 * P.float().t() @ Q.float() + (out.float() if acc else 0.0))
+        probs.append((P, Q, out, 2.0, acc)); outs.append(out)
+        P, Q = cat[:, 896 + r * j:896 + r * (j + 1)], xs[j]
+        out = rnd(r, 896, seed=30 + j)
+        refs.append(P.float().t() @ Q.float() + (out.float() if j == 2 else 0.0))
+        probs.append((P, Q, out, 1.0, j == 2)); outs.append(out)
+        o += w
+    out = torch.empty(r, 4864, device="cuda", dtype=torch.bfloat16)
+    refs.append(t[:, :r].float().t() @ wide.float())
+    probs.append((t[:, :r], wide, out, 1.0, False)); outs.append(out)
+    out = torch.empty(4864, r, device="cuda", dtype=torch.bfloat16)
+    refs.append(0.5 * wide.float().t() @ t[:, r:2 * r].float())
+    probs.append((wide, t[:, r:2 * r], out, 0.5, False)); outs.append(out)
+    lib.lora_wgrad_grouped(probs, rows)
+    torch.cuda.synchronize()
+    for k, (got, ref) in enumerate(zip(outs, refs)):
+        assert relerr(got, ref) < 1e-2, (k, relerr(got, ref))
+
+
 @pytest.mark.parametrize("M,K,n,p", [(621, 896, 3, 0.1), (300, 4864, 1, 0.1), (130, 896, 2, 0.0), (64, 256, 4, 0.25)])
 def test_lora_dx(lib, M, K, n, p):
     """out = base + sum_j mask_j o (dt_j A_j) / (1 - p): masks taken from slb_dropout with the same seeds"""
