@@ -167,6 +167,11 @@ int slb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 /* ---- LM head tail: argmax over fp32 logits (llm.py:157-158) ---- */
 int slb_argmax_f32(const float* logits, int64_t ld, int rows, int cols, int64_t* out_idx, float* out_margin,
                    void* stream);
+/* the same + the bookkeeping of greedy_sample (llm.py:232-248) in the same launch: nxt[r] = argmax; column c = *pos - base of
+ * sampled [rows, ld_sampled] receives it unless done[r]; n_gen[r] += !done[r]; done[r] |= (argmax == eos) (eos < 0: never); *step = c + 1 */
+int slb_argmax_sample(const float* logits, int64_t ld, int rows, int cols, int64_t* nxt, int64_t* sampled, int64_t ld_sampled,
+                      int max_new, const int32_t* pos, int base, uint8_t* done, int64_t* n_gen, int64_t* step, int64_t eos,
+                      void* stream);
 /* ---- greedy decode loop (llm.py:217-248: embed the last sampled token, all decoder layers against the KV cache, final norm,
  * lm_head, argmax, EOS bookkeeping - per generated token) as ONE persistent kernel: one CTA per SM, grid-wide barriers between the
  * phases of a layer, token loop / position counter / EOS test on the device.  Replaces, per token, the chain

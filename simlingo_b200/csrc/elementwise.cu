@@ -356,8 +356,14 @@ __device__ __forceinline__ Top2 top2_merge(Top2 a, const Top2& b) {
   if (b.v2 > a.v2) a.v2 = b.v2;
   return a;
 }
+// optional bookkeeping of the greedy loop (llm.py:232-248) by the thread that holds the row's result: column `*pos - base` of the
+// row's sampled tokens, generated-token count, finished flag - instead of ~8 dependent element-wise torch kernels per token
+struct SampleState {
+  long long* sampled; long long ld; const int* pos; int base, max_new;
+  unsigned char* done; long long* n_gen; long long* step; long long eos;
+};
 __global__ void __launch_bounds__(1024)
-argmax_kernel(const float* __restrict__ logits, long long ld, int cols, long long* __restrict__ out_idx, float* __restrict__ margin) {
+argmax_kernel(const float* __restrict__ logits, long long ld, int cols, long long* __restrict__ out_idx, float* __restrict__ margin, SampleState st) {
   __shared__ Top2 sh[32];
   const float* r = logits + (size_t)blockIdx.x * ld;
   pdl_trigger();
@@ -410,6 +416,14 @@ argmax_kernel(const float* __restrict__ logits, long long ld, int cols, long lon
     if (threadIdx.x == 0) {
       out_idx[blockIdx.x] = t.i1;
       if (margin) margin[blockIdx.x] = t.v1 - t.v2;
+      if (st.sampled) {
+        const int row = blockIdx.x, col = *st.pos - st.base;
+        const unsigned char d = st.done[row];
+        if (!d && col >= 0 && col < st.max_new) st.sampled[(size_t)row * st.ld + col] = t.i1;   // torch.where(done, cur, nxt)
+        st.n_gen[row] += d ? 0 : 1;
+        if (st.eos >= 0 && (long long)t.i1 == st.eos) st.done[row] = 1;
+        if (row == 0) *st.step = col + 1;
+      }
     }
   }
 }
@@ -668,7 +682,20 @@ extern "C" int slb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* st
 
 extern "C" int slb_argmax_f32(const float* logits, int64_t ld, int rows, int cols, int64_t* out_idx, float* out_margin, void* stream) {
   SLB_CHECK_ARG(rows > 0 && cols > 0, "argmax: rows=%d cols=%d", rows, cols);
-  SLB_CUDA(slb_launch_pdl(true, argmax_kernel, dim3(rows), dim3(1024), 0, ST(stream), logits, (long long)ld, cols, (long long*)out_idx, out_margin));
+  SampleState st = {};
+  SLB_CUDA(slb_launch_pdl(true, argmax_kernel, dim3(rows), dim3(1024), 0, ST(stream), logits, (long long)ld, cols, (long long*)out_idx, out_margin, st));
+  return SLB_OK;
+}
+
+extern "C" int slb_argmax_sample(const float* logits, int64_t ld, int rows, int cols, int64_t* nxt, int64_t* sampled, int64_t ld_sampled,
+                                 int max_new, const int32_t* pos, int base, uint8_t* done, int64_t* n_gen, int64_t* step, int64_t eos,
+                                 void* stream) {
+  SLB_CHECK_ARG(rows > 0 && cols > 0 && max_new > 0, "argmax_sample: rows=%d cols=%d max_new=%d", rows, cols, max_new);
+  SLB_CHECK_ARG(logits && nxt && sampled && pos && done && n_gen && step, "argmax_sample: null state pointer");
+  SampleState st;
+  st.sampled = (long long*)sampled; st.ld = ld_sampled; st.pos = pos; st.base = base; st.max_new = max_new;
+  st.done = done; st.n_gen = (long long*)n_gen; st.step = (long long*)step; st.eos = eos;
+  SLB_CUDA(slb_launch_pdl(true, argmax_kernel, dim3(rows), dim3(1024), 0, ST(stream), logits, (long long)ld, cols, (long long*)nxt, (float*)nullptr, st));
   return SLB_OK;
 }
 

@@ -429,15 +429,9 @@ class Engine:
 
             def sample(last, residual=False):
                 lg = self.logits_from_residual(last) if residual else self.logits(last)
-                lib.argmax(lg, out_idx=rec["nxt"])
+                # argmax + sampled[:, pos - L] / n_gen / done / step in the same launch (was ~8 element-wise torch kernels per token)
+                lib.argmax_sample(lg, rec["nxt"], rec["sampled"], rec["pos"], L, rec["done"], rec["n_gen"], rec["step"], eos_token_id)
                 self.launches += 1
-                idx = rec["step"].view(1, 1).expand(B, 1)
-                cur = rec["sampled"].gather(1, idx)
-                rec["sampled"].scatter_(1, idx, torch.where(rec["done"][:, None], cur, rec["nxt"][:, None]))
-                rec["n_gen"].add_((~rec["done"]).long())
-                if eos_token_id is not None:
-                    rec["done"].logical_or_(rec["nxt"] == eos_token_id)
-                rec["step"].add_(1)
 
             def prefill():
                 rec["pos"].fill_(L)

@@ -388,6 +388,18 @@ def decode_loop(table, n_layers, batch, hidden, mlp, hq, hkv, emb, norm_w, lm_he
     _check(load().slb_decode_loop(C.byref(a), _stream()), "decode_loop")
 
 
+def argmax_sample(logits, nxt, sampled, pos, base, done, n_gen, step, eos):
+    """argmax of every logits row + the bookkeeping of ``greedy_sample`` (llm.py:232-248) in one launch; all state on the device"""
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    rows, cols = logits.shape
+    assert nxt.dtype == torch.int64 and nxt.numel() == rows and sampled.dtype == torch.int64 and sampled.shape[0] == rows and sampled.stride(1) == 1
+    assert pos.dtype == torch.int32 and step.dtype == torch.int64 and n_gen.dtype == torch.int64 and done.dtype in (torch.bool, torch.uint8)
+    _check(load().slb_argmax_sample(_p(logits), C.c_int64(logits.stride(0)), rows, cols, _p(nxt), _p(sampled), C.c_int64(sampled.stride(0)),
+                                    sampled.shape[1], _p(pos), int(base), _p(done), _p(n_gen), _p(step),
+                                    C.c_int64(-1 if eos is None else int(eos)), _stream()), "argmax_sample")
+    return nxt
+
+
 def driving_heads(feats, ld_batch, hw: HeadsWeights, batch, route=None, speed=None, ws=None):
     dev = feats.device
     route = torch.empty((batch, 20, 2), device=dev, dtype=torch.float32) if route is None else route
