@@ -454,3 +454,42 @@ def test_zero_checkpoint_directory_round_trip(tmp_path):
     os.remove(os.path.join(str(tmp_path / "zero_w1"), "latest"))
     with pytest.raises(ValueError, match="latest"):
         load_zero_checkpoint(str(tmp_path / "zero_w1"))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in lib.py / postprocess.py must have the layout the C compiler gives the header's structs: compile a
+    probe against include/simlingo_b200.h with gcc and compare sizeof and every field offset."""
+    import ctypes as C
+    from simlingo_b200 import lib
+    from simlingo_b200.postprocess import ControlParams
+    pairs = [("slb_gemm_args", lib.GemmArgs), ("slb_decode_args", lib.DecodeArgs), ("slb_wgrad_problem", lib.WgradProblem),
+             ("slb_heads_weights", lib.HeadsWeights), ("slb_wp_weights", lib.WpWeights), ("slb_control_params", ControlParams)]
+    header = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "simlingo_b200.h")).read(), flags=re.S)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "simlingo_b200.h"', 'int main(void) {']
+    expect = []
+    for cname, cls in pairs:
+        body = re.search(r"typedef struct\s*\{([^}]*)\}\s*" + cname + r"\s*;", header, re.S)
+        assert body, cname
+        text = body.group(1)
+        cfields = []
+        for decl in text.split(";"):
+            for part in decl.split(","):
+                m = re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip())
+                if m and part.strip():
+                    cfields.append(m.group(1))
+        pyfields = [f[0] for f in cls._fields_]
+        assert len(cfields) == len(pyfields), (cname, cfields, pyfields)
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for cf in cfields:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {cf}));')
+        lines.append('  printf("\\n");')
+        expect.append((cname, [C.sizeof(cls)] + [getattr(cls, f).offset for f in pyfields]))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    got = {ln.split()[0]: [int(v) for v in ln.split()[1:]] for ln in out}
+    for cname, vals in expect:
+        assert got[cname] == vals, (cname, got[cname], vals)
