@@ -731,7 +731,8 @@ def run_agent(args, ctx):
         torch.cuda.synchronize()
         keep[G] = (hb, sp.float().cpu(), rt.float().cpu(), model.sampled_tokens[0].cpu().tolist())
         dev_ms, e2e_ms = [], []
-        l0 = lib.LAUNCHES
+        eng = model._engine()
+        l0 = eng.launches   # kernels of the library launched by the engine, those inside replayed CUDA graphs included
         for _ in range(steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -739,7 +740,7 @@ def run_agent(args, ctx):
             e1.record()
             torch.cuda.synchronize()
             dev_ms.append(e0.elapsed_time(e1))
-        launches = (lib.LAUNCHES - l0) // steps
+        launches = (eng.launches - l0) // steps
         # end to end as the agent sees it (agent_simlingo.py:470-502, 796-797, 878): the cropped uint8 camera frame (359 x 1024)
         # leaves pinned host memory, is resized / tiled / normalised on the GPU (slb_preprocess_frames), goes through
         # DrivingModel.forward, and the predictions are turned into (steer, throttle, brake) by control_pid: geometry on the
@@ -826,9 +827,9 @@ def run_language(args, ctx):
 
     for _ in range(max(1, args.warmup)):
         step(False)
-    l0 = lib.LAUNCHES
+    l0 = eng.launches   # kernels of the library launched by the engine, those inside replayed CUDA graphs included
     ms = ctx.timed_region(lambda: step(False), args.steps)
-    launches = lib.LAUNCHES - l0
+    launches = eng.launches - l0
     ctx.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
